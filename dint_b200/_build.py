@@ -1,0 +1,54 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with the repo snapshot).
+
+  dint_b200/lib/libdint_b200.so   CUDA kernels + C ABI (include/dint_b200.h), nvcc, sm_100a only
+  dint_b200/lib/libdint_wl.so     workload clients (CPU C++: the reference's closed-loop clients restated)
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libdint_b200.so")
+WL_LIB = os.path.join(LIBDIR, "libdint_wl.so")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _sources(exts):
+    out = []
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in sorted(os.listdir(root)):
+            if f.endswith(exts):
+                out.append(os.path.join(root, f))
+    return out
+
+
+def find_nvcc():
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return cand if os.path.exists(cand) else None
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    cu_src = _sources((".cu", ".cuh", ".h"))
+    if force or _newer(LIB, cu_src):
+        nvcc = find_nvcc()
+        if nvcc is None:
+            raise RuntimeError("nvcc not found: cannot build libdint_b200.so (there is no CPU fallback)")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-o", LIB, os.path.join(CSRC, "engine.cu")]
+        subprocess.run(cmd, check=True)
+    wl_src = [os.path.join(CSRC, "workloads.cc")]
+    if os.path.exists(wl_src[0]) and (force or _newer(WL_LIB, wl_src + _sources((".h",)))):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", WL_LIB] + wl_src, check=True)
+    return LIB

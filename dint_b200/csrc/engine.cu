@@ -1,0 +1,557 @@
+// engine.cu -- host side of libdint_b200.so: state allocation in HBM, the per-chunk launch sequence,
+// host<->device pipelining for dint_submit(), state inspection, and the extern "C" ABI of
+// include/dint_b200.h.  No CPU implementation of the request path exists here: without a CUDA
+// device every compute entry point returns DINT_ENODEV.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dint_b200.h"
+#include "kernels.cuh"
+#include "kv.cuh"
+
+using namespace dint;
+
+static thread_local std::string g_last_error;
+static int set_err(int code, const char* what, cudaError_t ce = cudaSuccess) {
+  char buf[512];
+  if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+  else snprintf(buf, sizeof buf, "%s", what);
+  g_last_error = buf;
+  return code;
+}
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) return set_err(_e == cudaErrorMemoryAllocation ? DINT_ENOMEM : DINT_EIO, #call, _e); \
+  } while (0)
+
+static const uint32_t kMsgSize[DINT_NUM_KINDS] = {6, 9, 53, 53, 55, 23};
+static const uint32_t kLogEntry[DINT_NUM_KINDS] = {0, 0, 56, 0, 64, 32};
+static const uint32_t kValSize[DINT_NUM_KINDS] = {0, 0, 0, 40, 40, 8};
+
+enum { KT_CLASSIFY = 0, KT_LOGSCAN, KT_APPLY, KT_ORDERED, KT_LOAD, KT_NUM };
+static const char* kKernelNames[KT_NUM] = {"k_classify", "k_log_scan", "k_apply", "k_ordered", "k_kv_load"};
+
+struct EvPair { cudaEvent_t a, b; int which; };
+
+struct dint_engine {
+  int kind = 0;
+  int device = 0;
+  dint_cfg cfg{};
+  uint32_t msg = 0;
+  uint32_t chunk = 0;
+  uint32_t max_tiles = 0;
+  bool has_log = false;
+  Ctx ctx{};                       // device pointers + constants; per-launch fields filled per chunk
+  std::vector<void*> allocs;       // everything to cudaFree
+  cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+  uint8_t* d_req[2] = {nullptr, nullptr};
+  uint8_t* d_resp[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2]{}, ev_comp[2]{}, ev_out[2]{};
+  int coop_grid = 0;
+  uint64_t total_groups = 0;
+  // stats
+  dint_stats stats{};
+  unsigned long long counters_seen[4] = {0, 0, 0, 0};
+  // profiling
+  bool profiling = false;
+  std::vector<EvPair> ev_pool;
+  size_t ev_used = 0;
+  double kt_ms[KT_NUM] = {0};
+  uint64_t kt_n[KT_NUM] = {0};
+  // KV host mirrors
+  KvHost kv[kMaxTables];
+};
+
+template <typename T>
+static int dalloc(dint_engine* e, T** p, size_t count, bool zero = true) {
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  void* q = nullptr;
+  CU(cudaMalloc(&q, bytes));
+  e->allocs.push_back(q);
+  if (zero) CU(cudaMemsetAsync(q, 0, bytes, e->stream));
+  *p = (T*)q;
+  return DINT_OK;
+}
+
+// ---- profiling helpers ------------------------------------------------------------------------------
+static int prof_flush(dint_engine* e) {
+  for (size_t i = 0; i < e->ev_used; i++) {
+    float ms = 0;
+    CU(cudaEventSynchronize(e->ev_pool[i].b));
+    CU(cudaEventElapsedTime(&ms, e->ev_pool[i].a, e->ev_pool[i].b));
+    e->kt_ms[e->ev_pool[i].which] += ms;
+    e->kt_n[e->ev_pool[i].which]++;
+  }
+  e->ev_used = 0;
+  return DINT_OK;
+}
+struct ProfScope {
+  dint_engine* e; cudaStream_t s; EvPair* p = nullptr;
+  ProfScope(dint_engine* e_, cudaStream_t s_, int which) : e(e_), s(s_) {
+    e->stats.kernel_launches++;
+    if (!e->profiling) return;
+    if (e->ev_used == e->ev_pool.size()) {
+      if (e->ev_pool.size() >= 8192) { prof_flush(e); }
+      else {
+        EvPair np{}; cudaEventCreate(&np.a); cudaEventCreate(&np.b);
+        e->ev_pool.push_back(np);
+      }
+    }
+    p = &e->ev_pool[e->ev_used++];
+    p->which = which;
+    cudaEventRecord(p->a, s);
+  }
+  ~ProfScope() { if (p) cudaEventRecord(p->b, s); }
+};
+
+// ---- per-chunk launch sequence ------------------------------------------------------------------------
+template <int KIND, bool HAS_LOG>
+static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
+  {
+    ProfScope ps(e, s, KT_CLASSIFY);
+    k_classify<KIND, HAS_LOG><<<c.n_tiles, kThreads, 0, s>>>(c);
+  }
+  if (HAS_LOG) {
+    ProfScope ps(e, s, KT_LOGSCAN);
+    k_log_scan<<<1, kThreads, 0, s>>>(c);
+  }
+  {
+    ProfScope ps(e, s, KT_APPLY);
+    k_apply<KIND, HAS_LOG><<<c.n_tiles, kThreads, 0, s>>>(c);
+  }
+  if (KIND != K_LOG) {   // the log server has no per-key state: nothing to order, nothing to clear
+    ProfScope ps(e, s, KT_ORDERED);
+    void* args[] = {(void*)&c};
+    CU(cudaLaunchCooperativeKernel((void*)k_ordered<KIND>, dim3(e->coop_grid), dim3(kThreads), args, 0, s));
+  }
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+static int launch_chunk(dint_engine* e, const Ctx& c, cudaStream_t s) {
+  switch (e->kind) {
+    case DINT_LOCK2PL: return launch_chunk_t<K_LOCK2PL, false>(e, c, s);
+    case DINT_FASST: return launch_chunk_t<K_FASST, false>(e, c, s);
+    case DINT_LOG: return launch_chunk_t<K_LOG, true>(e, c, s);
+    case DINT_STORE: return launch_chunk_t<K_STORE, false>(e, c, s);
+    case DINT_TATP: return launch_chunk_t<K_TATP, true>(e, c, s);
+    case DINT_SMALLBANK: return launch_chunk_t<K_SMALLBANK, true>(e, c, s);
+  }
+  return DINT_EINVAL;
+}
+
+template <int KIND>
+static int coop_grid_for(int device, int* out) {
+  int per_sm = 0, sms = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ordered<KIND>, kThreads, 0));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (per_sm < 1) return set_err(DINT_EIO, "k_ordered cannot be resident");
+  if (per_sm > 4) per_sm = 4;
+  *out = per_sm * sms;
+  return DINT_OK;
+}
+
+static int run_device(dint_engine* e, const uint8_t* req, uint64_t n, uint8_t* resp, cudaStream_t s) {
+  for (uint64_t off = 0; off < n; off += e->chunk) {
+    Ctx c = e->ctx;
+    c.n = (uint32_t)((n - off < e->chunk) ? (n - off) : e->chunk);
+    c.n_tiles = (c.n + kTile - 1) / kTile;
+    c.req = req + off * e->msg;
+    c.resp = resp + off * e->msg;
+    int rc = launch_chunk(e, c, s);
+    if (rc) return rc;
+    e->stats.chunks++;
+  }
+  e->stats.requests += n;
+  return DINT_OK;
+}
+
+static int pull_counters(dint_engine* e) {
+  unsigned long long h[4];
+  CU(cudaMemcpy(h, e->ctx.counters, sizeof h, cudaMemcpyDeviceToHost));
+  e->stats.errors = h[0];
+  e->stats.conflicted = h[1];
+  e->stats.max_run = h[2];
+  return DINT_OK;
+}
+
+// ======================================================================================================
+extern "C" {
+
+uint32_t dint_msg_size(int kind) { return (kind >= 0 && kind < DINT_NUM_KINDS) ? kMsgSize[kind] : 0; }
+uint32_t dint_log_entry_size(int kind) { return (kind >= 0 && kind < DINT_NUM_KINDS) ? kLogEntry[kind] : 0; }
+const char* dint_last_error(void) { return g_last_error.c_str(); }
+uint64_t dint_test_fasthash64(uint64_t x, int len) { return len == 4 ? fasthash64_u32((uint32_t)x) : fasthash64_u64(x); }
+uint32_t dint_test_fastmod(uint64_t n, uint32_t d) { FastMod f = make_fastmod(d); return fast_mod(n, f); }
+
+void dint_default_cfg(int kind, dint_cfg* cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->lock_slots = 36000000u;
+  cfg->log_ring = 1000000u;
+  cfg->subs_sizing = (kind == DINT_TATP) ? 7000000u : 2000000u;
+  cfg->subs_populate = cfg->subs_sizing;
+  cfg->accts_sizing = 24000000u;
+  cfg->accts_populate = cfg->accts_sizing;
+  cfg->n_shards = 1;
+  cfg->shard_id = 0;
+  cfg->chunk = 1u << 20;
+}
+
+void* dint_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void dint_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void dint_destroy(dint_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocs) cudaFree(p);
+  for (auto& ep : e->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  for (int i = 0; i < 2; i++) {
+    if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+    if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+    if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+  }
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
+  delete e;
+}
+
+static int create_impl(dint_engine* e) {
+  const dint_cfg& cf = e->cfg;
+  Ctx& c = e->ctx;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CU(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+  }
+  c.n_shards = cf.n_shards;
+  c.shard_id = cf.shard_id;
+  c.shard_div = make_fastmod(cf.n_shards);
+  c.slot_mod = make_fastmod(cf.lock_slots);
+  c.ring_n = cf.log_ring ? cf.log_ring : 1;
+
+  // ---- per-kind state in HBM ----
+  uint64_t groups = 0;
+  auto local_groups = [&](uint64_t global) { return (global + cf.n_shards - 1) / cf.n_shards; };
+  int rc;
+  switch (e->kind) {
+    case DINT_LOCK2PL:
+      groups = local_groups(cf.lock_slots);
+      if ((rc = dalloc(e, &c.cnt2, groups))) return rc;
+      break;
+    case DINT_FASST:
+      groups = local_groups(cf.lock_slots);
+      if ((rc = dalloc(e, &c.lockbits, (groups + 31) / 32))) return rc;
+      if ((rc = dalloc(e, &c.ver, groups))) return rc;
+      break;
+    case DINT_LOG:
+      groups = 0;
+      break;
+    default:
+      if ((rc = kv_create_tables(e->kind, cf, c, e->kv, &groups,
+                                 [&](void** p, size_t bytes) -> int {
+                                   uint8_t* q = nullptr;
+                                   int r = dalloc(e, &q, bytes);
+                                   *p = q;
+                                   return r;
+                                 })))
+        return rc == DINT_EINVAL ? set_err(rc, "bad KV configuration") : rc;
+      break;
+  }
+  e->total_groups = groups;
+  if (groups >= 0xffffffffULL) return set_err(DINT_EINVAL, "too many groups");
+  c.bm_words = (uint32_t)((groups + 31) / 32);
+  if ((rc = dalloc(e, &c.bm, (size_t)5 * (c.bm_words ? c.bm_words : 1)))) return rc;
+  uint32_t bits = 1;
+  while ((1ULL << bits) < groups) bits++;
+  c.sort_passes = (bits + 7) / 8;
+
+  if (e->has_log) {
+    if ((rc = dalloc(e, &c.ring, (size_t)c.ring_n * kLogEntry[e->kind]))) return rc;
+  }
+  // ---- chunk scratch ----
+  const uint32_t ch = e->chunk;
+  e->max_tiles = (ch + kTile - 1) / kTile;
+  if ((rc = dalloc(e, &c.grp, ch))) return rc;
+  if ((rc = dalloc(e, &c.clist, (size_t)e->max_tiles * kTile))) return rc;
+  if ((rc = dalloc(e, &c.ccnt, e->max_tiles))) return rc;
+  if ((rc = dalloc(e, &c.cprefix, e->max_tiles + 1))) return rc;
+  if ((rc = dalloc(e, &c.sortA, ch))) return rc;
+  if ((rc = dalloc(e, &c.sortB, ch))) return rc;
+  if ((rc = dalloc(e, &c.ghist, (size_t)256 * ((ch + kSortTile - 1) / kSortTile)))) return rc;
+  if ((rc = dalloc(e, &c.rowtot, 256))) return rc;
+  if ((rc = dalloc(e, &c.log_tilecnt, e->max_tiles))) return rc;
+  if ((rc = dalloc(e, &c.log_tilebase, e->max_tiles))) return rc;
+  if ((rc = dalloc(e, &c.log_total, 2))) return rc;
+  if ((rc = dalloc(e, &c.counters, 4))) return rc;
+
+  switch (e->kind) {
+    case DINT_LOCK2PL: rc = coop_grid_for<K_LOCK2PL>(e->device, &e->coop_grid); break;
+    case DINT_FASST: rc = coop_grid_for<K_FASST>(e->device, &e->coop_grid); break;
+    case DINT_LOG: rc = DINT_OK; e->coop_grid = 1; break;
+    case DINT_STORE: rc = coop_grid_for<K_STORE>(e->device, &e->coop_grid); break;
+    case DINT_TATP: rc = coop_grid_for<K_TATP>(e->device, &e->coop_grid); break;
+    default: rc = coop_grid_for<K_SMALLBANK>(e->device, &e->coop_grid); break;
+  }
+  if (rc) return rc;
+  int coop = 0;
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+  if (!coop) return set_err(DINT_ENODEV, "device lacks cooperative launch");
+  CU(cudaStreamSynchronize(e->stream));
+  return DINT_OK;
+}
+
+int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
+  if (!out || kind < 0 || kind >= DINT_NUM_KINDS) return set_err(DINT_EINVAL, "bad kind/out");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(DINT_ENODEV, "no CUDA device: dint_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return set_err(DINT_EINVAL, "bad device ordinal");
+  dint_engine* e = new dint_engine();
+  e->kind = kind;
+  e->device = device;
+  if (cfg) e->cfg = *cfg; else dint_default_cfg(kind, &e->cfg);
+  dint_cfg& cf = e->cfg;
+  if (cf.n_shards == 0) cf.n_shards = 1;
+  if (cf.shard_id >= cf.n_shards || cf.lock_slots == 0) { delete e; return set_err(DINT_EINVAL, "bad shard/lock_slots"); }
+  if (cf.chunk == 0) cf.chunk = 1u << 20;
+  e->chunk = (cf.chunk + kTile - 1) / kTile * kTile;
+  e->msg = kMsgSize[kind];
+  e->has_log = kLogEntry[kind] != 0;
+  int rc = create_impl(e);
+  if (rc) { dint_destroy(e); return rc; }
+  *out = e;
+  return DINT_OK;
+}
+
+int dint_sync(dint_engine* e) {
+  if (!e) return DINT_EINVAL;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  int rc = prof_flush(e);
+  if (rc) return rc;
+  unsigned long long before = e->stats.errors;
+  if ((rc = pull_counters(e))) return rc;
+  return e->stats.errors != before ? DINT_EPROTO : DINT_OK;
+}
+
+int dint_submit_device(dint_engine* e, const void* req_dev, uint64_t n, void* resp_dev, void* cuda_stream) {
+  if (!e || (n && (!req_dev || !resp_dev))) return set_err(DINT_EINVAL, "null argument");
+  if (((uintptr_t)req_dev | (uintptr_t)resp_dev) & 15) return set_err(DINT_EINVAL, "device buffers must be 16-byte aligned");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  return run_device(e, (const uint8_t*)req_dev, n, (uint8_t*)resp_dev, s);
+}
+
+int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
+  if (!e || (n && (!req || !resp))) return set_err(DINT_EINVAL, "null argument");
+  CU(cudaSetDevice(e->device));
+  if (!e->d_req[0]) {
+    for (int i = 0; i < 2; i++) {
+      int rc;
+      if ((rc = dalloc(e, &e->d_req[i], (size_t)e->chunk * e->msg + 16, false))) return rc;
+      if ((rc = dalloc(e, &e->d_resp[i], (size_t)e->chunk * e->msg + 16, false))) return rc;
+    }
+  }
+  const uint8_t* rq = (const uint8_t*)req;
+  uint8_t* rs = (uint8_t*)resp;
+  unsigned long long err_before = e->stats.errors;
+  // three-stage pipeline over chunks: H2D (s_in) | kernels (stream) | D2H (s_out), double buffered
+  uint64_t k = 0;
+  for (uint64_t off = 0; off < n; off += e->chunk, k++) {
+    int b = (int)(k & 1);
+    uint64_t cn = (n - off < e->chunk) ? (n - off) : e->chunk;
+    size_t bytes = (size_t)cn * e->msg;
+    if (k >= 2) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));     // kernels of chunk k-2 done with d_req[b]
+    CU(cudaMemcpyAsync(e->d_req[b], rq + off * e->msg, bytes, cudaMemcpyHostToDevice, e->s_in));
+    CU(cudaEventRecord(e->ev_in[b], e->s_in));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+    if (k >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0));    // D2H of chunk k-2 done with d_resp[b]
+    int rc = run_device(e, e->d_req[b], cn, e->d_resp[b], e->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev_comp[b], e->stream));
+    CU(cudaStreamWaitEvent(e->s_out, e->ev_comp[b], 0));
+    CU(cudaMemcpyAsync(rs + off * e->msg, e->d_resp[b], bytes, cudaMemcpyDeviceToHost, e->s_out));
+    CU(cudaEventRecord(e->ev_out[b], e->s_out));
+    e->stats.h2d_bytes += bytes;
+    e->stats.d2h_bytes += bytes;
+  }
+  CU(cudaStreamSynchronize(e->s_out));
+  CU(cudaStreamSynchronize(e->stream));
+  int rc = prof_flush(e);
+  if (rc) return rc;
+  if ((rc = pull_counters(e))) return rc;
+  return e->stats.errors != err_before ? DINT_EPROTO : DINT_OK;
+}
+
+int dint_lock_state(dint_engine* e, int table, uint32_t slot, uint32_t out[2]) {
+  if (!e || !out) return DINT_EINVAL;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  out[0] = out[1] = 0;
+  const Ctx& c = e->ctx;
+  uint32_t g = slot;
+  if (e->kind == DINT_TATP || e->kind == DINT_SMALLBANK) {
+    if (table < 0 || table >= (int)c.n_tables) return DINT_EINVAL;
+    if (slot % c.n_shards != c.shard_id) return DINT_EINVAL;
+    g = c.tbl[table].grp_base + slot / c.n_shards;
+  } else if (e->kind == DINT_LOCK2PL || e->kind == DINT_FASST) {
+    if (slot % c.n_shards != c.shard_id) return DINT_EINVAL;
+    g = slot / c.n_shards;
+  } else return DINT_EINVAL;
+  if (g >= e->total_groups) return DINT_EINVAL;
+  if (e->kind == DINT_LOCK2PL || e->kind == DINT_SMALLBANK) {
+    uint2 v;
+    CU(cudaMemcpy(&v, c.cnt2 + g, sizeof v, cudaMemcpyDeviceToHost));
+    out[0] = v.x; out[1] = v.y;
+  } else {
+    uint32_t w;
+    CU(cudaMemcpy(&w, c.lockbits + (g >> 5), 4, cudaMemcpyDeviceToHost));
+    out[0] = (w >> (g & 31)) & 1u;
+    if (e->kind == DINT_FASST) CU(cudaMemcpy(&out[1], c.ver + g, 4, cudaMemcpyDeviceToHost));
+  }
+  return DINT_OK;
+}
+
+uint32_t dint_lock_slot(dint_engine* e, int table, uint64_t k) {
+  if (!e) return 0;
+  const Ctx& c = e->ctx;
+  if (e->kind == DINT_LOCK2PL || e->kind == DINT_FASST) return fast_mod(fasthash64_u32((uint32_t)k), c.slot_mod);
+  if ((e->kind == DINT_TATP || e->kind == DINT_SMALLBANK) && table >= 0 && table < (int)c.n_tables)
+    return fast_mod(fasthash64_u64(k), c.tbl[table].lock_mod);
+  return 0;
+}
+
+int dint_dump_log(dint_engine* e, void* out, uint64_t* appended) {
+  if (!e || !e->has_log) return DINT_EINVAL;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (out) CU(cudaMemcpy(out, e->ctx.ring, (size_t)e->ctx.ring_n * kLogEntry[e->kind], cudaMemcpyDeviceToHost));
+  if (appended) {
+    unsigned long long t[2];
+    CU(cudaMemcpy(t, e->ctx.log_total, sizeof t, cudaMemcpyDeviceToHost));
+    *appended = t[0];
+  }
+  return DINT_OK;
+}
+
+int dint_get_stats(dint_engine* e, dint_stats* s) {
+  if (!e || !s) return DINT_EINVAL;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  int rc = pull_counters(e);
+  if (rc) return rc;
+  *s = e->stats;
+  return DINT_OK;
+}
+void dint_reset_stats(dint_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaMemset(e->ctx.counters, 0, 4 * sizeof(unsigned long long));
+  e->stats = dint_stats{};
+  for (int i = 0; i < KT_NUM; i++) { e->kt_ms[i] = 0; e->kt_n[i] = 0; }
+}
+int dint_profile(dint_engine* e, int enable) {
+  if (!e) return DINT_EINVAL;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  int rc = prof_flush(e);
+  e->profiling = enable != 0;
+  return rc;
+}
+int dint_kernel_times(dint_engine* e, dint_kernel_time* out, int max_entries) {
+  if (!e || !out) return DINT_EINVAL;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  prof_flush(e);
+  int k = 0;
+  for (int i = 0; i < KT_NUM && k < max_entries; i++) {
+    if (!e->kt_n[i]) continue;
+    memset(&out[k], 0, sizeof out[k]);
+    snprintf(out[k].name, sizeof out[k].name, "%s", kKernelNames[i]);
+    out[k].launches = e->kt_n[i];
+    out[k].total_ms = e->kt_ms[i];
+    k++;
+  }
+  return k;
+}
+
+// ---- KV entry points (store / tatp / smallbank) -------------------------------------------------------
+int dint_load(dint_engine* e, int table, const uint64_t* keys, const void* vals, uint64_t n) {
+  if (!e || table < 0 || table >= (int)e->ctx.n_tables || (n && (!keys || !vals))) return set_err(DINT_EINVAL, "bad table/arguments");
+  CU(cudaSetDevice(e->device));
+  const uint32_t vs = kValSize[e->kind];
+  const uint64_t batch = 1u << 20;
+  uint64_t* dk = nullptr;
+  uint8_t* dv = nullptr;
+  CU(cudaMalloc(&dk, batch * 8));
+  cudaError_t ce = cudaMalloc(&dv, batch * vs);
+  if (ce != cudaSuccess) { cudaFree(dk); return set_err(DINT_ENOMEM, "cudaMalloc", ce); }
+  int rc = DINT_OK;
+  for (uint64_t off = 0; off < n && rc == DINT_OK; off += batch) {
+    uint64_t m = (n - off < batch) ? (n - off) : batch;
+    if (cudaMemcpyAsync(dk, keys + off, m * 8, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+        cudaMemcpyAsync(dv, (const uint8_t*)vals + off * vs, m * vs, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+      rc = set_err(DINT_EIO, "load copy", cudaGetLastError());
+      break;
+    }
+    {
+      ProfScope ps(e, e->stream, KT_LOAD);
+      kv_launch_load(e->kind, e->ctx, table, dk, dv, (uint32_t)m, e->stream);
+    }
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = set_err(DINT_EIO, "k_kv_load", cudaGetLastError());
+  }
+  cudaFree(dk);
+  cudaFree(dv);
+  if (rc == DINT_OK) {
+    int r2 = pull_counters(e);
+    if (r2) return r2;
+    if (e->stats.errors) return set_err(DINT_ENOMEM, "KV table full during load");
+  }
+  return rc;
+}
+
+int dint_populate(dint_engine* e) {
+  if (!e) return DINT_EINVAL;
+  if (e->ctx.n_tables == 0) return DINT_OK;       // lock / log servers start from zeroed arrays
+  return kv_populate(e->kind, e->cfg, [&](int table, const uint64_t* k, const void* v, uint64_t n) {
+    return dint_load(e, table, k, v, n);
+  });
+}
+
+int dint_kv_get(dint_engine* e, int table, uint64_t key, void* val, uint32_t* ver) {
+  if (!e || table < 0 || table >= (int)e->ctx.n_tables) return DINT_EINVAL;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  return kv_host_get(e->ctx, table, key, kValSize[e->kind], val, ver);
+}
+
+int64_t dint_kv_count(dint_engine* e, int table) {
+  if (!e || table < 0 || table >= (int)e->ctx.n_tables) return DINT_EINVAL;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, e->ctx.tbl[table].live, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return DINT_EIO;
+  return (int64_t)v;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// engine.cuh -- device-side context, wire layouts and per-kind request semantics.
+//
+// Batch semantics.  dint_submit() must answer exactly as ONE reference server thread would have,
+// taking the requests one by one in index order.  Two requests interact only if they touch the same
+// "group" (a lock slot; for the KV kinds the lock slot of the key, which also pins the key), so a
+// chunk of requests is processed in three launches:
+//
+//   K1 classify : stage the tile of wire records (TMA bulk copy), hash every key to its group id,
+//                 record the id, and mark per-group bitmaps.  A group has two resources: A (the
+//                 versioned data: ver_table entry / KV rows) and L (the lock word / counters).  A
+//                 request is a reader of A (RA), a writer of A (WA) and/or a writer of L (WL); the
+//                 bitmaps are R (an RA exists), WA, WWA (>= 2 WA), WL, WWL (>= 2 WL).  They are
+//                 exact (one bit per group) and small enough to live in the 126 MB L2 (36 M slots
+//                 -> 4.5 MB each).
+//   K2 apply    : a request is SOLO when nothing else in the chunk can interact with it
+//                 (RA: WA clear; WA: R and WWA clear; WL: WWL clear).  Solo requests are applied
+//                 directly, one thread each, against the HBM-resident state and their tile is
+//                 written back with one bulk store.  The others are listed, in index order, for K3.
+//   K3 ordered  : one cooperative launch: stable radix sort of the listed (group, index) pairs by
+//                 group, then every same-group run is replayed in index order by one thread using
+//                 the very same per-request function as K2; finally the bitmaps are cleared.
+//
+// apply_one<KIND>() below is therefore the single statement of each server's request semantics.
+#pragma once
+#include "common.cuh"
+
+namespace dint {
+
+enum Kind { K_LOCK2PL = 0, K_FASST = 1, K_LOG = 2, K_STORE = 3, K_TATP = 4, K_SMALLBANK = 5 };
+
+constexpr int kTile = 256;       // wire records per CTA in K1/K2
+constexpr int kThreads = 256;
+constexpr int kMaxTables = 5;
+constexpr uint32_t kSmallSort = 2048;   // K3: up to this many listed requests are sorted in shared memory
+
+// what a request touches inside its group (conflict detection)
+enum : uint32_t { C_RA = 1, C_WA = 2, C_WL = 4 };
+
+// ---- wire layouts (packed structs of the reference) ----------------------------------------------
+template <int KIND> struct Wire;
+template <> struct Wire<K_LOCK2PL> {   // lock_2pl/udp/net.h:25-31 {u8 action; u32 lid; u8 type}
+  static constexpr int MSG = 6, TYPE = 0, KEY = 1, LTYPE = 5;
+};
+template <> struct Wire<K_FASST> {     // lock_fasst/udp/net.h:25-31 {u8 type; u32 lid; u32 ver}
+  static constexpr int MSG = 9, TYPE = 0, KEY = 1, VER = 5;
+};
+template <> struct Wire<K_LOG> {       // log_server/udp/net.h:23-30 {u8 type; u64 key; u8 val[40]; u32 ver}
+  static constexpr int MSG = 53, TYPE = 0, KEY = 1, VAL = 9, VER = 49, VALSZ = 40, LOGENT = 56;
+};
+template <> struct Wire<K_STORE> {     // store/udp/net.h:34-41 (same shape)
+  static constexpr int MSG = 53, TYPE = 0, KEY = 1, VAL = 9, VER = 49, VALSZ = 40;
+};
+template <> struct Wire<K_TATP> {      // tatp/udp/net.h:57-65 {u8 ord; u8 type; u8 table; u64 key; u8 val[40]; u32 ver}
+  static constexpr int MSG = 55, TYPE = 1, TABLE = 2, KEY = 3, VAL = 11, VER = 51, VALSZ = 40, LOGENT = 64;
+};
+template <> struct Wire<K_SMALLBANK> { // smallbank/udp/net.h:43-52 {u8 ord; u8 type; u8 table; u64 key; u8 val[8]; u32 ver}
+  static constexpr int MSG = 23, TYPE = 1, TABLE = 2, KEY = 3, VAL = 11, VER = 19, VALSZ = 8, LOGENT = 32;
+};
+
+// ---- KV table: open addressing, one 64-byte (val 40) or 32-byte (val 8) entry per key -------------
+// entry = { u64 key; u32 ver; u32 meta; u8 val[VALSZ]; pad } -- a GET that hits on its first probe
+// costs exactly one aligned 64-byte (32-byte) HBM access.
+enum : uint32_t { ENT_EMPTY = 0, ENT_FULL = 1, ENT_TOMB = 2, ENT_BUSY = 3 };
+struct KvTable {
+  uint8_t* entries;
+  uint64_t cap_mask;       // capacity - 1 (power of two)
+  uint32_t cap_log2;
+  uint32_t ent_shift;      // log2(entry bytes): 6 or 5
+  FastMod lock_mod;        // kKeysPerEntry * hash_size of the reference (tatp.h:12-14, smallbank.h:12-14)
+  uint32_t grp_base;       // first group id of this table
+  uint32_t n_groups;       // local groups of this table
+  unsigned long long* live;  // live-key counter
+};
+
+struct Ctx {
+  // chunk
+  const uint8_t* req;      // n wire records, 16-byte aligned
+  uint8_t* resp;           // n wire records, 16-byte aligned (may equal req)
+  uint32_t n;
+  uint32_t n_tiles;
+  // conflict detection
+  uint32_t* grp;           // [chunk] group id per request (0xffffffff: none)
+  uint32_t* bm;            // 5 bitmaps of bm_words words each: R, WA, WWA, WL, WWL
+  uint32_t bm_words;
+  uint32_t* clist;         // [n_tiles][kTile] indices of listed requests, tile-segmented
+  uint32_t* ccnt;          // [n_tiles] listed requests per tile
+  uint32_t* cprefix;       // [n_tiles+1] exclusive prefix of ccnt (K3)
+  uint64_t* sortA;         // [chunk] (group << 32 | index)
+  uint64_t* sortB;
+  uint32_t* ghist;         // [256][sort tiles]
+  uint32_t* rowtot;        // [256]
+  uint32_t sort_passes;    // 8-bit digits covering the group-id bits
+  // sharding of the group space
+  FastMod shard_div;       // n_shards
+  uint32_t n_shards, shard_id;
+  // lock tables (lock_2pl / lock_fasst)
+  FastMod slot_mod;        // kLockHashSize
+  uint32_t* lockbits;      // fasst / tatp: 1 bit per group
+  uint32_t* ver;           // fasst: u32 per slot
+  uint2* cnt2;             // lock_2pl / smallbank: {num_ex, num_sh} per group
+  // KV
+  KvTable tbl[kMaxTables];
+  uint32_t n_tables;
+  // log
+  uint8_t* ring;
+  uint32_t ring_n;
+  uint32_t* log_tilecnt;   // [n_tiles] log appends per tile (K1)
+  unsigned long long* log_tilebase;  // [n_tiles] absolute append ordinal of the tile's first append (K1b)
+  unsigned long long* log_total;     // [2]: [0] appends before this chunk ... running total, [1] this chunk's total
+  // bookkeeping
+  unsigned long long* counters;   // [0] errors [1] conflicted [2] max_run
+};
+
+// ---- bitmap helpers -------------------------------------------------------------------------------
+DINT_D bool bm_test(const uint32_t* bm, uint32_t g) { return (bm[g >> 5] >> (g & 31)) & 1u; }
+DINT_D void bm_set(uint32_t* bm, uint32_t g) { atomicOr(&bm[g >> 5], 1u << (g & 31)); }
+DINT_D uint32_t bm_fetch_set(uint32_t* bm, uint32_t g) {
+  uint32_t bit = 1u << (g & 31);
+  return atomicOr(&bm[g >> 5], bit) & bit;
+}
+DINT_D void bm_clear_bit(uint32_t* bm, uint32_t g) { atomicAnd(&bm[g >> 5], ~(1u << (g & 31))); }
+
+// global group id -> local group id of this shard (owner = global % n_shards)
+DINT_D bool to_local_group(const Ctx& c, uint32_t gglobal, uint32_t& glocal) {
+  if (c.n_shards == 1) { glocal = gglobal; return true; }
+  uint32_t q = (uint32_t)fast_div(gglobal, c.shard_div);
+  glocal = q;
+  return gglobal - q * c.n_shards == c.shard_id;
+}
+
+// ---- decode: what a wire record touches (type_info, cheap) and which group (group_of, hashes) ------
+struct TypeInfo {
+  uint32_t mask;    // C_RA | C_WA | C_WL
+  bool invalid;     // the reference would panic() on this record
+  bool is_log;      // appends to the commit log
+};
+constexpr uint32_t kNoGroup = 0xffffffffu;
+
+template <int KIND> DINT_D TypeInfo type_info(const uint8_t* rec);
+// returns false when the record's group is not owned by this shard (or names a bad table)
+template <int KIND> DINT_D bool group_of(const Ctx& c, const uint8_t* rec, uint32_t& grp);
+
+template <> DINT_D TypeInfo type_info<K_LOCK2PL>(const uint8_t* rec) {
+  using W = Wire<K_LOCK2PL>;
+  uint8_t action = rec[W::TYPE], lt = rec[W::LTYPE];
+  // lock_2pl/udp/server.cc:82,109,112,121: acquire needs a valid lock type, release accepts any
+  if (action > 1 || (action == 0 && lt > 1)) return TypeInfo{0, true, false};
+  return TypeInfo{C_WL, false, false};   // every lock_2pl request reads or changes the slot's counters
+}
+template <> DINT_D bool group_of<K_LOCK2PL>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
+  uint32_t g = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + Wire<K_LOCK2PL>::KEY)), c.slot_mod);  // :71-72
+  return to_local_group(c, g, grp);
+}
+
+template <> DINT_D TypeInfo type_info<K_FASST>(const uint8_t* rec) {
+  uint8_t t = rec[Wire<K_FASST>::TYPE];
+  if (t > 3) return TypeInfo{0, true, false};               // lock_fasst/udp/server.cc:116-117
+  // kRead reads ver_table; kAcquireLock / kAbort CAS the lock word; kCommit does ver++ and the CAS
+  return TypeInfo{(t == 0) ? C_RA : (t == 3) ? (C_WA | C_WL) : C_WL, false, false};
+}
+template <> DINT_D bool group_of<K_FASST>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
+  uint32_t g = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + Wire<K_FASST>::KEY)), c.slot_mod);    // :81-82
+  return to_local_group(c, g, grp);
+}
+
+template <> DINT_D TypeInfo type_info<K_LOG>(const uint8_t* rec) {
+  if (rec[Wire<K_LOG>::TYPE] != 0) return TypeInfo{0, true, false};   // log_server/udp/server.cc:76-77
+  return TypeInfo{0, false, true};
+}
+template <> DINT_D bool group_of<K_LOG>(const Ctx&, const uint8_t*, uint32_t& grp) {
+  grp = kNoGroup;
+  return true;
+}
+
+// ---- apply_one: the request semantics, in place on the wire record --------------------------------
+// `rec` holds the request and becomes the reply (the reference mutates the received buffer and sends
+// it back: lock_fasst/udp/server.cc:87-89).  Caller guarantees exclusive access to the group.
+// log_ord: absolute append ordinal for log requests (ring index = ord % ring_n), log_keep: false when
+// a later append of the same chunk lands on the same ring entry.
+template <int KIND>
+DINT_D void apply_one(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long log_ord, bool log_keep);
+
+template <>
+DINT_D void apply_one<K_LOCK2PL>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long, bool) {
+  using W = Wire<K_LOCK2PL>;
+  uint8_t action = rec[W::TYPE], lt = rec[W::LTYPE];
+  uint2 s = c.cnt2[g];                     // x = num_ex, y = num_sh
+  if (action == 0) {                       // kAcquireLock, lock_2pl/udp/server.cc:82-110
+    if (lt == 0) {                         // kShared :83-93
+      if (s.x == 0) { s.y++; c.cnt2[g] = s; rec[W::TYPE] = 2; } else rec[W::TYPE] = 3;
+    } else {                               // kExclusive :96-107
+      if (s.x == 0 && s.y == 0) { s.x++; c.cnt2[g] = s; rec[W::TYPE] = 2; } else rec[W::TYPE] = 3;
+    }
+  } else {                                 // kReleaseLock :112-119 (u32 wrap-around preserved)
+    if (lt == 0) { s.y--; c.cnt2[g] = s; }
+    else if (lt == 1) { s.x--; c.cnt2[g] = s; }
+    rec[W::TYPE] = 5;                      // kReleaseAck
+  }
+}
+
+template <>
+DINT_D void apply_one<K_FASST>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long, bool) {
+  using W = Wire<K_FASST>;
+  uint8_t t = rec[W::TYPE];
+  if (t == 0) {                            // kRead, lock_fasst/udp/server.cc:86-90
+    st_u32_unaligned(rec + W::VER, c.ver[g]);
+    rec[W::TYPE] = 4;
+  } else if (t == 1) {                     // kAcquireLock :92-101  CAS(0 -> 1)
+    rec[W::TYPE] = bm_fetch_set(c.lockbits, g) ? 6 : 5;
+  } else if (t == 2) {                     // kAbort :103-107       CAS(1 -> 0)
+    bm_clear_bit(c.lockbits, g);
+    rec[W::TYPE] = 7;
+  } else {                                 // kCommit :109-114      ver++, CAS(1 -> 0)
+    c.ver[g] = c.ver[g] + 1;
+    bm_clear_bit(c.lockbits, g);
+    rec[W::TYPE] = 8;
+  }
+}
+
+template <>
+DINT_D void apply_one<K_LOG>(const Ctx& c, uint8_t* rec, uint32_t, unsigned long long ord, bool keep) {
+  using W = Wire<K_LOG>;
+  if (keep) {                              // log_server/udp/server.cc:79-84; entry {key@0 val@8 ver@48}
+    uint8_t* e = c.ring + (size_t)(ord % c.ring_n) * W::LOGENT;
+    uint32_t w[13];                        // key(2) + val(10) + ver(1) are contiguous on the wire
+    ld_words_unaligned<13>(rec + W::KEY, w);
+    uint2* e8 = (uint2*)e;
+#pragma unroll
+    for (int i = 0; i < 6; i++) e8[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    *(uint32_t*)(e + 48) = w[12];
+  }
+  rec[W::TYPE] = 1;                        // kAck :86
+}
+
+// marks a record as "the reference would panic() here" (errors row)
+template <int KIND> DINT_D void mark_invalid(const Ctx& c, uint8_t* rec) {
+  rec[Wire<KIND>::TYPE] = 0xFF;
+  atomicAdd(&c.counters[0], 1ULL);
+}
+
+}  // namespace dint

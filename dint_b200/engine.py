@@ -1,0 +1,267 @@
+"""ctypes binding of libdint_b200.so (include/dint_b200.h): the GPU-resident stand-in for one
+reference server process (`server <threads>` / `server_shard <id> <threads>`).
+
+There is no CPU implementation behind this class: if the CUDA library cannot be built/loaded, or no
+CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+from .wire import MSG_SIZE, LOG_ENTRY_SIZE, KIND_NAMES
+
+DINT_OK, DINT_EPROTO = 0, -71
+
+
+class DintCfg(C.Structure):
+    _fields_ = [("lock_slots", C.c_uint32), ("log_ring", C.c_uint32), ("subs_sizing", C.c_uint32),
+                ("subs_populate", C.c_uint32), ("accts_sizing", C.c_uint32), ("accts_populate", C.c_uint32),
+                ("n_shards", C.c_uint32), ("shard_id", C.c_uint32), ("chunk", C.c_uint32),
+                ("kv_capacity_log2", C.c_uint32 * 5), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+
+
+class DintStats(C.Structure):
+    _fields_ = [("requests", C.c_uint64), ("chunks", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("conflicted", C.c_uint64), ("max_run", C.c_uint64), ("errors", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+
+
+class DintKernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("total_ms", C.c_double)]
+
+
+_lib = None
+
+# every symbol include/dint_b200.h declares
+ABI_SYMBOLS = [
+    "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
+    "dint_submit", "dint_submit_device", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
+    "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
+    "dint_test_fasthash64", "dint_test_fastmod",
+]
+
+
+def lib():
+    """Load (building first if the sources are newer) libdint_b200.so.  Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.find_nvcc() is not None:
+        _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing and nvcc is not available: dint_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.dint_msg_size.restype = u32; L.dint_msg_size.argtypes = [i32]
+    L.dint_default_cfg.restype = None; L.dint_default_cfg.argtypes = [i32, C.POINTER(DintCfg)]
+    L.dint_create.restype = i32; L.dint_create.argtypes = [i32, C.POINTER(DintCfg), i32, C.POINTER(vp)]
+    L.dint_destroy.restype = None; L.dint_destroy.argtypes = [vp]
+    L.dint_populate.restype = i32; L.dint_populate.argtypes = [vp]
+    L.dint_load.restype = i32; L.dint_load.argtypes = [vp, i32, vp, vp, u64]
+    L.dint_submit.restype = i32; L.dint_submit.argtypes = [vp, vp, u64, vp]
+    L.dint_submit_device.restype = i32; L.dint_submit_device.argtypes = [vp, vp, u64, vp, vp]
+    L.dint_sync.restype = i32; L.dint_sync.argtypes = [vp]
+    L.dint_kv_get.restype = i32; L.dint_kv_get.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]
+    L.dint_kv_count.restype = C.c_int64; L.dint_kv_count.argtypes = [vp, i32]
+    L.dint_lock_state.restype = i32; L.dint_lock_state.argtypes = [vp, i32, u32, C.POINTER(u32)]
+    L.dint_lock_slot.restype = u32; L.dint_lock_slot.argtypes = [vp, i32, u64]
+    L.dint_dump_log.restype = i32; L.dint_dump_log.argtypes = [vp, vp, C.POINTER(u64)]
+    L.dint_log_entry_size.restype = u32; L.dint_log_entry_size.argtypes = [i32]
+    L.dint_get_stats.restype = i32; L.dint_get_stats.argtypes = [vp, C.POINTER(DintStats)]
+    L.dint_reset_stats.restype = None; L.dint_reset_stats.argtypes = [vp]
+    L.dint_profile.restype = i32; L.dint_profile.argtypes = [vp, i32]
+    L.dint_kernel_times.restype = i32; L.dint_kernel_times.argtypes = [vp, C.POINTER(DintKernelTime), i32]
+    L.dint_last_error.restype = C.c_char_p; L.dint_last_error.argtypes = []
+    L.dint_host_alloc.restype = vp; L.dint_host_alloc.argtypes = [C.c_size_t]
+    L.dint_host_free.restype = None; L.dint_host_free.argtypes = [vp]
+    L.dint_test_fasthash64.restype = u64; L.dint_test_fasthash64.argtypes = [u64, i32]
+    L.dint_test_fastmod.restype = u32; L.dint_test_fastmod.argtypes = [u64, u32]
+    _lib = L
+    return L
+
+
+class DintError(RuntimeError):
+    def __init__(self, code, what):
+        msg = lib().dint_last_error().decode(errors="replace")
+        super().__init__(f"{what}: error {code} ({msg})")
+        self.code = code
+
+
+def default_cfg(kind, **over):
+    cfg = DintCfg()
+    lib().dint_default_cfg(kind, C.byref(cfg))
+    for k, v in over.items():
+        if k == "kv_capacity_log2":
+            for i, x in enumerate(v):
+                cfg.kv_capacity_log2[i] = x
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+class PinnedBuffer:
+    """Page-locked host buffer exposed as a numpy uint8 array (dint_host_alloc)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = lib().dint_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("dint_host_alloc failed")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(self.nbytes,))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().dint_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One GPU-resident server of the given kind.
+
+    submit() has the semantics of feeding the requests, in order, to ONE thread of the reference
+    server and collecting its replies (see include/dint_b200.h).
+    """
+
+    def __init__(self, kind, device=0, populate=False, **cfg_over):
+        self.kind = kind
+        self.msg = MSG_SIZE[kind]
+        self.cfg = default_cfg(kind, **cfg_over)
+        self.device = device
+        h = C.c_void_p()
+        rc = lib().dint_create(kind, C.byref(self.cfg), device, C.byref(h))
+        if rc != 0:
+            raise DintError(rc, f"dint_create({KIND_NAMES[kind]})")
+        self.h = h
+        if populate:
+            self.populate()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().dint_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- population ------------------------------------------------------------------------------
+    def populate(self):
+        rc = lib().dint_populate(self.h)
+        if rc != 0:
+            raise DintError(rc, "dint_populate")
+
+    def load(self, table, keys, vals):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.uint8)
+        rc = lib().dint_load(self.h, table, keys.ctypes.data, vals.ctypes.data, keys.size)
+        if rc != 0:
+            raise DintError(rc, "dint_load")
+
+    # -- request path ----------------------------------------------------------------------------
+    def submit(self, req, out=None, check=True):
+        """Host path: req is a uint8 array of n*msg bytes (or structured wire records)."""
+        raw = np.ascontiguousarray(req).view(np.uint8).reshape(-1)
+        n = raw.size // self.msg
+        if raw.size != n * self.msg:
+            raise ValueError("request buffer is not a whole number of wire records")
+        if out is None:
+            out = np.empty_like(raw)
+        rc = lib().dint_submit(self.h, raw.ctypes.data, n, out.ctypes.data)
+        if rc != 0 and (check or rc != DINT_EPROTO):
+            raise DintError(rc, "dint_submit")
+        return out
+
+    def submit_device(self, req_ptr, n, resp_ptr, stream=0):
+        """Device path: raw device pointers (16-byte aligned), asynchronous on `stream`."""
+        rc = lib().dint_submit_device(self.h, C.c_void_p(req_ptr), n, C.c_void_p(resp_ptr),
+                                      C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise DintError(rc, "dint_submit_device")
+
+    def submit_tensor(self, req, out=None, stream=None):
+        """Device path on torch CUDA uint8 tensors; runs on the current torch stream by default."""
+        import torch
+        assert req.is_cuda and req.dtype == torch.uint8 and req.is_contiguous()
+        n = req.numel() // self.msg
+        if out is None:
+            out = torch.empty_like(req)
+        s = stream if stream is not None else torch.cuda.current_stream(req.device).cuda_stream
+        self.submit_device(req.data_ptr(), n, out.data_ptr(), s)
+        return out
+
+    def sync(self, check=True):
+        rc = lib().dint_sync(self.h)
+        if rc != 0 and (check or rc != DINT_EPROTO):
+            raise DintError(rc, "dint_sync")
+        return rc
+
+    # -- inspection ------------------------------------------------------------------------------
+    def kv_get(self, table, key):
+        val = (C.c_uint8 * 40)()
+        ver = C.c_uint32(0)
+        rc = lib().dint_kv_get(self.h, table, key, val, C.byref(ver))
+        if rc < 0:
+            raise DintError(rc, "dint_kv_get")
+        return None if rc == 1 else (bytes(val), ver.value)
+
+    def kv_count(self, table):
+        return lib().dint_kv_count(self.h, table)
+
+    def lock_slot(self, table, key):
+        return lib().dint_lock_slot(self.h, table, key)
+
+    def lock_state(self, table, slot):
+        out = (C.c_uint32 * 2)()
+        rc = lib().dint_lock_state(self.h, table, slot, out)
+        if rc != 0:
+            raise DintError(rc, "dint_lock_state")
+        return out[0], out[1]
+
+    def dump_log(self):
+        es = LOG_ENTRY_SIZE[self.kind]
+        n = self.cfg.log_ring
+        out = np.zeros((n, es), dtype=np.uint8)
+        appended = C.c_uint64(0)
+        rc = lib().dint_dump_log(self.h, out.ctypes.data, C.byref(appended))
+        if rc != 0:
+            raise DintError(rc, "dint_dump_log")
+        return out, appended.value
+
+    def stats(self):
+        s = DintStats()
+        rc = lib().dint_get_stats(self.h, C.byref(s))
+        if rc != 0:
+            raise DintError(rc, "dint_get_stats")
+        return {k: getattr(s, k) for k, _ in DintStats._fields_ if k != "reserved"}
+
+    def reset_stats(self):
+        lib().dint_reset_stats(self.h)
+
+    def profile(self, enable=True):
+        rc = lib().dint_profile(self.h, 1 if enable else 0)
+        if rc != 0:
+            raise DintError(rc, "dint_profile")
+
+    def kernel_times(self):
+        arr = (DintKernelTime * 16)()
+        k = lib().dint_kernel_times(self.h, arr, 16)
+        return {arr[i].name.decode(): (arr[i].launches, arr[i].total_ms) for i in range(max(k, 0))}

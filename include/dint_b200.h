@@ -1,0 +1,159 @@
+/*
+ * dint_b200.h -- C ABI of libdint_b200.so, the B200-resident replacement for the per-request
+ * server hot path of DINT (NSDI'24).
+ *
+ * The reference has no plugin/FFI API: the public interface of its hot path is the WIRE PROTOCOL
+ * (one packed struct per UDP datagram; the reply is the same buffer with type/val/ver rewritten and
+ * echoed to the sender) plus the server command line.  This ABI is what a transport front-end (UDP
+ * recvmmsg/sendmmsg batcher, Caladan, DPDK burst loop) binds instead of calling the reference's
+ * handler body one datagram at a time.  Each entry point cites the reference code it replaces
+ * (paths relative to the DINT repository root).
+ *
+ * Semantics contract of dint_submit*: the n requests are processed AS IF one reference server
+ * thread had received them one by one in index order (request i sees the effects of every j < i);
+ * resp[i] is byte-for-byte the datagram that thread would have sent for req[i].  kRetry-class
+ * replies, which exist only for thread-vs-thread spin contention in the reference
+ * (lock_2pl/udp/server.cc:75-80, smallbank/udp/server_shard.cc:111-119), are never produced.
+ *
+ * There is no CPU fallback: every compute entry point fails with DINT_ENODEV when no CUDA device
+ * is usable.
+ */
+#ifndef DINT_B200_H
+#define DINT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Which reference server the engine stands in for. */
+enum dint_kind {
+  DINT_LOCK2PL = 0,   /* lock_2pl/udp/server.cc:55-123       wire: lock_2pl/udp/net.h:25-31   (6 B)  */
+  DINT_FASST = 1,     /* lock_fasst/udp/server.cc:49-120     wire: lock_fasst/udp/net.h:25-31 (9 B)  */
+  DINT_LOG = 2,       /* log_server/udp/server.cc:48-89      wire: log_server/udp/net.h:23-30 (53 B) */
+  DINT_STORE = 3,     /* store/udp/server.cc:50-98           wire: store/udp/net.h:34-41      (53 B) */
+  DINT_TATP = 4,      /* tatp/udp/server_shard.cc:88-211     wire: tatp/udp/net.h:57-65       (55 B) */
+  DINT_SMALLBANK = 5, /* smallbank/udp/server_shard.cc:82-190 wire: smallbank/udp/net.h:43-52 (23 B) */
+  DINT_NUM_KINDS = 6
+};
+
+/* Error codes (negative return values). */
+enum {
+  DINT_OK = 0,
+  DINT_EINVAL = -22,  /* bad argument */
+  DINT_ENOMEM = -12,  /* device/host allocation failed */
+  DINT_ENODEV = -19,  /* no usable CUDA device (there is no CPU fallback) */
+  DINT_EIO = -5,      /* a CUDA call failed; see dint_last_error() */
+  DINT_EPROTO = -71   /* the batch held a request the reference would panic() on; the offending
+                         replies carry type 0xFF, the rest of the batch was processed normally */
+};
+
+/*
+ * Sizes the reference bakes in as constexpr (SURVEY.md section 5 "config / flags").  Defaults =
+ * the reference constants; dint_default_cfg() fills them in.
+ */
+typedef struct dint_cfg {
+  uint32_t lock_slots;     /* kLockHashSize 36,000,000: lock_2pl/udp/utils.h:16, lock_fasst/udp/utils.h:16 */
+  uint32_t log_ring;       /* kMaxLogEntryNum 1,000,000: log_server/udp/utils.h:16, tatp/udp/kvs.h:19 */
+  uint32_t subs_sizing;    /* kSubscriberNum that SIZES hash tables and lock-hash moduli:
+                              store 2,000,000 (store/udp/tatp.h:10, server.cc:113),
+                              tatp 7,000,000 (tatp/udp/tatp.h:28, server_shard.cc:75-79, tatp.h:12-14) */
+  uint32_t subs_populate;  /* subscribers dint_populate() inserts (<= subs_sizing; a prefix of the
+                              reference population, whose LCG streams are sequential in s_id) */
+  uint32_t accts_sizing;   /* smallbank kAccountNum 24,000,000 (smallbank/udp/smallbank.h:17,
+                              server_shard.cc:72-73, smallbank.h:10-14) */
+  uint32_t accts_populate; /* accounts dint_populate() inserts */
+  uint32_t n_shards;       /* key-space shards (GPUs); this engine owns lock slots / buckets with
+                              slot % n_shards == shard_id.  1 = whole key space. */
+  uint32_t shard_id;
+  uint32_t chunk;          /* requests per internal launch group (0 = default 1<<20) */
+  uint32_t kv_capacity_log2[5]; /* per-table open-addressing capacity (0 = auto: >= 2x expected keys) */
+  uint32_t flags;          /* DINT_F_* */
+  uint32_t reserved[4];
+} dint_cfg;
+
+#define DINT_F_GRAPH 1u    /* replay the per-chunk launch sequence through a CUDA graph */
+
+typedef struct dint_engine dint_engine;
+
+/* Counters since create (or the last dint_reset_stats). */
+typedef struct dint_stats {
+  uint64_t requests;        /* requests processed */
+  uint64_t chunks;          /* internal launch groups */
+  uint64_t kernel_launches; /* kernels launched by this engine */
+  uint64_t conflicted;      /* requests that took the ordered (intra-batch conflict) path */
+  uint64_t max_run;         /* longest same-slot run seen on the ordered path */
+  uint64_t errors;          /* requests answered with type 0xFF */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t reserved[4];
+} dint_stats;
+
+/* Per-kernel device time, accumulated with CUDA events while profiling is on. */
+typedef struct dint_kernel_time {
+  char name[32];
+  uint64_t launches;
+  double total_ms;
+} dint_kernel_time;
+
+uint32_t dint_msg_size(int kind);                       /* sizeof(struct message) of that server */
+void dint_default_cfg(int kind, dint_cfg *cfg);
+
+/* Replaces server start-up: main() + net_init() + kvs_init()/array definitions
+ * (lock_fasst/udp/server.cc:124-149, store/udp/server.cc:101-132, tatp/udp/server_shard.cc:71-85,278-320).
+ * Allocates all state in HBM of CUDA device `device`; tables start EMPTY (see dint_populate). */
+int dint_create(int kind, const dint_cfg *cfg, int device, dint_engine **out);
+void dint_destroy(dint_engine *e);
+
+/* Replaces populate_table / populate_*_table / populate_saving_and_checking_tables
+ * (store/udp/tatp.h:45-66, tatp/udp/tatp.h:285-412, smallbank/udp/smallbank.h:105-127):
+ * the same deterministic population, bytes the reference leaves uninitialised are zero. */
+int dint_populate(dint_engine *e);
+
+/* Bulk kvs_insert (store/udp/kvs.h:77-104) of n (key, value) pairs from HOST arrays into `table`;
+ * vals is n * val_size bytes (40; smallbank 8).  Also the path that loads an image dumped from
+ * another server.  Keys must not already exist (the reference's insert never checks either). */
+int dint_load(dint_engine *e, int table, const uint64_t *keys, const void *vals, uint64_t n);
+
+/* Replaces the `while (1) { net_recv; handler body; net_send; }` loop for a batch
+ * (lock_2pl/udp/server.cc:70-122, lock_fasst/udp/server.cc:78-119, log_server/udp/server.cc:73-88,
+ * store/udp/server.cc:75-97, tatp/udp/server_shard.cc:113-210, smallbank/udp/server_shard.cc:107-189).
+ * req/resp: HOST arrays of n packed wire structs (resp may alias req).  Copies in, computes on the
+ * GPU, copies out, returns when resp is complete.  Returns 0, DINT_EPROTO, or another error. */
+int dint_submit(dint_engine *e, const void *req, uint64_t n, void *resp);
+
+/* Same, with DEVICE arrays (16-byte aligned) and asynchronous on `cuda_stream` (a cudaStream_t; NULL
+ * = the engine's own stream).  Errors surface at the next dint_sync()/dint_get_stats(). */
+int dint_submit_device(dint_engine *e, const void *req_dev, uint64_t n, void *resp_dev, void *cuda_stream);
+int dint_sync(dint_engine *e);
+
+/* ---- state inspection: parity of the final server state, not only of the wire ------------------ */
+/* kvs_get on the device table (store/udp/kvs.h:37-55): 0 = found, 1 = not found. */
+int dint_kv_get(dint_engine *e, int table, uint64_t key, void *val, uint32_t *ver);
+int64_t dint_kv_count(dint_engine *e, int table);
+/* lock_2pl: out = {num_ex, num_sh}; lock_fasst: {lock, ver}; tatp: {lock, 0}; smallbank: {num_ex, num_sh} */
+int dint_lock_state(dint_engine *e, int table, uint32_t slot, uint32_t out[2]);
+/* slot the reference would compute for a lock id / key (fasthash64 % size) -- for tests */
+uint32_t dint_lock_slot(dint_engine *e, int table, uint64_t key_or_lid);
+/* copies ring 0 of the commit log (log_ring entries of dint_log_entry_size bytes, laid out as the
+ * reference's struct log_entry) and the number of appends so far */
+int dint_dump_log(dint_engine *e, void *out, uint64_t *appended);
+uint32_t dint_log_entry_size(int kind);
+
+int dint_get_stats(dint_engine *e, dint_stats *s);
+void dint_reset_stats(dint_engine *e);
+int dint_profile(dint_engine *e, int enable);            /* per-kernel CUDA-event timing on/off */
+int dint_kernel_times(dint_engine *e, dint_kernel_time *out, int max_entries);  /* returns #entries */
+const char *dint_last_error(void);
+
+/* pinned host memory for req/resp buffers */
+void *dint_host_alloc(size_t bytes);
+void dint_host_free(void *p);
+
+/* hooks for unit tests of the host/device-shared arithmetic (no GPU needed) */
+uint64_t dint_test_fasthash64(uint64_t x, int len);      /* len 4 or 8, seed 0xdeadbeef */
+uint32_t dint_test_fastmod(uint64_t n, uint32_t d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
