@@ -136,45 +136,38 @@ DINT_D void st_u32_unaligned(uint8_t* p, uint32_t v) {
     p[3] = (uint8_t)(v >> 24);
   }
 }
-// Load NW consecutive words starting at an arbitrary byte address.
+// Load NW consecutive words starting at an arbitrary byte address.  Branch-free: lanes of a warp sit at
+// all four alignments (record sizes are odd), so alignment-dependent branches would serialise.
 template <int NW>
 DINT_D void ld_words_unaligned(const uint8_t* p, uint32_t (&out)[NW]) {
   uintptr_t a = (uintptr_t)p;
   const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
-  uint32_t sh = (uint32_t)(a & 3) * 8;
+  const uint32_t sh = (uint32_t)(a & 3) * 8;
   uint32_t prev = w[0];
-  if (sh == 0) {
-    out[0] = prev;
 #pragma unroll
-    for (int i = 1; i < NW; i++) out[i] = w[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < NW; i++) {
-      uint32_t nxt = w[i + 1];
-      out[i] = __funnelshift_r(prev, nxt, sh);
-      prev = nxt;
-    }
+  for (int i = 0; i < NW; i++) {
+    uint32_t nxt = (i + 1 < NW || sh) ? w[i + 1] : 0u;   // the word past the field is only touched when it holds field bytes
+    out[i] = __funnelshift_r(prev, nxt, sh);
+    prev = nxt;
   }
 }
-// Store NW consecutive words at an arbitrary byte address: aligned interior words, byte stores for
-// the (<=3 + <=3) edge bytes.
+// Store NW consecutive words at an arbitrary byte address: aligned interior words, predicated byte
+// stores for the (<=3 + <=3) edge bytes -- never a read-modify-write of bytes owned by a neighbour.
 template <int NW>
 DINT_D void st_words_unaligned(uint8_t* p, const uint32_t (&v)[NW]) {
-  uint32_t mis = (uint32_t)((uintptr_t)p & 3);
-  if (mis == 0) {
-    uint32_t* w = (uint32_t*)p;
+  const uint32_t mis = (uint32_t)((uintptr_t)p & 3);
+  uint32_t* w = (uint32_t*)(p - mis);                    // aligned word holding the first byte
+  const uint32_t sh = mis * 8;
+  if (mis == 0) w[0] = v[0];
 #pragma unroll
-    for (int i = 0; i < NW; i++) w[i] = v[i];
-    return;
-  }
-  uint32_t head = 4 - mis;                 // bytes before the first aligned word
-  uint32_t sh = head * 8;
-  for (uint32_t b = 0; b < head; b++) p[b] = (uint8_t)(v[0] >> (8 * b));
-  uint32_t* w = (uint32_t*)(p + head);
+  for (int b = 0; b < 3; b++)                            // head: bytes mis..3 of w[0]
+    if (mis != 0 && mis + b < 4) p[b] = (uint8_t)(v[0] >> (8 * b));
 #pragma unroll
-  for (int i = 0; i < NW - 1; i++) w[i] = __funnelshift_r(v[i], v[i + 1], sh);
-  uint8_t* t = p + head + 4 * (NW - 1);
-  for (uint32_t b = 0; b < mis; b++) t[b] = (uint8_t)(v[NW - 1] >> (sh + 8 * b));
+  for (int i = 1; i < NW; i++) w[i] = __funnelshift_l(v[i - 1], v[i], sh);
+  uint8_t* t = (uint8_t*)(w + NW);
+#pragma unroll
+  for (int b = 0; b < 3; b++)                            // tail: bytes 0..mis-1 of w[NW]
+    if ((uint32_t)b < mis) t[b] = (uint8_t)(v[NW - 1] >> (32 - sh + 8 * b));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -52,7 +52,13 @@ struct dint_engine {
   uint8_t* d_resp[2] = {nullptr, nullptr};
   cudaEvent_t ev_in[2]{}, ev_comp[2]{}, ev_out[2]{};
   int coop_grid = 0;
+  int grid_classify = 0, grid_apply = 0;     // persistent CTAs (SMs x resident CTAs per SM)
+  uint32_t smem_stage = 0;                   // dynamic shared memory of K1/K2: kStages staged tiles
   uint64_t total_groups = 0;
+  uint32_t* d_flags[2] = {nullptr, nullptr}; // flag-nibble sets, alternating per chunk
+  uint32_t* d_grp[2] = {nullptr, nullptr};   // group ids of the current / previous chunk
+  uint64_t chunk_seq = 0;
+  uint32_t prev_n = 0;                       // requests of the previous chunk whose flags are still set
   // stats
   dint_stats stats{};
   unsigned long long counters_seen[4] = {0, 0, 0, 0};
@@ -114,7 +120,10 @@ template <int KIND, bool HAS_LOG>
 static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
     ProfScope ps(e, s, KT_CLASSIFY);
-    k_classify<KIND, HAS_LOG><<<c.n_tiles, kThreads, 0, s>>>(c);
+    int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kThreads - 1) / (4 * kThreads));
+    if (clr > want) want = clr;
+    int grid = want < e->grid_classify ? want : e->grid_classify;
+    k_classify<KIND, HAS_LOG><<<grid < 1 ? 1 : grid, kThreads, e->smem_stage, s>>>(c);
   }
   if (HAS_LOG) {
     ProfScope ps(e, s, KT_LOGSCAN);
@@ -122,9 +131,10 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   }
   {
     ProfScope ps(e, s, KT_APPLY);
-    k_apply<KIND, HAS_LOG><<<c.n_tiles, kThreads, 0, s>>>(c);
+    int grid = (int)c.n_tiles < e->grid_apply ? (int)c.n_tiles : e->grid_apply;
+    k_apply<KIND, HAS_LOG><<<grid, kThreads, e->smem_stage, s>>>(c);
   }
-  if (KIND != K_LOG) {   // the log server has no per-key state: nothing to order, nothing to clear
+  if (KIND != K_LOG) {   // the log server has no per-key state: nothing to order
     ProfScope ps(e, s, KT_ORDERED);
     void* args[] = {(void*)&c};
     CU(cudaLaunchCooperativeKernel((void*)k_ordered<KIND>, dim3(e->coop_grid), dim3(kThreads), args, 0, s));
@@ -145,14 +155,26 @@ static int launch_chunk(dint_engine* e, const Ctx& c, cudaStream_t s) {
   return DINT_EINVAL;
 }
 
-template <int KIND>
-static int coop_grid_for(int device, int* out) {
+template <int KIND, bool HAS_LOG>
+static int grids_for(dint_engine* e) {
   int per_sm = 0, sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+  e->smem_stage = Stage<Wire<KIND>::MSG>::N * Stage<Wire<KIND>::MSG>::BYTES;
+  if (e->smem_stage > 48 * 1024) {
+    CU(cudaFuncSetAttribute(k_classify<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
+    CU(cudaFuncSetAttribute(k_apply<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
+  }
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kThreads, e->smem_stage));
+  if (per_sm < 1) return set_err(DINT_EIO, "k_classify cannot be resident");
+  e->grid_classify = per_sm * sms;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apply<KIND, HAS_LOG>, kThreads, e->smem_stage));
+  if (per_sm < 1) return set_err(DINT_EIO, "k_apply cannot be resident");
+  e->grid_apply = per_sm * sms;
+  if (KIND == K_LOG) { e->coop_grid = 1; return DINT_OK; }
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ordered<KIND>, kThreads, 0));
-  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   if (per_sm < 1) return set_err(DINT_EIO, "k_ordered cannot be resident");
   if (per_sm > 4) per_sm = 4;
-  *out = per_sm * sms;
+  e->coop_grid = per_sm * sms;
   return DINT_OK;
 }
 
@@ -163,8 +185,16 @@ static int run_device(dint_engine* e, const uint8_t* req, uint64_t n, uint8_t* r
     c.n_tiles = (c.n + kTile - 1) / kTile;
     c.req = req + off * e->msg;
     c.resp = resp + off * e->msg;
+    const int cur = (int)(e->chunk_seq & 1);
+    c.grp = e->d_grp[cur];
+    c.grp_prev = e->d_grp[cur ^ 1];
+    c.flags = e->d_flags[cur];
+    c.flags_prev = e->d_flags[cur ^ 1];
+    c.prev_n = e->prev_n;
     int rc = launch_chunk(e, c, s);
     if (rc) return rc;
+    e->chunk_seq++;
+    e->prev_n = c.n;
     e->stats.chunks++;
   }
   e->stats.requests += n;
@@ -212,7 +242,7 @@ void dint_host_free(void* p) { if (p) cudaFreeHost(p); }
 void dint_destroy(dint_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   for (auto& ep : e->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (int i = 0; i < 2; i++) {
@@ -274,8 +304,13 @@ static int create_impl(dint_engine* e) {
   }
   e->total_groups = groups;
   if (groups >= 0xffffffffULL) return set_err(DINT_EINVAL, "too many groups");
-  c.bm_words = (uint32_t)((groups + 31) / 32);
-  if ((rc = dalloc(e, &c.bm, (size_t)5 * (c.bm_words ? c.bm_words : 1)))) return rc;
+  {
+    uint32_t fl = 25;                                  // 2^25 nibbles = 16 MB per set: L2-resident
+    while (fl > 10 && (1ULL << (fl - 1)) >= groups * 2 + 2048) fl--;   // tiny group spaces need less
+    c.flags_mask = (1u << fl) - 1;
+    for (int i = 0; i < 2; i++)
+      if ((rc = dalloc(e, &e->d_flags[i], (size_t)1 << (fl - 3)))) return rc;
+  }
   uint32_t bits = 1;
   while ((1ULL << bits) < groups) bits++;
   c.sort_passes = (bits + 7) / 8;
@@ -286,10 +321,19 @@ static int create_impl(dint_engine* e) {
   // ---- chunk scratch ----
   const uint32_t ch = e->chunk;
   e->max_tiles = (ch + kTile - 1) / kTile;
-  if ((rc = dalloc(e, &c.grp, ch))) return rc;
+  for (int i = 0; i < 2; i++)
+    if ((rc = dalloc(e, &e->d_grp[i], ch))) return rc;
   if ((rc = dalloc(e, &c.clist, (size_t)e->max_tiles * kTile))) return rc;
   if ((rc = dalloc(e, &c.ccnt, e->max_tiles))) return rc;
   if ((rc = dalloc(e, &c.cprefix, e->max_tiles + 1))) return rc;
+  if ((rc = dalloc(e, &c.nc_total, 2))) return rc;
+  {
+    uint32_t lg = 0;
+    while (((uint64_t)kBucketFill << lg) < ch) lg++;
+    c.bucket_log2 = lg;
+    if ((rc = dalloc(e, &c.buckets, ((size_t)1 << lg) * kBucketCap, false))) return rc;
+    if ((rc = dalloc(e, &c.bcnt, (size_t)1 << lg))) return rc;
+  }
   if ((rc = dalloc(e, &c.sortA, ch))) return rc;
   if ((rc = dalloc(e, &c.sortB, ch))) return rc;
   if ((rc = dalloc(e, &c.ghist, (size_t)256 * ((ch + kSortTile - 1) / kSortTile)))) return rc;
@@ -300,12 +344,12 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.counters, 4))) return rc;
 
   switch (e->kind) {
-    case DINT_LOCK2PL: rc = coop_grid_for<K_LOCK2PL>(e->device, &e->coop_grid); break;
-    case DINT_FASST: rc = coop_grid_for<K_FASST>(e->device, &e->coop_grid); break;
-    case DINT_LOG: rc = DINT_OK; e->coop_grid = 1; break;
-    case DINT_STORE: rc = coop_grid_for<K_STORE>(e->device, &e->coop_grid); break;
-    case DINT_TATP: rc = coop_grid_for<K_TATP>(e->device, &e->coop_grid); break;
-    default: rc = coop_grid_for<K_SMALLBANK>(e->device, &e->coop_grid); break;
+    case DINT_LOCK2PL: rc = grids_for<K_LOCK2PL, false>(e); break;
+    case DINT_FASST: rc = grids_for<K_FASST, false>(e); break;
+    case DINT_LOG: rc = grids_for<K_LOG, true>(e); break;
+    case DINT_STORE: rc = grids_for<K_STORE, false>(e); break;
+    case DINT_TATP: rc = grids_for<K_TATP, true>(e); break;
+    default: rc = grids_for<K_SMALLBANK, true>(e); break;
   }
   if (rc) return rc;
   int coop = 0;
@@ -345,7 +389,7 @@ int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
 int dint_sync(dint_engine* e) {
   if (!e) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   int rc = prof_flush(e);
   if (rc) return rc;
   unsigned long long before = e->stats.errors;
@@ -357,7 +401,7 @@ int dint_submit_device(dint_engine* e, const void* req_dev, uint64_t n, void* re
   if (!e || (n && (!req_dev || !resp_dev))) return set_err(DINT_EINVAL, "null argument");
   if (((uintptr_t)req_dev | (uintptr_t)resp_dev) & 15) return set_err(DINT_EINVAL, "device buffers must be 16-byte aligned");
   CU(cudaSetDevice(e->device));
-  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  cudaStream_t s = (cudaStream_t)cuda_stream;        // NULL = the legacy default stream, as in every CUDA API
   return run_device(e, (const uint8_t*)req_dev, n, (uint8_t*)resp_dev, s);
 }
 
@@ -371,6 +415,7 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
       if ((rc = dalloc(e, &e->d_resp[i], (size_t)e->chunk * e->msg + 16, false))) return rc;
     }
   }
+  CU(cudaDeviceSynchronize());     // order after anything submitted on user streams
   const uint8_t* rq = (const uint8_t*)req;
   uint8_t* rs = (uint8_t*)resp;
   unsigned long long err_before = e->stats.errors;
@@ -405,7 +450,7 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
 int dint_lock_state(dint_engine* e, int table, uint32_t slot, uint32_t out[2]) {
   if (!e || !out) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   out[0] = out[1] = 0;
   const Ctx& c = e->ctx;
   uint32_t g = slot;
@@ -443,7 +488,7 @@ uint32_t dint_lock_slot(dint_engine* e, int table, uint64_t k) {
 int dint_dump_log(dint_engine* e, void* out, uint64_t* appended) {
   if (!e || !e->has_log) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   if (out) CU(cudaMemcpy(out, e->ctx.ring, (size_t)e->ctx.ring_n * kLogEntry[e->kind], cudaMemcpyDeviceToHost));
   if (appended) {
     unsigned long long t[2];
@@ -456,7 +501,7 @@ int dint_dump_log(dint_engine* e, void* out, uint64_t* appended) {
 int dint_get_stats(dint_engine* e, dint_stats* s) {
   if (!e || !s) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   int rc = pull_counters(e);
   if (rc) return rc;
   *s = e->stats;
@@ -465,7 +510,7 @@ int dint_get_stats(dint_engine* e, dint_stats* s) {
 void dint_reset_stats(dint_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   cudaMemset(e->ctx.counters, 0, 4 * sizeof(unsigned long long));
   e->stats = dint_stats{};
   for (int i = 0; i < KT_NUM; i++) { e->kt_ms[i] = 0; e->kt_n[i] = 0; }
@@ -473,7 +518,7 @@ void dint_reset_stats(dint_engine* e) {
 int dint_profile(dint_engine* e, int enable) {
   if (!e) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   int rc = prof_flush(e);
   e->profiling = enable != 0;
   return rc;
@@ -481,7 +526,7 @@ int dint_profile(dint_engine* e, int enable) {
 int dint_kernel_times(dint_engine* e, dint_kernel_time* out, int max_entries) {
   if (!e || !out) return DINT_EINVAL;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   prof_flush(e);
   int k = 0;
   for (int i = 0; i < KT_NUM && k < max_entries; i++) {
@@ -541,14 +586,14 @@ int dint_populate(dint_engine* e) {
 int dint_kv_get(dint_engine* e, int table, uint64_t key, void* val, uint32_t* ver) {
   if (!e || table < 0 || table >= (int)e->ctx.n_tables) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   return kv_host_get(e->ctx, table, key, kValSize[e->kind], val, ver);
 }
 
 int64_t dint_kv_count(dint_engine* e, int table) {
   if (!e || table < 0 || table >= (int)e->ctx.n_tables) return DINT_EINVAL;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   unsigned long long v = 0;
   if (cudaMemcpy(&v, e->ctx.tbl[table].live, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return DINT_EIO;
   return (int64_t)v;

@@ -6,19 +6,23 @@
 // chunk of requests is processed in three launches:
 //
 //   K1 classify : stage the tile of wire records (TMA bulk copy), hash every key to its group id,
-//                 record the id, and mark per-group bitmaps.  A group has two resources: A (the
-//                 versioned data: ver_table entry / KV rows) and L (the lock word / counters).  A
-//                 request is a reader of A (RA), a writer of A (WA) and/or a writer of L (WL); the
-//                 bitmaps are R (an RA exists), WA, WWA (>= 2 WA), WL, WWL (>= 2 WL).  They are
-//                 exact (one bit per group) and small enough to live in the 126 MB L2 (36 M slots
-//                 -> 4.5 MB each).
+//                 record the id, and mark a 4-bit flag nibble per group.  A group has two resources:
+//                 A (the versioned data: ver_table entry / KV rows) and L (the lock word / counters).
+//                 A request is a reader of A (RA), a writer of A (WA) and/or a writer of L (WL); the
+//                 nibble holds R (an RA exists), WA, WL and W2 (two or more writers of one class).
+//                 The flag array is hash-folded to 2^25 nibbles (16 MB), so it stays in the 126 MB
+//                 L2; folding can only add conflicts, never hide one.  Two flag sets alternate
+//                 between chunks: K1 of chunk k also zeroes the words chunk k-1 touched.
 //   K2 apply    : a request is SOLO when nothing else in the chunk can interact with it
-//                 (RA: WA clear; WA: R and WWA clear; WL: WWL clear).  Solo requests are applied
+//                 (RA: WA clear; WA: R and W2 clear; WL: W2 clear).  Solo requests are applied
 //                 directly, one thread each, against the HBM-resident state and their tile is
 //                 written back with one bulk store.  The others are listed, in index order, for K3.
-//   K3 ordered  : one cooperative launch: stable radix sort of the listed (group, index) pairs by
-//                 group, then every same-group run is replayed in index order by one thread using
-//                 the very same per-request function as K2; finally the bitmaps are cleared.
+//                 Persistent CTAs run a 3-stage TMA pipeline over the tiles.
+//   K3 ordered  : one cooperative launch.  K2 hashes the listed (group, index) pairs into buckets of
+//                 <= 256; each bucket is sorted in shared memory (a warp for <= 32 pairs, else a CTA) and every
+//                 same-group run is replayed in index order by one thread using the very same
+//                 per-request function as K2.  Heavily skewed chunks that overflow a bucket fall
+//                 back to a stable LSD radix sort over the whole list.
 //
 // apply_one<KIND>() below is therefore the single statement of each server's request semantics.
 #pragma once
@@ -31,10 +35,14 @@ enum Kind { K_LOCK2PL = 0, K_FASST = 1, K_LOG = 2, K_STORE = 3, K_TATP = 4, K_SM
 constexpr int kTile = 256;       // wire records per CTA in K1/K2
 constexpr int kThreads = 256;
 constexpr int kMaxTables = 5;
-constexpr uint32_t kSmallSort = 2048;   // K3: up to this many listed requests are sorted in shared memory
+constexpr uint32_t kBucketCap = 256;    // K3: bucket capacity (sorted in shared memory)
+constexpr uint32_t kBucketFill = 64;    // K3: chunk / kBucketFill buckets (mean occupancy 64 if EVERY request were listed)
+constexpr int kStages = 3;              // TMA pipeline depth of the persistent K1/K2 CTAs
 
 // what a request touches inside its group (conflict detection)
 enum : uint32_t { C_RA = 1, C_WA = 2, C_WL = 4 };
+// flag nibble bits
+enum : uint32_t { F_R = 1, F_WA = 2, F_WL = 4, F_W2 = 8 };
 
 // ---- wire layouts (packed structs of the reference) ----------------------------------------------
 template <int KIND> struct Wire;
@@ -79,12 +87,19 @@ struct Ctx {
   uint32_t n;
   uint32_t n_tiles;
   // conflict detection
-  uint32_t* grp;           // [chunk] group id per request (0xffffffff: none)
-  uint32_t* bm;            // 5 bitmaps of bm_words words each: R, WA, WWA, WL, WWL
-  uint32_t bm_words;
+  uint32_t* grp;           // [chunk] group id per request of THIS chunk (0xffffffff: none)
+  const uint32_t* grp_prev;  // [prev_n] group ids of the previous chunk (its flags are cleared by this K1)
+  uint32_t prev_n;
+  uint32_t* flags;         // this chunk's flag set: 2^flags_log2 nibbles
+  uint32_t* flags_prev;    // the previous chunk's flag set
+  uint32_t flags_mask;     // 2^flags_log2 - 1
   uint32_t* clist;         // [n_tiles][kTile] indices of listed requests, tile-segmented
   uint32_t* ccnt;          // [n_tiles] listed requests per tile
-  uint32_t* cprefix;       // [n_tiles+1] exclusive prefix of ccnt (K3)
+  uint32_t* cprefix;       // [n_tiles+1] exclusive prefix of ccnt (K3 general path)
+  uint32_t* nc_total;      // [2]: [0] listed requests of this chunk, [1] bucket overflows
+  uint64_t* buckets;       // [2^bucket_log2][kBucketCap] (group << 32 | index), filled by K2
+  uint32_t* bcnt;          // [2^bucket_log2]
+  uint32_t bucket_log2;
   uint64_t* sortA;         // [chunk] (group << 32 | index)
   uint64_t* sortB;
   uint32_t* ghist;         // [256][sort tiles]
@@ -120,6 +135,10 @@ DINT_D uint32_t bm_fetch_set(uint32_t* bm, uint32_t g) {
 }
 DINT_D void bm_clear_bit(uint32_t* bm, uint32_t g) { atomicAnd(&bm[g >> 5], ~(1u << (g & 31))); }
 
+// flag nibble of group g inside a flag set
+DINT_D uint32_t flag_word(const Ctx& c, uint32_t g) { return (g & c.flags_mask) >> 3; }
+DINT_D uint32_t flag_shift(uint32_t g) { return (g & 7u) * 4u; }
+
 // global group id -> local group id of this shard (owner = global % n_shards)
 DINT_D bool to_local_group(const Ctx& c, uint32_t gglobal, uint32_t& glocal) {
   if (c.n_shards == 1) { glocal = gglobal; return true; }
@@ -128,18 +147,50 @@ DINT_D bool to_local_group(const Ctx& c, uint32_t gglobal, uint32_t& glocal) {
   return gglobal - q * c.n_shards == c.shard_id;
 }
 
-// ---- decode: what a wire record touches (type_info, cheap) and which group (group_of, hashes) ------
+// ---- decode: what a wire record touches (type_info, cheap) and where (key_info, hashes) -----------
 struct TypeInfo {
   uint32_t mask;    // C_RA | C_WA | C_WL
   bool invalid;     // the reference would panic() on this record
   bool is_log;      // appends to the commit log
 };
+struct KeyInfo {
+  uint64_t key;     // lock id / KV key
+  uint64_t h;       // fasthash64 of it (KV kinds: also picks the table entry)
+  uint32_t grp;     // local group id, kNoGroup when the record is not this shard's
+};
 constexpr uint32_t kNoGroup = 0xffffffffu;
 
 template <int KIND> DINT_D TypeInfo type_info(const uint8_t* rec);
-// returns false when the record's group is not owned by this shard (or names a bad table)
-template <int KIND> DINT_D bool group_of(const Ctx& c, const uint8_t* rec, uint32_t& grp);
+template <int KIND> DINT_D KeyInfo key_info(const Ctx& c, const uint8_t* rec);
 
+// State fetched BEFORE the conflict decision is known, so that its HBM latency overlaps the flag
+// lookup instead of following it (see k_apply).  Never trusted across a write to the same group:
+// K3 re-fetches immediately before every replayed request.
+template <int KIND> struct Pre;
+template <int KIND> DINT_D Pre<KIND> prefetch(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo& ti);
+// Warp-wide variant used by k_apply: called by all 32 lanes (`active` = this lane has a request to fetch
+// for).  The KV kinds fetch table entries with several adjacent lanes per entry, so that an entry is ONE
+// 64-byte memory request instead of four 16-byte ones: random-access throughput on this chip is bounded
+// by outstanding requests per SM, not by bytes (tools/ubench.cu).
+template <int KIND>
+DINT_D Pre<KIND> prefetch_coop(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo& ti, bool active);
+
+// apply_one: the request semantics, in place on the wire record.  `rec` holds the request and becomes
+// the reply (the reference mutates the received buffer and sends it back: lock_fasst/udp/server.cc:87-89).
+// The caller guarantees that nothing else touches the same resource of the group concurrently.
+// log_ord: absolute append ordinal for log requests (ring index = ord % ring_n); log_keep: false when a
+// later append of the same chunk lands on the same ring entry.
+template <int KIND>
+DINT_D void apply_one(const Ctx& c, uint8_t* rec, const KeyInfo& ki, const Pre<KIND>& pf, unsigned long long log_ord,
+                      bool log_keep);
+
+// marks a record as "the reference would panic() here" (SURVEY.md section 8(b), errors row)
+template <int KIND> DINT_D void mark_invalid(const Ctx& c, uint8_t* rec) {
+  rec[Wire<KIND>::TYPE] = 0xFF;
+  atomicAdd(&c.counters[0], 1ULL);
+}
+
+// =================================== lock_2pl =========================================================
 template <> DINT_D TypeInfo type_info<K_LOCK2PL>(const uint8_t* rec) {
   using W = Wire<K_LOCK2PL>;
   uint8_t action = rec[W::TYPE], lt = rec[W::LTYPE];
@@ -147,44 +198,27 @@ template <> DINT_D TypeInfo type_info<K_LOCK2PL>(const uint8_t* rec) {
   if (action > 1 || (action == 0 && lt > 1)) return TypeInfo{0, true, false};
   return TypeInfo{C_WL, false, false};   // every lock_2pl request reads or changes the slot's counters
 }
-template <> DINT_D bool group_of<K_LOCK2PL>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
-  uint32_t g = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + Wire<K_LOCK2PL>::KEY)), c.slot_mod);  // :71-72
-  return to_local_group(c, g, grp);
+template <> DINT_D KeyInfo key_info<K_LOCK2PL>(const Ctx& c, const uint8_t* rec) {
+  KeyInfo k;
+  k.key = ld_u32_unaligned(rec + Wire<K_LOCK2PL>::KEY);
+  k.h = fasthash64_u32((uint32_t)k.key);                                  // server.cc:71
+  if (!to_local_group(c, fast_mod(k.h, c.slot_mod), k.grp)) k.grp = kNoGroup;   // :72
+  return k;
 }
-
-template <> DINT_D TypeInfo type_info<K_FASST>(const uint8_t* rec) {
-  uint8_t t = rec[Wire<K_FASST>::TYPE];
-  if (t > 3) return TypeInfo{0, true, false};               // lock_fasst/udp/server.cc:116-117
-  // kRead reads ver_table; kAcquireLock / kAbort CAS the lock word; kCommit does ver++ and the CAS
-  return TypeInfo{(t == 0) ? C_RA : (t == 3) ? (C_WA | C_WL) : C_WL, false, false};
+template <> struct Pre<K_LOCK2PL> { uint2 s; };
+template <> DINT_D Pre<K_LOCK2PL> prefetch<K_LOCK2PL>(const Ctx& c, const uint8_t*, const KeyInfo& ki, const TypeInfo&) {
+  return Pre<K_LOCK2PL>{__ldcg(&c.cnt2[ki.grp])};
 }
-template <> DINT_D bool group_of<K_FASST>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
-  uint32_t g = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + Wire<K_FASST>::KEY)), c.slot_mod);    // :81-82
-  return to_local_group(c, g, grp);
+template <> DINT_D Pre<K_LOCK2PL> prefetch_coop<K_LOCK2PL>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo& ti, bool active) {
+  return active ? prefetch<K_LOCK2PL>(c, rec, ki, ti) : Pre<K_LOCK2PL>{make_uint2(0, 0)};
 }
-
-template <> DINT_D TypeInfo type_info<K_LOG>(const uint8_t* rec) {
-  if (rec[Wire<K_LOG>::TYPE] != 0) return TypeInfo{0, true, false};   // log_server/udp/server.cc:76-77
-  return TypeInfo{0, false, true};
-}
-template <> DINT_D bool group_of<K_LOG>(const Ctx&, const uint8_t*, uint32_t& grp) {
-  grp = kNoGroup;
-  return true;
-}
-
-// ---- apply_one: the request semantics, in place on the wire record --------------------------------
-// `rec` holds the request and becomes the reply (the reference mutates the received buffer and sends
-// it back: lock_fasst/udp/server.cc:87-89).  Caller guarantees exclusive access to the group.
-// log_ord: absolute append ordinal for log requests (ring index = ord % ring_n), log_keep: false when
-// a later append of the same chunk lands on the same ring entry.
-template <int KIND>
-DINT_D void apply_one(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long log_ord, bool log_keep);
-
 template <>
-DINT_D void apply_one<K_LOCK2PL>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long, bool) {
+DINT_D void apply_one<K_LOCK2PL>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, const Pre<K_LOCK2PL>& pf,
+                                 unsigned long long, bool) {
   using W = Wire<K_LOCK2PL>;
+  const uint32_t g = ki.grp;
   uint8_t action = rec[W::TYPE], lt = rec[W::LTYPE];
-  uint2 s = c.cnt2[g];                     // x = num_ex, y = num_sh
+  uint2 s = pf.s;                          // x = num_ex, y = num_sh
   if (action == 0) {                       // kAcquireLock, lock_2pl/udp/server.cc:82-110
     if (lt == 0) {                         // kShared :83-93
       if (s.x == 0) { s.y++; c.cnt2[g] = s; rec[W::TYPE] = 2; } else rec[W::TYPE] = 3;
@@ -198,12 +232,35 @@ DINT_D void apply_one<K_LOCK2PL>(const Ctx& c, uint8_t* rec, uint32_t g, unsigne
   }
 }
 
+// =================================== lock_fasst =======================================================
+template <> DINT_D TypeInfo type_info<K_FASST>(const uint8_t* rec) {
+  uint8_t t = rec[Wire<K_FASST>::TYPE];
+  if (t > 3) return TypeInfo{0, true, false};               // lock_fasst/udp/server.cc:116-117
+  // kRead reads ver_table; kAcquireLock / kAbort CAS the lock word; kCommit does ver++ and the CAS
+  return TypeInfo{(t == 0) ? C_RA : (t == 3) ? (C_WA | C_WL) : C_WL, false, false};
+}
+template <> DINT_D KeyInfo key_info<K_FASST>(const Ctx& c, const uint8_t* rec) {
+  KeyInfo k;
+  k.key = ld_u32_unaligned(rec + Wire<K_FASST>::KEY);
+  k.h = fasthash64_u32((uint32_t)k.key);                                  // server.cc:81
+  if (!to_local_group(c, fast_mod(k.h, c.slot_mod), k.grp)) k.grp = kNoGroup;   // :82
+  return k;
+}
+template <> struct Pre<K_FASST> { uint32_t ver; };
+template <> DINT_D Pre<K_FASST> prefetch<K_FASST>(const Ctx& c, const uint8_t*, const KeyInfo& ki, const TypeInfo& ti) {
+  return Pre<K_FASST>{(ti.mask & (C_RA | C_WA)) ? __ldcg(&c.ver[ki.grp]) : 0u};
+}
+template <> DINT_D Pre<K_FASST> prefetch_coop<K_FASST>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo& ti, bool active) {
+  return active ? prefetch<K_FASST>(c, rec, ki, ti) : Pre<K_FASST>{0u};
+}
 template <>
-DINT_D void apply_one<K_FASST>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long, bool) {
+DINT_D void apply_one<K_FASST>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, const Pre<K_FASST>& pf,
+                               unsigned long long, bool) {
   using W = Wire<K_FASST>;
+  const uint32_t g = ki.grp;
   uint8_t t = rec[W::TYPE];
   if (t == 0) {                            // kRead, lock_fasst/udp/server.cc:86-90
-    st_u32_unaligned(rec + W::VER, c.ver[g]);
+    st_u32_unaligned(rec + W::VER, pf.ver);
     rec[W::TYPE] = 4;
   } else if (t == 1) {                     // kAcquireLock :92-101  CAS(0 -> 1)
     rec[W::TYPE] = bm_fetch_set(c.lockbits, g) ? 6 : 5;
@@ -211,14 +268,24 @@ DINT_D void apply_one<K_FASST>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned 
     bm_clear_bit(c.lockbits, g);
     rec[W::TYPE] = 7;
   } else {                                 // kCommit :109-114      ver++, CAS(1 -> 0)
-    c.ver[g] = c.ver[g] + 1;
+    c.ver[g] = pf.ver + 1;
     bm_clear_bit(c.lockbits, g);
     rec[W::TYPE] = 8;
   }
 }
 
+// =================================== log_server =======================================================
+template <> DINT_D TypeInfo type_info<K_LOG>(const uint8_t* rec) {
+  if (rec[Wire<K_LOG>::TYPE] != 0) return TypeInfo{0, true, false};   // log_server/udp/server.cc:76-77
+  return TypeInfo{0, false, true};
+}
+template <> DINT_D KeyInfo key_info<K_LOG>(const Ctx&, const uint8_t*) { return KeyInfo{0, 0, kNoGroup}; }
+template <> struct Pre<K_LOG> {};
+template <> DINT_D Pre<K_LOG> prefetch<K_LOG>(const Ctx&, const uint8_t*, const KeyInfo&, const TypeInfo&) { return {}; }
+template <> DINT_D Pre<K_LOG> prefetch_coop<K_LOG>(const Ctx&, const uint8_t*, const KeyInfo&, const TypeInfo&, bool) { return {}; }
 template <>
-DINT_D void apply_one<K_LOG>(const Ctx& c, uint8_t* rec, uint32_t, unsigned long long ord, bool keep) {
+DINT_D void apply_one<K_LOG>(const Ctx& c, uint8_t* rec, const KeyInfo&, const Pre<K_LOG>&, unsigned long long ord,
+                             bool keep) {
   using W = Wire<K_LOG>;
   if (keep) {                              // log_server/udp/server.cc:79-84; entry {key@0 val@8 ver@48}
     uint8_t* e = c.ring + (size_t)(ord % c.ring_n) * W::LOGENT;
@@ -230,12 +297,6 @@ DINT_D void apply_one<K_LOG>(const Ctx& c, uint8_t* rec, uint32_t, unsigned long
     *(uint32_t*)(e + 48) = w[12];
   }
   rec[W::TYPE] = 1;                        // kAck :86
-}
-
-// marks a record as "the reference would panic() here" (SURVEY.md section 8(b), errors row)
-template <int KIND> DINT_D void mark_invalid(const Ctx& c, uint8_t* rec) {
-  rec[Wire<KIND>::TYPE] = 0xFF;
-  atomicAdd(&c.counters[0], 1ULL);
 }
 
 }  // namespace dint

@@ -28,44 +28,136 @@ DINT_D uint32_t tile_rank(bool flag, uint32_t* scratch, uint32_t& total) {
   return off + in_warp;
 }
 
+// Two ranks with one pair of barriers (flag a in the low half-word of the per-warp counts, b in the high).
+DINT_D void tile_rank2(bool a, bool b, uint32_t* scratch, uint32_t& ra, uint32_t& rb, uint32_t& ta, uint32_t& tb) {
+  const uint32_t ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
+  const uint32_t lt = (1u << lane_id()) - 1u;
+  if (lane_id() == 0) scratch[warp_id()] = __popc(ba) | (__popc(bb) << 16);
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++) {
+    uint32_t v = scratch[w];
+    if (w < (int)warp_id()) off += v;
+    tot += v;
+  }
+  __syncthreads();
+  ra = (off & 0xffffu) + __popc(ba & lt);
+  rb = (off >> 16) + __popc(bb & lt);
+  ta = tot & 0xffffu;
+  tb = tot >> 16;
+}
+
+DINT_D uint32_t bucket_of(uint32_t g, uint32_t log2p) { return log2p ? (g * 0x9E3779B1u) >> (32 - log2p) : 0; }
+
+// bytes of one pipeline stage: a tile of wire records, padded so every stage stays 128-byte aligned
+template <int MSG> struct Stage {
+  static constexpr uint32_t BYTES = ((kTile * MSG + 16 + 127) / 128) * 128;
+  // pipeline depth: big records get 2 stages so that 8 CTAs (2048 threads) still fit in one SM's shared memory
+  static constexpr uint32_t N = (BYTES > 8192) ? 2 : kStages;
+};
+
+// Persistent-CTA tile pipeline: CTA b owns tiles b, b + gridDim.x, ...; thread 0 keeps kStages - 1
+// TMA bulk loads in flight ahead of the tile being processed.
+struct TileIter {
+  uint32_t n_my;        // tiles owned by this CTA
+  DINT_D uint32_t tile(uint32_t i) const { return blockIdx.x + i * gridDim.x; }
+};
+DINT_D TileIter tile_iter(uint32_t n_tiles) {
+  TileIter it;
+  it.n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  return it;
+}
+template <int MSG>
+DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, const TileIter& it, uint32_t i) {
+  const uint32_t t = it.tile(i), first = t * kTile;
+  const uint32_t cnt = min((uint32_t)kTile, c.n - first);
+  const uint32_t body = (cnt * MSG) & ~15u;
+  const uint32_t buf = i % Stage<MSG>::N;
+  if (body) {
+    mbar_expect_tx(&full[buf], body);
+    tma_load_1d(smem + buf * Stage<MSG>::BYTES, c.req + (size_t)first * MSG, body, &full[buf]);
+  }
+}
+// all threads: wait for tile i's bulk load, fetch the (<16-byte) tail of the very last tile by hand
+template <int MSG>
+DINT_D uint8_t* acquire_tile(const Ctx& c, uint8_t* smem, uint64_t* full, const TileIter& it, uint32_t i,
+                             uint32_t& first, uint32_t& cnt) {
+  const uint32_t t = it.tile(i);
+  first = t * kTile;
+  cnt = min((uint32_t)kTile, c.n - first);
+  const uint32_t bytes = cnt * MSG, body = bytes & ~15u;
+  uint8_t* tile = smem + (i % Stage<MSG>::N) * Stage<MSG>::BYTES;
+  if (body) mbar_wait(&full[i % Stage<MSG>::N], (i / Stage<MSG>::N) & 1u);
+  if (body != bytes) {
+    const uint8_t* src = c.req + (size_t)first * MSG;
+    for (uint32_t b = body + threadIdx.x; b < bytes; b += blockDim.x) tile[b] = src[b];
+    __syncthreads();
+  }
+  return tile;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// K1 classify
+// K1 classify (+ clears the flag words of the previous chunk)
 // ---------------------------------------------------------------------------------------------------
 template <int KIND, bool HAS_LOG>
 __global__ void __launch_bounds__(kThreads) k_classify(const Ctx c) {
   using W = Wire<KIND>;
-  __shared__ __align__(16) uint8_t tile[kTile * W::MSG + 16];
-  __shared__ uint64_t bar;
+  constexpr uint32_t NS = Stage<W::MSG>::N;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[kStages];
   __shared__ uint32_t scratch[kThreads / 32];
-  const uint32_t t = blockIdx.x, first = t * kTile;
-  const uint32_t cnt = min((uint32_t)kTile, c.n - first);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  stage_in(tile, c.req + (size_t)first * W::MSG, cnt * W::MSG, &bar, 0);
-
-  const bool valid = threadIdx.x < cnt;
-  bool is_log = false;
-  if (valid) {
-    const uint8_t* rec = tile + threadIdx.x * W::MSG;
-    TypeInfo ti = type_info<KIND>(rec);
-    uint32_t g = kNoGroup;
-    if (!ti.invalid && ti.mask) {
-      if (!group_of<KIND>(c, rec, g)) g = kNoGroup;
-      if (g != kNoGroup) {
-        uint32_t* bm = c.bm;
-        const uint32_t bw = c.bm_words;
-        if (ti.mask & C_RA) bm_set(bm, g);                                        // R
-        if (ti.mask & C_WA) { if (bm_fetch_set(bm + bw, g)) bm_set(bm + 2 * bw, g); }      // WA, WWA
-        if (ti.mask & C_WL) { if (bm_fetch_set(bm + 3 * bw, g)) bm_set(bm + 4 * bw, g); }  // WL, WWL
-      }
-    }
-    c.grp[first + threadIdx.x] = g;
-    is_log = !ti.invalid && ti.is_log;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
+    if (blockIdx.x == 0) { c.nc_total[0] = 0; c.nc_total[1] = 0; }
   }
-  if (HAS_LOG) {
-    uint32_t total;
-    (void)tile_rank(is_log, scratch, total);
-    if (threadIdx.x == 0) c.log_tilecnt[t] = total;
+  __syncthreads();
+  const TileIter it = tile_iter(c.n_tiles);
+  if (threadIdx.x == 0)
+    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+
+  // retire the previous chunk's flags: every word it touched is zeroed (all of that set's nibbles
+  // were written by that chunk, so whole-word stores are exact)
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < c.prev_n; i += gridDim.x * kThreads) {
+    uint32_t g = c.grp_prev[i];
+    if (g != kNoGroup) c.flags_prev[flag_word(c, g)] = 0;
+  }
+
+  for (uint32_t i = 0; i < it.n_my; i++) {
+    // the stage that held tile i-1 is free (barrier at the end of iteration i-1): refill it now
+    if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
+    uint32_t first, cnt;
+    const uint8_t* tile = acquire_tile<W::MSG>(c, smem, full, it, i, first, cnt);
+    const bool valid = threadIdx.x < cnt;
+    bool is_log = false;
+    if (valid) {
+      const uint8_t* rec = tile + threadIdx.x * W::MSG;
+      TypeInfo ti = type_info<KIND>(rec);
+      uint32_t g = kNoGroup;
+      if (!ti.invalid && ti.mask) {
+        g = key_info<KIND>(c, rec).grp;
+        if (g != kNoGroup) {
+          uint32_t* w = &c.flags[flag_word(c, g)];
+          const uint32_t sh = flag_shift(g);
+          if (ti.mask == C_RA) {
+            atomicOr(w, F_R << sh);                      // no return value: a fire-and-forget RED
+          } else {
+            uint32_t bits = ((ti.mask & C_RA) ? F_R : 0u) | ((ti.mask & C_WA) ? F_WA : 0u) | ((ti.mask & C_WL) ? F_WL : 0u);
+            uint32_t old = (atomicOr(w, bits << sh) >> sh) & 15u;
+            if (((ti.mask & C_WA) && (old & F_WA)) || ((ti.mask & C_WL) && (old & F_WL))) atomicOr(w, F_W2 << sh);
+          }
+        }
+      }
+      c.grp[first + threadIdx.x] = g;
+      is_log = !ti.invalid && ti.is_log;
+    }
+    if (HAS_LOG) {
+      uint32_t total;
+      (void)tile_rank(is_log, scratch, total);          // contains the CTA barriers that free the stage
+      if (threadIdx.x == 0) c.log_tilecnt[it.tile(i)] = total;
+    } else {
+      __syncthreads();                                   // everyone is done reading this stage
+    }
   }
 }
 
@@ -109,60 +201,97 @@ __global__ void __launch_bounds__(kThreads) k_log_scan(const Ctx c) {
 template <int KIND, bool HAS_LOG>
 __global__ void __launch_bounds__(kThreads) k_apply(const Ctx c) {
   using W = Wire<KIND>;
-  __shared__ __align__(16) uint8_t tile[kTile * W::MSG + 16];
-  __shared__ uint64_t bar;
+  constexpr uint32_t NS = Stage<W::MSG>::N;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[kStages];
   __shared__ uint32_t scratch[kThreads / 32];
-  const uint32_t t = blockIdx.x, first = t * kTile;
-  const uint32_t cnt = min((uint32_t)kTile, c.n - first);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (threadIdx.x == 0)
+    for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
   __syncthreads();
-  stage_in(tile, c.req + (size_t)first * W::MSG, cnt * W::MSG, &bar, 0);
+  const TileIter it = tile_iter(c.n_tiles);
+  if (threadIdx.x == 0)
+    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
 
-  const bool valid = threadIdx.x < cnt;
-  uint8_t* rec = tile + threadIdx.x * W::MSG;
-  TypeInfo ti{0, false, false};
-  uint32_t g = kNoGroup;
-  bool listed = false;
-  if (valid) {
-    ti = type_info<KIND>(rec);
-    g = c.grp[first + threadIdx.x];
-    if (!ti.invalid && ti.mask && g == kNoGroup) ti.invalid = true;   // not this shard's / bad table
-    if (!ti.invalid && ti.mask) {
-      const uint32_t* bm = c.bm;
-      const uint32_t bw = c.bm_words;
-      if ((ti.mask & C_RA) && bm_test(bm + bw, g)) listed = true;
-      if ((ti.mask & C_WA) && (bm_test(bm, g) || bm_test(bm + 2 * bw, g))) listed = true;
-      if ((ti.mask & C_WL) && bm_test(bm + 4 * bw, g)) listed = true;
+  for (uint32_t i = 0; i < it.n_my; i++) {
+    if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) {
+      // the stage that held tile i-1 is refilled as soon as its bulk store has finished READING it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
+    }
+    uint32_t first, cnt;
+    uint8_t* tile = acquire_tile<W::MSG>(c, smem, full, it, i, first, cnt);
+    const uint32_t t = it.tile(i);
+    const bool valid = threadIdx.x < cnt;
+    uint8_t* rec = tile + threadIdx.x * W::MSG;
+    TypeInfo ti{0, false, false};
+    KeyInfo ki{0, 0, kNoGroup};
+    Pre<KIND> pf;
+    bool listed = false;
+    if (valid) {
+      ti = type_info<KIND>(rec);
+      if (!ti.invalid && ti.mask) {
+        ki = key_info<KIND>(c, rec);                 // re-hash: cheaper than a dependent load of grp[]
+        if (ki.grp == kNoGroup) ti.invalid = true;   // not this shard's / bad table
+      }
+    }
+    {
+      // issue the state fetch and the flag lookup back to back: one HBM latency, not two
+      const bool active = valid && !ti.invalid && ti.mask;
+      pf = prefetch_coop<KIND>(c, rec, ki, ti, active);
+      if (active) {
+        const uint32_t f = (__ldcg(&c.flags[flag_word(c, ki.grp)]) >> flag_shift(ki.grp)) & 15u;
+        listed = ((ti.mask & C_RA) && (f & F_WA)) || ((ti.mask & C_WA) && (f & (F_R | F_W2))) ||
+                 ((ti.mask & C_WL) && (f & F_W2));
+      }
+    }
+    unsigned long long log_ord = 0;
+    bool log_keep = false;
+    {
+      // listed requests: (a) the tile-segmented, index-ordered list (radix fallback of K3),
+      //                  (b) the hash bucket K3 sorts in shared memory
+      const bool lg = HAS_LOG && valid && !ti.invalid && ti.is_log;
+      uint32_t r_list, r_log, n_list, n_log;
+      tile_rank2(listed, lg, scratch, r_list, r_log, n_list, n_log);
+      if (lg) {
+        log_ord = c.log_tilebase[t] + r_log;
+        log_keep = log_ord + c.ring_n >= c.log_total[1];   // no later append of this chunk overwrites it
+      }
+      if (listed) {
+        const uint32_t idx = first + threadIdx.x;
+        c.clist[(size_t)t * kTile + r_list] = idx;
+        const uint32_t b = bucket_of(ki.grp, c.bucket_log2);
+        const uint32_t pos = atomicAdd(&c.bcnt[b], 1u);
+        if (pos < kBucketCap) c.buckets[(size_t)b * kBucketCap + pos] = ((uint64_t)ki.grp << 32) | idx;
+        else atomicAdd(&c.nc_total[1], 1u);
+      }
+      if (threadIdx.x == 0) {
+        c.ccnt[t] = n_list;
+        if (n_list) atomicAdd(&c.nc_total[0], n_list);
+      }
+    }
+    if (valid) {
+      if (ti.invalid) mark_invalid<KIND>(c, rec);
+      else if (!listed) apply_one<KIND>(c, rec, ki, pf, log_ord, log_keep);
+      // listed: the record leaves this kernel unchanged; K3 rewrites it in place in resp
+    }
+    // ---- write the tile back; keep the load pipeline kStages - 1 tiles ahead ----
+    const uint32_t bytes = cnt * W::MSG, body = bytes & ~15u;
+    uint8_t* gdst = c.resp + (size_t)first * W::MSG;
+    fence_proxy_async_smem();
+    __syncthreads();
+    for (uint32_t b = body + threadIdx.x; b < bytes; b += blockDim.x) gdst[b] = tile[b];
+    if (threadIdx.x == 0) {
+      if (body) tma_store_1d(gdst, tile, body);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
-  unsigned long long log_ord = 0;
-  bool log_keep = false;
-  if (HAS_LOG) {
-    uint32_t total;
-    uint32_t r = tile_rank(valid && !ti.invalid && ti.is_log, scratch, total);
-    if (valid && !ti.invalid && ti.is_log) {
-      log_ord = c.log_tilebase[t] + r;
-      log_keep = log_ord + c.ring_n >= c.log_total[1];   // no later append of this chunk overwrites it
-    }
-  }
-  {
-    uint32_t total;
-    uint32_t r = tile_rank(listed, scratch, total);
-    if (listed) c.clist[(size_t)t * kTile + r] = first + threadIdx.x;
-    if (threadIdx.x == 0) c.ccnt[t] = total;
-  }
-  if (valid) {
-    if (ti.invalid) mark_invalid<KIND>(c, rec);
-    else if (!listed) apply_one<KIND>(c, rec, g, log_ord, log_keep);
-    // listed: the record leaves this kernel unchanged; K3 rewrites it in place in resp
-  }
-  stage_out(c.resp + (size_t)first * W::MSG, tile, cnt * W::MSG);
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K3 ordered replay (cooperative launch: the whole grid is co-resident and uses grid-wide barriers)
 // ---------------------------------------------------------------------------------------------------
-constexpr int kSortItems = 8;                         // items per thread per sort tile
+constexpr int kSortItems = 8;                         // items per thread per radix tile
 constexpr int kSortTile = kThreads * kSortItems;      // 2048
 
 template <int KIND>
@@ -173,53 +302,109 @@ DINT_D void replay_run(const Ctx& c, const uint64_t* sorted, uint32_t p, uint32_
   for (uint32_t q = p; q < nc; q++) {
     uint64_t e = sorted[q];
     if ((uint32_t)(e >> 32) != g) break;
-    apply_one<KIND>(c, c.resp + (size_t)(uint32_t)e * W::MSG, g, 0, false);
+    uint8_t* rec = c.resp + (size_t)(uint32_t)e * W::MSG;     // K2 left the request bytes here
+    const TypeInfo ti = type_info<KIND>(rec);
+    const KeyInfo ki = key_info<KIND>(c, rec);
+    const Pre<KIND> pf = prefetch<KIND>(c, rec, ki, ti);      // fetched AFTER the previous request of the run
+    apply_one<KIND>(c, rec, ki, pf, 0, false);
     len++;
   }
-  atomicMax(&c.counters[2], (unsigned long long)len);
+  if (len > 1) atomicMax(&c.counters[2], (unsigned long long)len);
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
+  const uint32_t nc = c.nc_total[0];
+  if (nc == 0) return;                                // uniform across the grid: nothing listed
   cg::grid_group grid = cg::this_grid();
-  __shared__ uint64_t skeys[kSmallSort];              // 16 KB: small sort; reused as counters by the radix passes
+  __shared__ uint64_t skeys[2048];                    // 16 KB: CTA sort [0,256), warp sorts [1024,1280); radix counters
   __shared__ uint32_t wsum[kThreads / 32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x;
+  const uint32_t P = 1u << c.bucket_log2;
+  const uint32_t overflow = c.nc_total[1];
 
-  // ---- phase 0: exclusive prefix of the per-tile list lengths (CTA 0) ----------------------------
-  if (blockIdx.x == 0) {
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < c.n_tiles; base += kThreads) {
-      uint32_t i = base + tid;
-      uint32_t v = i < c.n_tiles ? c.ccnt[i] : 0;
-      uint32_t x = v;
+  if (overflow == 0) {
+    // ---- bucket path: K2 already hashed every listed (group, index) pair into a bucket; buckets of
+    // <= 32 pairs are rank-sorted by one warp, larger ones bitonic-sorted by the CTA; no grid barrier.
+    uint64_t* wkeys = skeys + 1024 + warp_id() * 32;
+    for (uint32_t base = blockIdx.x * 8; base < P; base += gridDim.x * 8) {
+      const uint32_t b = base + warp_id();
+      const uint32_t m = b < P ? c.bcnt[b] : 0;
+      if (lane_id() == 0) wsum[warp_id()] = m;
+      if (m != 0 && m <= 32) {
+        const uint64_t key = lane_id() < m ? c.buckets[(size_t)b * kBucketCap + lane_id()] : ~0ULL;
+        uint32_t rank = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if ((int)lane_id() >= o) x += y;
+        for (int j = 0; j < 32; j++) rank += (__shfl_sync(0xffffffffu, key, j) < key) ? 1u : 0u;   // keys are distinct
+        if (lane_id() < m) wkeys[rank] = key;
+        __syncwarp();
+        if (lane_id() < m && (lane_id() == 0 || (uint32_t)(wkeys[lane_id() - 1] >> 32) != (uint32_t)(wkeys[lane_id()] >> 32)))
+          replay_run<KIND>(c, wkeys, lane_id(), m);
+        __syncwarp();
+        if (lane_id() == 0) c.bcnt[b] = 0;
       }
-      if (lane_id() == 31) wsum[warp_id()] = x;
       __syncthreads();
-      uint32_t woff = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; w++) {
-        if (w < (int)warp_id()) woff += wsum[w];
-        tot += wsum[w];
+      for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t mk = wsum[k];
+        if (mk <= 32) continue;                       // uniform across the CTA
+        const uint32_t bk = base + k;
+        uint32_t npow = 64;
+        while (npow < mk) npow <<= 1;
+        for (uint32_t i = tid; i < npow; i += kThreads) skeys[i] = i < mk ? c.buckets[(size_t)bk * kBucketCap + i] : ~0ULL;
+        __syncthreads();
+        for (uint32_t kk = 2; kk <= npow; kk <<= 1) {
+          for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < npow; i += kThreads) {
+              uint32_t ixj = i ^ j;
+              if (ixj > i) {
+                uint64_t a = skeys[i], bb = skeys[ixj];
+                bool up = (i & kk) == 0;
+                if ((a > bb) == up) { skeys[i] = bb; skeys[ixj] = a; }
+              }
+            }
+            __syncthreads();
+          }
+        }
+        for (uint32_t p = tid; p < mk; p += kThreads)
+          if (p == 0 || (uint32_t)(skeys[p - 1] >> 32) != (uint32_t)(skeys[p] >> 32)) replay_run<KIND>(c, skeys, p, mk);
+        __syncthreads();
+        if (tid == 0) c.bcnt[bk] = 0;
       }
-      if (i < c.n_tiles) c.cprefix[i] = s_carry + woff + (x - v);
-      __syncthreads();
-      if (tid == 0) s_carry += tot;
       __syncthreads();
     }
-    if (tid == 0) c.cprefix[c.n_tiles] = s_carry;
-  }
-  grid.sync();
-  const uint32_t nc = c.cprefix[c.n_tiles];
-
-  if (nc != 0) {
-    // ---- phase 1: densify the tile-segmented list into (group << 32 | index), index-ascending ----
+  } else {
+    // ---- fallback (skewed chunk): stable LSD radix sort of the whole list by group id --------------
+    for (uint32_t b = blockIdx.x * kThreads + tid; b < P; b += gridDim.x * kThreads) c.bcnt[b] = 0;
+    // (0) exclusive prefix of the per-tile list lengths (CTA 0)
+    if (blockIdx.x == 0) {
+      if (tid == 0) s_carry = 0;
+      __syncthreads();
+      for (uint32_t base = 0; base < c.n_tiles; base += kThreads) {
+        uint32_t i = base + tid;
+        uint32_t v = i < c.n_tiles ? c.ccnt[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+          if ((int)lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) wsum[warp_id()] = x;
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) {
+          if (w < (int)warp_id()) woff += wsum[w];
+          tot += wsum[w];
+        }
+        if (i < c.n_tiles) c.cprefix[i] = s_carry + woff + (x - v);
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
+      }
+    }
+    grid.sync();
+    // (1) densify the tile-segmented list into (group << 32 | index), index-ascending
     for (uint32_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
       uint32_t m = c.ccnt[t];
       if (tid < m) {
@@ -228,173 +413,134 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
       }
     }
     grid.sync();
-
-    if (nc <= kSmallSort) {
-      // ---- small path: bitonic sort of the full 64-bit keys in shared memory, one CTA --------------
-      if (blockIdx.x == 0) {
-        uint32_t npow = 1;
-        while (npow < nc) npow <<= 1;
-        for (uint32_t i = tid; i < npow; i += kThreads) skeys[i] = i < nc ? c.sortA[i] : ~0ULL;
+    uint64_t* src = c.sortA;
+    uint64_t* dst = c.sortB;
+    const uint32_t n_st = (nc + kSortTile - 1) / kSortTile;
+    uint32_t* s_hist = (uint32_t*)skeys;                       // [256]
+    uint32_t* s_wcnt = (uint32_t*)skeys + 256;                 // [8 warps][256]
+    for (uint32_t pass = 0; pass < c.sort_passes; pass++) {
+      const uint32_t shift = 32 + 8 * pass;
+      // (a) per-tile digit histograms
+      for (uint32_t T = blockIdx.x; T < n_st; T += gridDim.x) {
+        s_hist[tid] = 0;
         __syncthreads();
-        for (uint32_t k = 2; k <= npow; k <<= 1) {
-          for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = tid; i < npow; i += kThreads) {
-              uint32_t ixj = i ^ j;
-              if (ixj > i) {
-                uint64_t a = skeys[i], b = skeys[ixj];
-                bool up = (i & k) == 0;
-                if ((a > b) == up) { skeys[i] = b; skeys[ixj] = a; }
-              }
-            }
-            __syncthreads();
-          }
+        uint32_t base = T * kSortTile;
+#pragma unroll
+        for (int k = 0; k < kSortItems; k++) {
+          uint32_t i = base + k * kThreads + tid;
+          if (i < nc) atomicAdd(&s_hist[(uint32_t)(src[i] >> shift) & 255u], 1u);
         }
-        for (uint32_t p = tid; p < nc; p += kThreads)
-          if (p == 0 || (uint32_t)(skeys[p - 1] >> 32) != (uint32_t)(skeys[p] >> 32))
-            replay_run<KIND>(c, skeys, p, nc);
+        __syncthreads();
+        c.ghist[(size_t)tid * n_st + T] = s_hist[tid];
+        __syncthreads();
       }
-    } else {
-      // ---- general path: stable LSD radix sort by group id, 8 bits per pass -------------------------
-      uint64_t* src = c.sortA;
-      uint64_t* dst = c.sortB;
-      const uint32_t n_st = (nc + kSortTile - 1) / kSortTile;
-      uint32_t* s_hist = (uint32_t*)skeys;                       // [256]
-      uint32_t* s_wcnt = (uint32_t*)skeys + 256;                 // [8 warps][256]
-      for (uint32_t pass = 0; pass < c.sort_passes; pass++) {
-        const uint32_t shift = 32 + 8 * pass;
-        // (a) per-tile digit histograms
-        for (uint32_t T = blockIdx.x; T < n_st; T += gridDim.x) {
-          s_hist[tid] = 0;
-          __syncthreads();
-          uint32_t base = T * kSortTile;
+      grid.sync();
+      // (b) row totals
+      for (uint32_t d = blockIdx.x; d < 256; d += gridDim.x) {
+        uint32_t s = 0;
+        for (uint32_t T = tid; T < n_st; T += kThreads) s += c.ghist[(size_t)d * n_st + T];
 #pragma unroll
-          for (int k = 0; k < kSortItems; k++) {
-            uint32_t i = base + k * kThreads + tid;
-            if (i < nc) atomicAdd(&s_hist[(uint32_t)(src[i] >> shift) & 255u], 1u);
-          }
-          __syncthreads();
-          c.ghist[(size_t)tid * n_st + T] = s_hist[tid];
-          __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane_id() == 0) wsum[warp_id()] = s;
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t tot = 0;
+          for (int w = 0; w < kThreads / 32; w++) tot += wsum[w];
+          c.rowtot[d] = tot;
         }
-        grid.sync();
-        // (b) row totals
-        for (uint32_t d = blockIdx.x; d < 256; d += gridDim.x) {
-          uint32_t s = 0;
-          for (uint32_t T = tid; T < n_st; T += kThreads) s += c.ghist[(size_t)d * n_st + T];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane_id() == 0) wsum[warp_id()] = s;
-          __syncthreads();
-          if (tid == 0) {
-            uint32_t tot = 0;
-            for (int w = 0; w < kThreads / 32; w++) tot += wsum[w];
-            c.rowtot[d] = tot;
-          }
-          __syncthreads();
-        }
-        grid.sync();
-        // (c) rows -> global exclusive offsets (digit-major, tile-minor)
-        for (uint32_t d = blockIdx.x; d < 256; d += gridDim.x) {
-          uint32_t part = (tid < d) ? c.rowtot[tid] : 0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-          if (lane_id() == 0) wsum[warp_id()] = part;
-          __syncthreads();
-          if (tid == 0) {
-            uint32_t b = 0;
-            for (int w = 0; w < kThreads / 32; w++) b += wsum[w];
-            s_carry = b;
-          }
-          __syncthreads();
-          for (uint32_t base = 0; base < n_st; base += kThreads) {
-            uint32_t T = base + tid;
-            uint32_t v = T < n_st ? c.ghist[(size_t)d * n_st + T] : 0;
-            uint32_t x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-              if ((int)lane_id() >= o) x += y;
-            }
-            if (lane_id() == 31) wsum[warp_id()] = x;
-            __syncthreads();
-            uint32_t woff = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; w++) {
-              if (w < (int)warp_id()) woff += wsum[w];
-              tot += wsum[w];
-            }
-            if (T < n_st) c.ghist[(size_t)d * n_st + T] = s_carry + woff + (x - v);
-            __syncthreads();
-            if (tid == 0) s_carry += tot;
-            __syncthreads();
-          }
-        }
-        grid.sync();
-        // (d) stable scatter: warp w owns items [w*256, w*256+256) of the tile, in 8 rounds of 32
-        for (uint32_t T = blockIdx.x; T < n_st; T += gridDim.x) {
-          for (uint32_t i = tid; i < 8 * 256; i += kThreads) s_wcnt[i] = 0;
-          __syncthreads();
-          const uint32_t wbase = T * kSortTile + warp_id() * (kSortItems * 32);
-          uint64_t key[kSortItems];
-          uint32_t rank[kSortItems];
-#pragma unroll
-          for (int k = 0; k < kSortItems; k++) {
-            uint32_t i = wbase + k * 32 + lane_id();
-            bool ok = i < nc;
-            key[k] = ok ? src[i] : 0;
-            uint32_t dgt = ok ? ((uint32_t)(key[k] >> shift) & 255u) : 256u + lane_id();  // inactive lanes never match
-            uint32_t peers = __match_any_sync(0xffffffffu, dgt);
-            uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
-            uint32_t basec = 0;
-            if (ok) {
-              uint32_t* cptr = &s_wcnt[warp_id() * 256 + dgt];
-              if (before == 0) { basec = *cptr; *cptr = basec + __popc(peers); }
-              basec = __shfl_sync(peers, basec, __ffs(peers) - 1);
-            }
-            rank[k] = basec + before;
-            __syncwarp();
-          }
-          __syncthreads();
-          // exclusive scan over warps for digit = tid
-          {
-            uint32_t run = c.ghist[(size_t)tid * n_st + T];
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; w++) {
-              uint32_t v = s_wcnt[w * 256 + tid];
-              s_wcnt[w * 256 + tid] = run;
-              run += v;
-            }
-          }
-          __syncthreads();
-#pragma unroll
-          for (int k = 0; k < kSortItems; k++) {
-            uint32_t i = wbase + k * 32 + lane_id();
-            if (i < nc) {
-              uint32_t dgt = (uint32_t)(key[k] >> shift) & 255u;
-              dst[s_wcnt[warp_id() * 256 + dgt] + rank[k]] = key[k];
-            }
-          }
-          __syncthreads();
-        }
-        grid.sync();
-        uint64_t* tmp = src; src = dst; dst = tmp;
+        __syncthreads();
       }
-      // ---- replay: one thread per same-group run ---------------------------------------------------
-      for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, src, p, nc);
-    }
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&c.counters[1], (unsigned long long)nc);
-  }
-
-  // ---- clear the conflict bitmaps: only words this chunk touched -----------------------------------
-  for (uint32_t i = blockIdx.x * kThreads + tid; i < c.n; i += gridDim.x * kThreads) {
-    uint32_t g = c.grp[i];
-    if (g != kNoGroup) {
-      uint32_t w = g >> 5;
+      grid.sync();
+      // (c) rows -> global exclusive offsets (digit-major, tile-minor)
+      for (uint32_t d = blockIdx.x; d < 256; d += gridDim.x) {
+        uint32_t part = (tid < d) ? c.rowtot[tid] : 0;
 #pragma unroll
-      for (int b = 0; b < 5; b++) c.bm[(size_t)b * c.bm_words + w] = 0;
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane_id() == 0) wsum[warp_id()] = part;
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t b = 0;
+          for (int w = 0; w < kThreads / 32; w++) b += wsum[w];
+          s_carry = b;
+        }
+        __syncthreads();
+        for (uint32_t base = 0; base < n_st; base += kThreads) {
+          uint32_t T = base + tid;
+          uint32_t v = T < n_st ? c.ghist[(size_t)d * n_st + T] : 0;
+          uint32_t x = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane_id() >= o) x += y;
+          }
+          if (lane_id() == 31) wsum[warp_id()] = x;
+          __syncthreads();
+          uint32_t woff = 0, tot = 0;
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; w++) {
+            if (w < (int)warp_id()) woff += wsum[w];
+            tot += wsum[w];
+          }
+          if (T < n_st) c.ghist[(size_t)d * n_st + T] = s_carry + woff + (x - v);
+          __syncthreads();
+          if (tid == 0) s_carry += tot;
+          __syncthreads();
+        }
+      }
+      grid.sync();
+      // (d) stable scatter: warp w owns items [w*256, w*256+256) of the tile, in 8 rounds of 32
+      for (uint32_t T = blockIdx.x; T < n_st; T += gridDim.x) {
+        for (uint32_t i = tid; i < 8 * 256; i += kThreads) s_wcnt[i] = 0;
+        __syncthreads();
+        const uint32_t wbase = T * kSortTile + warp_id() * (kSortItems * 32);
+        uint64_t key[kSortItems];
+        uint32_t rank[kSortItems];
+#pragma unroll
+        for (int k = 0; k < kSortItems; k++) {
+          uint32_t i = wbase + k * 32 + lane_id();
+          bool ok = i < nc;
+          key[k] = ok ? src[i] : 0;
+          uint32_t dgt = ok ? ((uint32_t)(key[k] >> shift) & 255u) : 256u + lane_id();  // inactive lanes never match
+          uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+          uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
+          uint32_t basec = 0;
+          if (ok) {
+            uint32_t* cptr = &s_wcnt[warp_id() * 256 + dgt];
+            if (before == 0) { basec = *cptr; *cptr = basec + __popc(peers); }
+            basec = __shfl_sync(peers, basec, __ffs(peers) - 1);
+          }
+          rank[k] = basec + before;
+          __syncwarp();
+        }
+        __syncthreads();
+        {                                   // exclusive scan over warps for digit = tid
+          uint32_t run = c.ghist[(size_t)tid * n_st + T];
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; w++) {
+            uint32_t v = s_wcnt[w * 256 + tid];
+            s_wcnt[w * 256 + tid] = run;
+            run += v;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSortItems; k++) {
+          uint32_t i = wbase + k * 32 + lane_id();
+          if (i < nc) {
+            uint32_t dgt = (uint32_t)(key[k] >> shift) & 255u;
+            dst[s_wcnt[warp_id() * 256 + dgt] + rank[k]] = key[k];
+          }
+        }
+        __syncthreads();
+      }
+      grid.sync();
+      uint64_t* tmp = src; src = dst; dst = tmp;
     }
+    // replay: one thread per same-group run
+    for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
+      if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, src, p, nc);
   }
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&c.counters[1], (unsigned long long)nc);
 }
 
 }  // namespace dint

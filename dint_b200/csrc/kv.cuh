@@ -29,15 +29,20 @@ constexpr uint64_t kKvMix = 0x9E3779B97F4A7C15ULL;
 #ifdef __CUDACC__
 DINT_D uint64_t kv_home(const KvTable& t, uint64_t h) { return (h * kKvMix) >> (64 - t.cap_log2); }
 
-// Probe for `key`.  On a hit returns the entry and leaves its 16-byte vectors in `v` (v[0] = key lo/hi,
-// ver, meta; v[1..] = value); returns nullptr on a miss.
+template <int VALSZ>
+DINT_D void kv_load_entry(const uint8_t* e, uint4 (&v)[Ent<VALSZ>::NV]) {
+#pragma unroll
+  for (int k = 0; k < Ent<VALSZ>::NV; k++) v[k] = __ldcg((const uint4*)e + k);   // one aligned entry, L1 bypass
+}
+
+// Probe for `key`.  `v` arrives holding the HOME entry (fetched by prefetch()); on a hit returns the
+// entry and leaves its 16-byte vectors in `v` (v[0] = key lo/hi, ver, meta; v[1..] = value).
 template <int VALSZ>
 DINT_D uint8_t* kv_find(const KvTable& t, uint64_t key, uint64_t h, uint4 (&v)[Ent<VALSZ>::NV]) {
   uint64_t i = kv_home(t, h);
   for (uint64_t probe = 0; probe <= t.cap_mask; probe++) {
     uint8_t* e = t.entries + (i << t.ent_shift);
-#pragma unroll
-    for (int k = 0; k < Ent<VALSZ>::NV; k++) v[k] = __ldcg((const uint4*)e + k);   // one aligned entry, L1 bypass
+    if (probe) kv_load_entry<VALSZ>(e, v);
     uint32_t meta = v[0].w;
     if (meta == ENT_EMPTY) return nullptr;
     if (meta == ENT_FULL && v[0].x == (uint32_t)key && v[0].y == (uint32_t)(key >> 32)) return e;
@@ -48,13 +53,15 @@ DINT_D uint8_t* kv_find(const KvTable& t, uint64_t key, uint64_t h, uint4 (&v)[E
 
 // kvs_get (kvs.h:37-55): on a hit copy val and ver into the wire record.
 template <int VALSZ>
-DINT_D bool kv_get_into(const KvTable& t, uint64_t key, uint64_t h, uint8_t* wire_val, uint8_t* wire_ver) {
-  uint4 v[Ent<VALSZ>::NV];
+DINT_D bool kv_get_into(const KvTable& t, uint64_t key, uint64_t h, uint4 (&v)[Ent<VALSZ>::NV], uint8_t* wire_val,
+                        uint8_t* wire_ver) {
   if (!kv_find<VALSZ>(t, key, h, v)) return false;
   uint32_t w[Ent<VALSZ>::NW];
-  const uint32_t* flat = (const uint32_t*)v;
 #pragma unroll
-  for (int k = 0; k < Ent<VALSZ>::NW; k++) w[k] = flat[4 + k];
+  for (int k = 0; k < Ent<VALSZ>::NW; k++) {
+    const uint4& q = v[1 + k / 4];
+    w[k] = (k % 4 == 0) ? q.x : (k % 4 == 1) ? q.y : (k % 4 == 2) ? q.z : q.w;
+  }
   st_words_unaligned<Ent<VALSZ>::NW>(wire_val, w);
   st_u32_unaligned(wire_ver, v[0].z);
   return true;
@@ -73,8 +80,7 @@ DINT_D void kv_write_val(uint8_t* e, const uint32_t (&w)[Ent<VALSZ>::NW]) {
 
 // kvs_set (kvs.h:57-75): overwrite val, ver++.
 template <int VALSZ>
-DINT_D bool kv_set_from(const KvTable& t, uint64_t key, uint64_t h, const uint8_t* wire_val) {
-  uint4 v[Ent<VALSZ>::NV];
+DINT_D bool kv_set_from(const KvTable& t, uint64_t key, uint64_t h, uint4 (&v)[Ent<VALSZ>::NV], const uint8_t* wire_val) {
   uint8_t* e = kv_find<VALSZ>(t, key, h, v);
   if (!e) return false;
   uint32_t w[Ent<VALSZ>::NW];
@@ -119,8 +125,7 @@ DINT_D bool kv_insert_from(const KvTable& t, uint64_t key, uint64_t h, const uin
 
 // kvs_delete (kvs.h:106-136)
 template <int VALSZ>
-DINT_D bool kv_delete(const KvTable& t, uint64_t key, uint64_t h) {
-  uint4 v[Ent<VALSZ>::NV];
+DINT_D bool kv_delete(const KvTable& t, uint64_t key, uint64_t h, uint4 (&v)[Ent<VALSZ>::NV]) {
   uint8_t* e = kv_find<VALSZ>(t, key, h, v);
   if (!e) return false;
   *((volatile uint32_t*)(e + 12)) = ENT_TOMB;
@@ -129,12 +134,51 @@ DINT_D bool kv_delete(const KvTable& t, uint64_t key, uint64_t h) {
 }
 
 // group of a KV key: the reference's bucket (store) or lock_hash (tatp.h:12-14, smallbank.h:12-14)
-DINT_D bool kv_group(const Ctx& c, uint32_t table, uint64_t h, uint32_t& grp) {
+DINT_D uint32_t kv_group(const Ctx& c, uint32_t table, uint64_t h) {
   const KvTable& t = c.tbl[table];
-  uint32_t g = fast_mod(h, t.lock_mod), gl;
-  if (!to_local_group(c, g, gl)) return false;
-  grp = t.grp_base + gl;
-  return true;
+  uint32_t gl;
+  if (!to_local_group(c, fast_mod(h, t.lock_mod), gl)) return kNoGroup;
+  return t.grp_base + gl;
+}
+// the home entry of (table, key): the one access a first-probe hit needs
+template <int VALSZ>
+DINT_D void kv_prefetch_home(const Ctx& c, uint32_t table, uint64_t h, uint4 (&v)[Ent<VALSZ>::NV]) {
+  const KvTable& t = c.tbl[table];
+  kv_load_entry<VALSZ>(t.entries + (kv_home(t, h) << t.ent_shift), v);
+}
+
+// Warp-cooperative fetch of every lane's home entry: NV adjacent lanes read one entry with a single
+// coalesced request (64 B = 4 lanes x 16 B, 32 B = 2 lanes), then the 16-byte pieces are handed to the
+// owning lane with shuffles.  Must be executed by all 32 lanes; `need` = this lane wants its entry.
+template <int VALSZ>
+DINT_D void kv_prefetch_home_coop(const uint8_t* entry, bool need, uint4 (&v)[Ent<VALSZ>::NV]) {
+  constexpr int LPE = Ent<VALSZ>::NV;        // lanes per entry
+  constexpr int EPR = 32 / LPE;              // entries fetched per round
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned long long a = (unsigned long long)entry;
+#pragma unroll
+  for (int r = 0; r < LPE; r++) {
+    const int src = r * EPR + (int)(lane / LPE);
+    const unsigned long long sa = __shfl_sync(0xffffffffu, a, src);
+    const int sneed = __shfl_sync(0xffffffffu, need ? 1 : 0, src);
+    uint4 piece = make_uint4(0, 0, 0, 0);
+    if (sneed) piece = __ldcg((const uint4*)sa + (lane % LPE));
+#pragma unroll
+    for (int k = 0; k < LPE; k++) {
+      const int from = (int)(lane % EPR) * LPE + k;
+      uint4 got;
+      got.x = __shfl_sync(0xffffffffu, piece.x, from);
+      got.y = __shfl_sync(0xffffffffu, piece.y, from);
+      got.z = __shfl_sync(0xffffffffu, piece.z, from);
+      got.w = __shfl_sync(0xffffffffu, piece.w, from);
+      if ((int)(lane / EPR) == r) v[k] = got;
+    }
+  }
+}
+template <int VALSZ>
+DINT_D const uint8_t* kv_home_ptr(const Ctx& c, uint32_t table, uint64_t h) {
+  const KvTable& t = c.tbl[table];
+  return t.entries + (kv_home(t, h) << t.ent_shift);
 }
 
 // =================================== store ==========================================================
@@ -145,21 +189,36 @@ template <> DINT_D TypeInfo type_info<K_STORE>(const uint8_t* rec) {
                                                             // population path (store/ebpf/store_user.c)
   return TypeInfo{0, true, false};                          // :93-94
 }
-template <> DINT_D bool group_of<K_STORE>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
-  return kv_group(c, 0, fasthash64_u64(ld_u64_unaligned(rec + Wire<K_STORE>::KEY)), grp);   // kvs.h:33-35
+template <> DINT_D KeyInfo key_info<K_STORE>(const Ctx& c, const uint8_t* rec) {
+  KeyInfo k;
+  k.key = ld_u64_unaligned(rec + Wire<K_STORE>::KEY);
+  k.h = fasthash64_u64(k.key);                              // kvs.h:33-35
+  k.grp = kv_group(c, 0, k.h);
+  return k;
+}
+template <> struct Pre<K_STORE> { uint4 v[4]; };
+template <> DINT_D Pre<K_STORE> prefetch<K_STORE>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo&) {
+  Pre<K_STORE> p;
+  if (rec[Wire<K_STORE>::TYPE] != 2) kv_prefetch_home<40>(c, 0, ki.h, p.v);
+  return p;
+}
+template <> DINT_D Pre<K_STORE> prefetch_coop<K_STORE>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo&, bool active) {
+  Pre<K_STORE> p;
+  const bool need = active && rec[Wire<K_STORE>::TYPE] != 2;
+  kv_prefetch_home_coop<40>(need ? kv_home_ptr<40>(c, 0, ki.h) : nullptr, need, p.v);
+  return p;
 }
 template <>
-DINT_D void apply_one<K_STORE>(const Ctx& c, uint8_t* rec, uint32_t, unsigned long long, bool) {
+DINT_D void apply_one<K_STORE>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, const Pre<K_STORE>& pf, unsigned long long, bool) {
   using W = Wire<K_STORE>;
-  const uint64_t key = ld_u64_unaligned(rec + W::KEY);
-  const uint64_t h = fasthash64_u64(key);
   const uint8_t t = rec[W::TYPE];
+  uint4 v[4] = {pf.v[0], pf.v[1], pf.v[2], pf.v[3]};
   if (t == 0) {
-    rec[W::TYPE] = kv_get_into<40>(c.tbl[0], key, h, rec + W::VAL, rec + W::VER) ? 3 : 7;   // kGrantRead / kNotExist
+    rec[W::TYPE] = kv_get_into<40>(c.tbl[0], ki.key, ki.h, v, rec + W::VAL, rec + W::VER) ? 3 : 7;   // kGrantRead / kNotExist
   } else if (t == 1) {
-    rec[W::TYPE] = kv_set_from<40>(c.tbl[0], key, h, rec + W::VAL) ? 5 : 7;                 // kSetAck / kNotExist
+    rec[W::TYPE] = kv_set_from<40>(c.tbl[0], ki.key, ki.h, v, rec + W::VAL) ? 5 : 7;                 // kSetAck / kNotExist
   } else {
-    if (kv_insert_from<40>(c.tbl[0], key, h, rec + W::VAL)) rec[W::TYPE] = 8;               // kInsertAck
+    if (kv_insert_from<40>(c.tbl[0], ki.key, ki.h, rec + W::VAL)) rec[W::TYPE] = 8;                  // kInsertAck
     else mark_invalid<K_STORE>(c, rec);
   }
 }
@@ -177,12 +236,34 @@ template <> DINT_D TypeInfo type_info<K_TATP>(const uint8_t* rec) {
     default: return TypeInfo{0, true, false};                       // tatp/udp/server_shard.cc:209
   }
 }
-template <> DINT_D bool group_of<K_TATP>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
+template <> DINT_D KeyInfo key_info<K_TATP>(const Ctx& c, const uint8_t* rec) {
   using W = Wire<K_TATP>;
-  return kv_group(c, rec[W::TABLE], fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), grp);
+  KeyInfo k;
+  k.key = ld_u64_unaligned(rec + W::KEY);
+  k.h = fasthash64_u64(k.key);
+  k.grp = kv_group(c, rec[W::TABLE], k.h);                          // lock_hash, tatp/udp/tatp.h:12-14
+  return k;
+}
+template <> struct Pre<K_TATP> { uint4 v[4]; };
+DINT_D bool tatp_touches_row(uint8_t type) {   // request types that look a row up (not insert / lock / log)
+  return type == 0 || type == 12 || type == 13 || type == 22 || type == 23;
+}
+template <> DINT_D Pre<K_TATP> prefetch<K_TATP>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo&) {
+  using W = Wire<K_TATP>;
+  Pre<K_TATP> p;
+  if (tatp_touches_row(rec[W::TYPE])) kv_prefetch_home<40>(c, rec[W::TABLE], ki.h, p.v);
+  return p;
+}
+template <> DINT_D Pre<K_TATP> prefetch_coop<K_TATP>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo&, bool active) {
+  using W = Wire<K_TATP>;
+  Pre<K_TATP> p;
+  const bool need = active && tatp_touches_row(rec[W::TYPE]);
+  kv_prefetch_home_coop<40>(need ? kv_home_ptr<40>(c, rec[W::TABLE], ki.h) : nullptr, need, p.v);
+  return p;
 }
 template <>
-DINT_D void apply_one<K_TATP>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long ord, bool keep) {
+DINT_D void apply_one<K_TATP>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, const Pre<K_TATP>& pf, unsigned long long ord,
+                              bool keep) {
   using W = Wire<K_TATP>;
   const uint8_t type = rec[W::TYPE], table = rec[W::TABLE];
   if (type == 14 || type == 24) {          // kCommitLog :182-194 / kDeleteLog :196-207
@@ -204,19 +285,20 @@ DINT_D void apply_one<K_TATP>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned l
     return;
   }
   const KvTable& t = c.tbl[table];
-  const uint64_t key = ld_u64_unaligned(rec + W::KEY);
-  const uint64_t h = fasthash64_u64(key);
+  const uint64_t key = ki.key, h = ki.h;
+  const uint32_t g = ki.grp;
+  uint4 v[4] = {pf.v[0], pf.v[1], pf.v[2], pf.v[3]};
   bool ok = true;
   switch (type) {
-    case 0: rec[W::TYPE] = kv_get_into<40>(t, key, h, rec + W::VAL, rec + W::VER) ? 4 : 6; break;  // :116-121
-    case 1: rec[W::TYPE] = bm_fetch_set(c.lockbits, g) ? 8 : 7; break;                             // :123-132
-    case 2: bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 9; break;                                  // :134-138
-    case 12: ok = kv_set_from<40>(t, key, h, rec + W::VAL); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 15; break;    // :140-146
-    case 18: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 20; break; // :148-154
-    case 22: ok = kv_delete<40>(t, key, h); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 25; break;                    // :156-162
-    case 13: ok = kv_set_from<40>(t, key, h, rec + W::VAL); rec[W::TYPE] = 16; break;              // :164-168
-    case 19: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); rec[W::TYPE] = 21; break;           // :170-174
-    default: ok = kv_delete<40>(t, key, h); rec[W::TYPE] = 26; break;                              // 23 :176-180
+    case 0: rec[W::TYPE] = kv_get_into<40>(t, key, h, v, rec + W::VAL, rec + W::VER) ? 4 : 6; break;  // :116-121
+    case 1: rec[W::TYPE] = bm_fetch_set(c.lockbits, g) ? 8 : 7; break;                                // :123-132
+    case 2: bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 9; break;                                     // :134-138
+    case 12: ok = kv_set_from<40>(t, key, h, v, rec + W::VAL); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 15; break;  // :140-146
+    case 18: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 20; break;  // :148-154
+    case 22: ok = kv_delete<40>(t, key, h, v); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 25; break;                  // :156-162
+    case 13: ok = kv_set_from<40>(t, key, h, v, rec + W::VAL); rec[W::TYPE] = 16; break;              // :164-168
+    case 19: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); rec[W::TYPE] = 21; break;              // :170-174
+    default: ok = kv_delete<40>(t, key, h, v); rec[W::TYPE] = 26; break;                              // 23 :176-180
   }
   if (!ok) mark_invalid<K_TATP>(c, rec);   // kvs_set / kvs_delete on a missing key: tatp/udp/kvs.h:91,152 panic
 }
@@ -233,12 +315,35 @@ template <> DINT_D TypeInfo type_info<K_SMALLBANK>(const uint8_t* rec) {
     default: return TypeInfo{0, true, false};                       // smallbank/udp/server_shard.cc:188
   }
 }
-template <> DINT_D bool group_of<K_SMALLBANK>(const Ctx& c, const uint8_t* rec, uint32_t& grp) {
+template <> DINT_D KeyInfo key_info<K_SMALLBANK>(const Ctx& c, const uint8_t* rec) {
   using W = Wire<K_SMALLBANK>;
-  return kv_group(c, rec[W::TABLE], fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), grp);   // :109
+  KeyInfo k;
+  k.key = ld_u64_unaligned(rec + W::KEY);
+  k.h = fasthash64_u64(k.key);
+  k.grp = kv_group(c, rec[W::TABLE], k.h);                          // :109 lock_hash
+  return k;
+}
+template <> struct Pre<K_SMALLBANK> { uint4 v[2]; uint2 s; };
+template <> DINT_D Pre<K_SMALLBANK> prefetch<K_SMALLBANK>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo&) {
+  using W = Wire<K_SMALLBANK>;
+  Pre<K_SMALLBANK> p;
+  const uint8_t type = rec[W::TYPE];
+  if (type <= 3) p.s = __ldcg(&c.cnt2[ki.grp]);
+  if (type != 2 && type != 3) kv_prefetch_home<8>(c, rec[W::TABLE], ki.h, p.v);
+  return p;
+}
+template <> DINT_D Pre<K_SMALLBANK> prefetch_coop<K_SMALLBANK>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo&, bool active) {
+  using W = Wire<K_SMALLBANK>;
+  Pre<K_SMALLBANK> p;
+  const uint8_t type = active ? rec[W::TYPE] : 2;
+  if (active && type <= 3) p.s = __ldcg(&c.cnt2[ki.grp]);
+  const bool need = active && type != 2 && type != 3;
+  kv_prefetch_home_coop<8>(need ? kv_home_ptr<8>(c, rec[W::TABLE], ki.h) : nullptr, need, p.v);
+  return p;
 }
 template <>
-DINT_D void apply_one<K_SMALLBANK>(const Ctx& c, uint8_t* rec, uint32_t g, unsigned long long ord, bool keep) {
+DINT_D void apply_one<K_SMALLBANK>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, const Pre<K_SMALLBANK>& pf,
+                                   unsigned long long ord, bool keep) {
   using W = Wire<K_SMALLBANK>;
   const uint8_t type = rec[W::TYPE], table = rec[W::TABLE];
   if (type == 6) {                         // kCommitLog :175-186; log_entry {table@0 key@8 val@16 ver@24}
@@ -255,21 +360,22 @@ DINT_D void apply_one<K_SMALLBANK>(const Ctx& c, uint8_t* rec, uint32_t g, unsig
     return;
   }
   const KvTable& t = c.tbl[table];
-  const uint64_t key = ld_u64_unaligned(rec + W::KEY);
-  const uint64_t h = fasthash64_u64(key);
+  const uint64_t key = ki.key, h = ki.h;
+  const uint32_t g = ki.grp;
+  uint4 v[2] = {pf.v[0], pf.v[1]};
   bool ok = true;
   if (type <= 3) {
-    uint2 s = c.cnt2[g];                   // x = num_ex, y = num_sh
+    uint2 s = pf.s;                        // x = num_ex, y = num_sh
     if (type == 0) {                       // :121-133
-      if (s.x == 0) { s.y++; c.cnt2[g] = s; ok = kv_get_into<8>(t, key, h, rec + W::VAL, rec + W::VER); rec[W::TYPE] = 7; }
+      if (s.x == 0) { s.y++; c.cnt2[g] = s; ok = kv_get_into<8>(t, key, h, v, rec + W::VAL, rec + W::VER); rec[W::TYPE] = 7; }
       else rec[W::TYPE] = 8;
     } else if (type == 1) {                // :135-147
-      if (s.x == 0 && s.y == 0) { s.x++; c.cnt2[g] = s; ok = kv_get_into<8>(t, key, h, rec + W::VAL, rec + W::VER); rec[W::TYPE] = 9; }
+      if (s.x == 0 && s.y == 0) { s.x++; c.cnt2[g] = s; ok = kv_get_into<8>(t, key, h, v, rec + W::VAL, rec + W::VER); rec[W::TYPE] = 9; }
       else rec[W::TYPE] = 10;
     } else if (type == 2) { s.y--; c.cnt2[g] = s; rec[W::TYPE] = 11; }   // :149-154
     else { s.x--; c.cnt2[g] = s; rec[W::TYPE] = 12; }                    // :156-161
   } else {                                 // kCommitPrim :163-167 / kCommitBck :169-173
-    ok = kv_set_from<8>(t, key, h, rec + W::VAL);
+    ok = kv_set_from<8>(t, key, h, v, rec + W::VAL);
     rec[W::TYPE] = (type == 4) ? 13 : 14;
   }
   if (!ok) mark_invalid<K_SMALLBANK>(c, rec);   // smallbank/udp/kvs.h:67,86 panic
@@ -283,8 +389,7 @@ __global__ void __launch_bounds__(256) k_kv_load(const Ctx c, int table, const u
   const KvTable& t = c.tbl[table];
   uint64_t key = keys[i];
   uint64_t h = fasthash64_u64(key);
-  uint32_t g;
-  if (!kv_group(c, table, h, g)) return;        // another shard's key
+  if (kv_group(c, table, h) == kNoGroup) return;   // another shard's key
   uint32_t w[Ent<VALSZ>::NW];
   const uint32_t* src = (const uint32_t*)(vals + (size_t)i * VALSZ);
 #pragma unroll
@@ -295,7 +400,9 @@ __global__ void __launch_bounds__(256) k_kv_load(const Ctx c, int table, const u
 template <int VALSZ>
 __global__ void k_kv_get1(const Ctx c, int table, uint64_t key, uint32_t* out /* [0]=found [1]=ver [2..]=val */) {
   uint4 v[Ent<VALSZ>::NV];
-  uint8_t* e = kv_find<VALSZ>(c.tbl[table], key, fasthash64_u64(key), v);
+  const uint64_t h = fasthash64_u64(key);
+  kv_prefetch_home<VALSZ>(c, table, h, v);
+  uint8_t* e = kv_find<VALSZ>(c.tbl[table], key, h, v);
   out[0] = e ? 1u : 0u;
   if (e) {
     out[1] = v[0].z;

@@ -121,10 +121,12 @@ int dint_load(dint_engine *e, int table, const uint64_t *keys, const void *vals,
  * GPU, copies out, returns when resp is complete.  Returns 0, DINT_EPROTO, or another error. */
 int dint_submit(dint_engine *e, const void *req, uint64_t n, void *resp);
 
-/* Same, with DEVICE arrays (16-byte aligned) and asynchronous on `cuda_stream` (a cudaStream_t; NULL
- * = the engine's own stream).  Errors surface at the next dint_sync()/dint_get_stats(). */
+/* Same, with DEVICE arrays (16-byte aligned), asynchronous on `cuda_stream` (a cudaStream_t; NULL = the
+ * legacy default stream, as everywhere in CUDA).  Successive calls must be issued on streams that
+ * order them (the engine's state is one sequential history).  Request errors surface at the next
+ * dint_sync()/dint_get_stats(). */
 int dint_submit_device(dint_engine *e, const void *req_dev, uint64_t n, void *resp_dev, void *cuda_stream);
-int dint_sync(dint_engine *e);
+int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */
 
 /* ---- state inspection: parity of the final server state, not only of the wire ------------------ */
 /* kvs_get on the device table (store/udp/kvs.h:37-55): 0 = found, 1 = not found. */
