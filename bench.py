@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark (see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's GPU engine
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU server (oracle/_ref)
+
+Metric (BASELINE.json): committed txns/sec on lock_fasst.  Workload at N = 1: the reference's own
+lock_fasst trace shape (lock_fasst/caladan/trace_init.sh: 24,000,000 lock ids, uniform, 5-10 ids per
+transaction, write probability 0.2) driven closed-loop by 1,048,576 logical clients through the FaSST
+protocol of lock_fasst/caladan/client.cc against a 36,000,000-slot lock table ("REF" in SURVEY.md 8(d)).
+One STEP = one batch of 4 client rounds = 4,194,304 wire requests.  Every step replays a DIFFERENT
+segment of one long recorded closed-loop trace (so inputs are never L2-resident from the previous
+step) from a freshly reset server state, and the reply stream of every step is checked bit-for-bit
+against the closed-loop recording.  BASELINE.json's literal "4800 keys, Zipf 0.8" reading ("HOT") and
+the store GET path are measured too and reported under "extra".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIENTS = 1 << 20
+ROUNDS_PER_STEP = 4
+STEP_REQS = CLIENTS * ROUNDS_PER_STEP
+# algorithmic bytes per request: wire in + wire out + state at the reference's field granularity
+FASST_BYTES = {4: 22, 5: 26, 6: 22, 7: 22, 8: 30}          # by reply type
+STORE_GET_BYTES = 186
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                f = [x.strip() for x in line.split(",")]
+                if len(f) == 6:
+                    self.samples.append(f)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.kill()
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def record_closed_loop(eng, wl, n_steps, pinned):
+    """Drive the client state machines against the engine; returns per-step request / reply arrays
+    and per-step committed-transaction counts."""
+    msg = eng.msg
+    reqs = np.empty((n_steps, STEP_REQS * msg), dtype=np.uint8)
+    resps = np.empty_like(reqs)
+    committed = []
+    rq, rs = pinned
+    for s in range(n_steps):
+        before = wl.stats()["committed"]
+        for r in range(ROUNDS_PER_STEP):
+            wl.next(rq.array[: CLIENTS * msg])
+            eng.submit(rq.array[: CLIENTS * msg], out=rs.array[: CLIENTS * msg])
+            wl.feed(rs.array[: CLIENTS * msg])
+            reqs[s, r * CLIENTS * msg:(r + 1) * CLIENTS * msg] = rq.array[: CLIENTS * msg]
+            resps[s, r * CLIENTS * msg:(r + 1) * CLIENTS * msg] = rs.array[: CLIENTS * msg]
+        committed.append(wl.stats()["committed"] - before)
+    return reqs, resps, committed
+
+
+def run_fasst(args, torch, dist, rank, world, fam_name, fam, steps, warmup, do_e2e=True, do_cpu=True):
+    from dint_b200 import Engine, PinnedBuffer, wire
+    from dint_b200.workloads import Workload
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    n_steps = steps + warmup
+    msg = 9
+    pinned = (PinnedBuffer(STEP_REQS * msg), PinnedBuffer(STEP_REQS * msg))
+    # ---- record the closed-loop trace against the GPU engine itself ----
+    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+        wl = Workload(wire.FASST, n_clients=CLIENTS, seed=20230 + rank, **fam)
+        reqs, resps, committed = record_closed_loop(eng, wl, n_steps, pinned)
+        wl_stats = wl.stats()
+    # ---- device-resident replay from a fresh state: the timed region ----
+    out = {}
+    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+        d_req = torch.from_numpy(reqs).to(dev)
+        d_resp = torch.empty((STEP_REQS * msg,), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        ok = True
+        for s in range(warmup):
+            eng.submit_tensor(d_req[s], d_resp)
+        torch.cuda.synchronize(dev)
+        ok &= bool((d_resp.cpu().numpy() == resps[warmup - 1]).all()) if warmup else True
+        eng.reset_stats()
+        eng.profile(True)
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(warmup, n_steps):
+            eng.submit_tensor(d_req[s], d_resp)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        eng.profile(False)
+        kt = eng.kernel_times()
+        st = eng.stats()
+        ok &= bool((d_resp.cpu().numpy() == resps[n_steps - 1]).all())
+        out.update(ms=ms, kernel_times=kt, stats=st, clocks=clocks, parity_last_step=ok)
+        del d_req
+    timed_committed = sum(committed[warmup:])
+    timed_reqs = steps * STEP_REQS
+    out.update(committed=timed_committed, requests=timed_reqs, wl_stats=wl_stats)
+    # algorithmic bytes of the timed region, from the reply types
+    types = np.concatenate([resps[s].reshape(-1, msg)[:, 0] for s in range(warmup, n_steps)])
+    cnt = np.bincount(types, minlength=9)
+    out["alg_bytes"] = int(sum(FASST_BYTES[t] * int(cnt[t]) for t in FASST_BYTES))
+    out["reply_mix"] = {str(t): int(cnt[t]) for t in FASST_BYTES}
+    # ---- end to end through the host-facing C ABI call (pinned host buffers, H2D + D2H inside) ----
+    if do_e2e:
+        with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+            rq, rs = pinned
+            for s in range(warmup):
+                rq.array[:] = reqs[s]
+                eng.submit(rq.array, out=rs.array)
+            host_in = [PinnedBuffer(STEP_REQS * msg) for _ in range(min(steps, 4))]
+            t_e2e, ok2 = 0.0, True
+            for s in range(warmup, n_steps):
+                b = host_in[(s - warmup) % len(host_in)]
+                b.array[:] = reqs[s]                        # staging into pinned memory: not timed
+                if dist is not None:
+                    dist.barrier()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                eng.submit(b.array, out=rs.array)           # timed: H2D + kernels + D2H, returns when resp is complete
+                t_e2e += time.perf_counter() - t0
+                if s == n_steps - 1:
+                    ok2 = bool((rs.array == resps[s]).all())
+            out.update(e2e_s=t_e2e, e2e_parity=ok2)
+    # ---- CPU baseline: the unmodified reference server, one handler thread, bounded sample ----
+    if do_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_baseline(wire.FASST, reqs[0], committed[0] / STEP_REQS, threads=1, target_s=12.0,
+                                           check_against=resps[0])
+    return out
+
+
+def cpu_baseline(kind, sample_req, txn_per_req, threads, target_s, check_against=None):
+    """Time oracle/_ref (the reference's own server.cc under the replay shim) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    if not O.ref_available(kind):
+        # the C restatement, timed in-process ("port")
+        ora = O.Oracle(kind)
+        t0 = time.perf_counter()
+        ora.process(sample_req)
+        dt = time.perf_counter() - t0
+        n = sample_req.size // O.MSG_SIZE[kind]
+        return {"value": n / dt * txn_per_req, "unit": "txn/s", "cores": 1, "kind": "port",
+                "sample": f"{n} requests once through oracle/libdint_oracle.so", "req_per_s": n / dt}
+    n = sample_req.size // O.MSG_SIZE[kind]
+    # calibrate the repeat count on one pass
+    out, st = O.run_ref(kind, sample_req, threads=1, repeat=1, want_out=check_against is not None)
+    parity = None
+    if check_against is not None:
+        parity = bool(np.array_equal(out, check_against))
+    rate1 = st["req_per_s"]
+    repeat = max(1, int(target_s * rate1 * max(1, threads) * 0.7 / n))
+    _, st = O.run_ref(kind, sample_req, threads=threads, repeat=repeat, want_out=False, spread=threads > 1)
+    return {"value": st["req_per_s"] * txn_per_req, "unit": "txn/s", "cores": threads, "kind": "reference",
+            "sample": f"first step of the trace ({n} requests) x {repeat} passes through oracle/_ref "
+                      f"`server {threads}` under the replay shim ({st['seconds']:.1f} s)",
+            "req_per_s": st["req_per_s"], "gpu_replies_equal_reference": parity}
+
+
+def run_store_get(args, torch, rank, steps, warmup):
+    """The store lookup path: 100 % kRead, NURand keys over the reference's 24 M-key population."""
+    from dint_b200 import Engine, wire
+    from dint_b200.workloads import Workload
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    n = 1 << 22
+    wl = Workload(wire.STORE, n_clients=n, seed=1 + rank)
+    with Engine(wire.STORE, device=dev.index, chunk=args.chunk, populate=True) as eng:
+        bufs = [torch.from_numpy(wl.next().copy()).to(dev) for _ in range(steps + warmup)]   # open-loop: no feedback needed
+        d_out = torch.empty_like(bufs[0])
+        for s in range(warmup):
+            eng.submit_tensor(bufs[s], d_out)
+        torch.cuda.synchronize(dev)
+        eng.reset_stats()
+        eng.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(warmup, warmup + steps):
+            eng.submit_tensor(bufs[s], d_out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        eng.profile(False)
+        kt = eng.kernel_times()
+        hits = int((d_out.view(-1, 53)[:, 0] == 3).sum().item())
+    peak, how = peaks()
+    l, t = kt["k_apply"]
+    ach = STORE_GET_BYTES * n * steps / l / (t / l * 1e-3) / 1e9
+    return {"workload": "store kRead, NURand keys, 24,000,000-key table (reference population), device-resident",
+            "get_per_s": n * steps / (ms * 1e-3), "hit_fraction_last_step": hits / n,
+            "roofline": {"kernel": "k_apply<store>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "peak_source": how, "avg_launch_us": t / l * 1e3},
+            "kernel_ms": {k: v[1] for k, v in kt.items()}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dint_b200", choices=["dint_b200", "reference"])
+    ap.add_argument("--chunk", type=int, default=1 << 20)
+    ap.add_argument("--no-extra", action="store_true", help="skip the HOT and store GET side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "dint_b200" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        return main_reference(args, rank, world)
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (dint_b200 has no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    from dint_b200.workloads import REF, HOT
+
+    if world > 1:
+        from dint_b200 import shard
+        res = shard.bench_fasst_sharded(args, torch, dist, rank, world, REF)
+    else:
+        res = run_fasst(args, torch, dist, rank, world, "REF", REF, args.steps, args.warmup)
+
+    # reduce over ranks: time = max, work = sum
+    ms, committed, reqs = res["ms"], res["committed"], res["requests"]
+    e2e_s = res.get("e2e_s")
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s or 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w = torch.tensor([committed, reqs, res["stats"]["kernel_launches"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(t[0]), float(t[1]) or None
+        committed, reqs, launches = int(w[0]), int(w[1]), int(w[2])
+    else:
+        launches = res["stats"]["kernel_launches"]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_how = peaks()
+    kt = res["kernel_times"]
+    dom = max(kt.items(), key=lambda kv: kv[1][1])
+    name, (nl, tot_ms) = dom
+    avg_s = tot_ms / nl * 1e-3
+    alg_per_launch = res["alg_bytes"] / nl
+    achieved = alg_per_launch / avg_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(name + "<lock_fasst>")
+    line = {
+        "metric": "committed txns/sec (lock_fasst)", "value": committed / (ms * 1e-3), "unit": "txn/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "lock_fasst REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(write)=0.2, closed-loop "
+                               "FaSST clients (read/acquire/validate/commit), 36,000,000-slot table; "
+                               f"{CLIENTS} logical clients per GPU, {ROUNDS_PER_STEP} rounds = {STEP_REQS} requests per step per GPU",
+                   "requests_per_step": STEP_REQS * world, "chunk": args.chunk,
+                   "cache": "every step replays a different 37.7 MB trace segment (inputs larger than reuse distance; "
+                            "lock/version tables 148.5 MB > 126 MB L2)",
+                   "parallelism": f"key-space sharded x{world}" if world > 1 else "single GPU"},
+        "requests_per_s": reqs / (ms * 1e-3),
+        "replies_bit_exact_vs_closed_loop_recording": bool(res["parity_last_step"]),
+        "abort_stats": {k: res["wl_stats"][k] for k in ("committed", "validation_aborts", "lock_rejects")},
+        "conflicted_fraction": res["stats"]["conflicted"] / max(1, res["stats"]["requests"]),
+        "clocks": res["clocks"],
+        "gpu_launches": launches,
+        "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_how,
+                     "avg_launch_us": avg_s * 1e6, "launches": nl, "algorithmic_bytes_per_launch": alg_per_launch,
+                     "all_kernels_ms": {k: round(v[1], 3) for k, v in kt.items()}},
+    }
+    if e2e_s:
+        line["e2e"] = {"value": committed / e2e_s, "unit": "txn/s", "h2d_bytes_per_step": STEP_REQS * 9 * world,
+                       "d2h_bytes_per_step": STEP_REQS * 9 * world, "requests_per_s": reqs / e2e_s,
+                       "replies_bit_exact": bool(res.get("e2e_parity", False)),
+                       "path": "dint_submit(): pinned host wire structs -> H2D -> kernels -> D2H, per step"}
+    if "cpu_baseline" in res:
+        line["cpu_baseline"] = res["cpu_baseline"]
+    if not args.no_extra and world == 1:
+        try:
+            hot = run_fasst(args, torch, None, rank, world, "HOT", HOT, max(3, args.steps // 3), 3, do_e2e=False, do_cpu=False)
+            line["extra"] = {"lock_fasst_HOT": {
+                "workload": "BASELINE.json literal: 4800 lock ids, Zipf 0.8, same clients/protocol",
+                "txn_per_s": hot["committed"] / (hot["ms"] * 1e-3), "requests_per_s": hot["requests"] / (hot["ms"] * 1e-3),
+                "abort_stats": {k: hot["wl_stats"][k] for k in ("committed", "validation_aborts", "lock_rejects")},
+                "conflicted_fraction": hot["stats"]["conflicted"] / max(1, hot["stats"]["requests"]),
+                "replies_bit_exact": bool(hot["parity_last_step"])}}
+            line["extra"]["store_get"] = run_store_get(args, torch, rank, max(3, args.steps // 2), 3)
+        except Exception as ex:  # side measurements must never cost the headline line
+            line.setdefault("extra", {})["error"] = repr(ex)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main_reference(args, rank, world):
+    """--impl reference: the reference's own lock_fasst UDP server (oracle/_ref, built from
+    /root/reference unmodified), all host threads, same trace shape / metric."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from dint_b200 import wire
+    from dint_b200.workloads import Workload, REF
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # the same closed-loop trace shape, recorded against the CPU restatement (no GPU needed on this arm)
+    clients, rounds = 1 << 18, 8
+    ora = O.Oracle(wire.FASST)
+    wl = Workload(wire.FASST, n_clients=clients, seed=20230, **REF)
+    reqs = []
+    for _ in range(rounds):
+        r = wl.next()
+        wl.feed(ora.process(r))
+        reqs.append(r.copy())
+    sample = np.concatenate(reqs)
+    st = wl.stats()
+    txn_per_req = st["committed"] / st["requests"]
+    n = sample.size // 9
+    kind = "reference" if O.ref_available(wire.FASST) else "port"
+    steps, times, reqs_done = args.steps, [], 0
+    for s in range(args.warmup + steps):
+        if kind == "reference":
+            _, stt = O.run_ref(wire.FASST, sample, threads=cores, repeat=max(1, cores // 2), want_out=False, spread=True)
+            dt, nn = stt["seconds"], stt["requests"]
+        else:
+            t0 = time.perf_counter(); O.Oracle(wire.FASST).process(sample); dt = time.perf_counter() - t0; nn = n
+        if s >= args.warmup:
+            times.append(dt); reqs_done += nn
+    total = sum(times)
+    val = reqs_done / total * txn_per_req
+    line = {"impl": "reference", "metric": "committed txns/sec (lock_fasst)", "value": val, "unit": "txn/s",
+            "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": total / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "lock_fasst REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(write)=0.2, closed-loop "
+                                   "FaSST clients, 36,000,000-slot table",
+                       "note": "handler only: the reference server.cc under the LD_PRELOAD replay shim (no UDP syscalls), "
+                               f"`server {cores}` re-pinned one thread per host core; a step = {n} requests x {max(1, cores // 2)} passes"},
+            "requests_per_s": reqs_done / total,
+            "cpu_baseline": {"value": val, "unit": "txn/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+                             "sample": f"{n}-request closed-loop trace x {max(1, cores // 2)} passes per step"},
+            "e2e": {"value": val, "unit": "txn/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,9 @@
 //  * TMA (cp.async.bulk) 1-D staging of a tile of wire records global<->shared.
 #pragma once
 #include <cstdint>
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#endif
 
 #ifndef __CUDACC__
 #define __host__

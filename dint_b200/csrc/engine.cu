@@ -386,6 +386,26 @@ int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
   return DINT_OK;
 }
 
+int dint_route_owner(dint_engine* e, const void* req_dev, uint64_t n, uint8_t* owner_dev, void* cuda_stream) {
+  if (!e || (n && (!req_dev || !owner_dev)) || n > 0xffffffffULL) return set_err(DINT_EINVAL, "bad argument");
+  if (n == 0) return DINT_OK;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const uint32_t blocks = (uint32_t)((n + kThreads - 1) / kThreads);
+  const uint8_t* rq = (const uint8_t*)req_dev;
+  e->stats.kernel_launches++;
+  switch (e->kind) {
+    case DINT_LOCK2PL: k_route_owner<K_LOCK2PL><<<blocks, kThreads, 0, s>>>(e->ctx, rq, (uint32_t)n, owner_dev); break;
+    case DINT_FASST: k_route_owner<K_FASST><<<blocks, kThreads, 0, s>>>(e->ctx, rq, (uint32_t)n, owner_dev); break;
+    case DINT_LOG: k_route_owner<K_LOG><<<blocks, kThreads, 0, s>>>(e->ctx, rq, (uint32_t)n, owner_dev); break;
+    case DINT_STORE: k_route_owner<K_STORE><<<blocks, kThreads, 0, s>>>(e->ctx, rq, (uint32_t)n, owner_dev); break;
+    case DINT_TATP: k_route_owner<K_TATP><<<blocks, kThreads, 0, s>>>(e->ctx, rq, (uint32_t)n, owner_dev); break;
+    default: k_route_owner<K_SMALLBANK><<<blocks, kThreads, 0, s>>>(e->ctx, rq, (uint32_t)n, owner_dev); break;
+  }
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
 int dint_sync(dint_engine* e) {
   if (!e) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));

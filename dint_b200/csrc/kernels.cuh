@@ -97,6 +97,31 @@ DINT_D uint8_t* acquire_tile(const Ctx& c, uint8_t* smem, uint64_t* full, const 
   return tile;
 }
 
+// owner shard of every request (multi-GPU routing; see dint_route_owner)
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uint8_t* req, uint32_t n, uint8_t* owner) {
+  using W = Wire<KIND>;
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* rec = req + (size_t)i * W::MSG;
+  const TypeInfo ti = type_info<KIND>(rec);
+  uint32_t o = c.shard_id;                          // no per-key state touched: serve it where it arrived
+  if (!ti.invalid && ti.mask) {
+    uint32_t gglobal;                               // the slot / bucket / lock_hash ONE server would compute
+    if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) {
+      gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
+    } else if constexpr (KIND == K_STORE) {
+      gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[0].lock_mod);
+    } else if constexpr (KIND == K_TATP || KIND == K_SMALLBANK) {
+      gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[rec[W::TABLE]].lock_mod);
+    } else {
+      gglobal = c.shard_id;
+    }
+    o = gglobal - (uint32_t)fast_div(gglobal, c.shard_div) * c.n_shards;
+  }
+  owner[i] = (uint8_t)o;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1 classify (+ clears the flag words of the previous chunk)
 // ---------------------------------------------------------------------------------------------------

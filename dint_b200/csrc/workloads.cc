@@ -24,6 +24,8 @@
 #include <cstring>
 #include <vector>
 
+#include "common.cuh"   // fasthash64 / exact fast modulo, shared with the device code
+
 extern "C" {
 typedef struct dint_wl_cfg {
   uint32_t kind;        // enum dint_kind (0 lock_2pl, 1 lock_fasst, 2 log, 3 store)
@@ -281,6 +283,42 @@ void dint_wl_feed(dint_wl* w, const void* resp) {
 void dint_wl_stats(const dint_wl* w, uint64_t out[6]) {
   out[0] = w->st_requests; out[1] = w->st_committed; out[2] = w->st_validation_aborts;
   out[3] = w->st_lock_rejects; out[4] = w->st_not_exist; out[5] = w->st_rounds;
+}
+
+// Host twin of dint_route_owner (used by the gloo / CPU tests of the sharded routing logic):
+// owner[i] = (fasthash64(key) % mods[table]) % n_shards for requests that touch per-key state, else `self`.
+// kind: enum dint_kind (0..5); mods: group modulus per table (lock kinds: mods[0] = lock_slots).
+void dint_wl_owner(uint32_t kind, const uint32_t* mods, uint32_t n_shards, uint32_t self, const void* req, uint64_t n,
+                   uint8_t* owner) {
+  static const uint32_t msg[6] = {6, 9, 53, 53, 55, 23};
+  const uint8_t* p = (const uint8_t*)req;
+  for (uint64_t i = 0; i < n; i++, p += msg[kind]) {
+    uint32_t o = self;
+    bool keyed = false;
+    uint32_t table = 0;
+    uint64_t h = 0;
+    switch (kind) {
+      case 0: keyed = p[0] <= 1 && !(p[0] == 0 && p[5] > 1); if (keyed) { uint32_t k; memcpy(&k, p + 1, 4); h = dint::fasthash64_u32(k); } break;
+      case 1: keyed = p[0] <= 3; if (keyed) { uint32_t k; memcpy(&k, p + 1, 4); h = dint::fasthash64_u32(k); } break;
+      case 2: break;
+      case 3: keyed = p[0] <= 2; if (keyed) { uint64_t k; memcpy(&k, p + 1, 8); h = dint::fasthash64_u64(k); } break;
+      case 4: {
+        const uint8_t t = p[1];
+        table = p[2];
+        keyed = table < 5 && (t <= 2 || t == 12 || t == 13 || t == 18 || t == 19 || t == 22 || t == 23);
+        if (keyed) { uint64_t k; memcpy(&k, p + 3, 8); h = dint::fasthash64_u64(k); }
+        break;
+      }
+      default: {
+        table = p[2];
+        keyed = table < 2 && p[1] <= 5;
+        if (keyed) { uint64_t k; memcpy(&k, p + 3, 8); h = dint::fasthash64_u64(k); }
+        break;
+      }
+    }
+    if (keyed) o = (uint32_t)((h % mods[table]) % n_shards);
+    owner[i] = (uint8_t)o;
+  }
 }
 
 }  // extern "C"

@@ -37,7 +37,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod",
@@ -64,6 +64,7 @@ def lib():
     L.dint_load.restype = i32; L.dint_load.argtypes = [vp, i32, vp, vp, u64]
     L.dint_submit.restype = i32; L.dint_submit.argtypes = [vp, vp, u64, vp]
     L.dint_submit_device.restype = i32; L.dint_submit_device.argtypes = [vp, vp, u64, vp, vp]
+    L.dint_route_owner.restype = i32; L.dint_route_owner.argtypes = [vp, vp, u64, vp, vp]
     L.dint_sync.restype = i32; L.dint_sync.argtypes = [vp]
     L.dint_kv_get.restype = i32; L.dint_kv_get.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]
     L.dint_kv_count.restype = C.c_int64; L.dint_kv_count.argtypes = [vp, i32]
@@ -207,6 +208,18 @@ class Engine:
         s = stream if stream is not None else torch.cuda.current_stream(req.device).cuda_stream
         self.submit_device(req.data_ptr(), n, out.data_ptr(), s)
         return out
+
+    def route_owner(self, req, stream=None):
+        """owner shard (uint8 CUDA tensor) of every wire record in the CUDA uint8 tensor `req`."""
+        import torch
+        n = req.numel() // self.msg
+        owner = torch.empty(n, dtype=torch.uint8, device=req.device)
+        s = stream if stream is not None else torch.cuda.current_stream(req.device).cuda_stream
+        rc = lib().dint_route_owner(self.h, C.c_void_p(req.data_ptr()), n, C.c_void_p(owner.data_ptr()),
+                                    C.c_void_p(s) if s else None)
+        if rc != 0:
+            raise DintError(rc, "dint_route_owner")
+        return owner
 
     def sync(self, check=True):
         rc = lib().dint_sync(self.h)

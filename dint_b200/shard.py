@@ -1,0 +1,210 @@
+"""Key-space sharding over the GPUs of one box: one process per GPU (torchrun), torch.distributed for the
+plumbing (NCCL on GPUs, gloo in the CPU tests).
+
+The reference shards on the CLIENT (key % 3, tatp/caladan/client_udp_shard.cc:187) and its servers never
+talk to each other.  Here every rank receives an arbitrary slice of the request stream, and the engine
+routes each request to the shard that owns its lock slot / bucket:
+
+    owner      = slot % world                       slot = fasthash64(key) % table_size, exactly the slot
+                                                    ONE reference server would use, so collisions are unchanged
+    dispatch   = stable partition by owner -> all-to-all (variable counts) of fixed-size wire records
+    local step = the shard's Engine (n_shards = world, shard_id = rank) on what it received
+    combine    = all-to-all back -> inverse permutation
+
+Order rule for bit-exactness: the global request order is rank-major (rank 0's slice first); a stable
+partition keeps that order inside every destination, and all_to_all concatenates sources in rank order,
+so each shard sees its requests in global order.  The result equals ONE sequential server processing
+the concatenation of all ranks' slices.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import wire
+from .engine import Engine, default_cfg
+
+
+def group_moduli(kind, cfg):
+    """Group modulus per table, as the engine derives it (kv.cuh kv_create_tables)."""
+    S, A = cfg.subs_sizing, cfg.accts_sizing
+    if kind in (wire.LOCK2PL, wire.FASST):
+        return [cfg.lock_slots, 1, 1, 1, 1]
+    if kind == wire.STORE:
+        return [S * 18 // 4, 1, 1, 1, 1]
+    if kind == wire.TATP:
+        return [4 * (S * 3 // 2 // 4), 4 * (S * 3 // 2 // 4), 4 * (S * 15 // 4 // 4), 4 * (S * 15 // 4 // 4), 4 * (S * 45 // 8 // 4)]
+    if kind == wire.SMALLBANK:
+        return [4 * (A * 3 // 2 // 4)] * 2 + [1, 1, 1]
+    return [1] * 5
+
+
+def owners_cpu(kind, cfg, world, rank, req):
+    """Host twin of Engine.route_owner (libdint_wl.so), for the gloo tests."""
+    from .workloads import lib as wl_lib
+    L = wl_lib()
+    L.dint_wl_owner.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.dint_wl_owner.restype = None
+    mods = (C.c_uint32 * 5)(*group_moduli(kind, cfg))
+    raw = np.ascontiguousarray(req, dtype=np.uint8).reshape(-1)
+    n = raw.size // wire.MSG_SIZE[kind]
+    out = np.empty(n, dtype=np.uint8)
+    L.dint_wl_owner(kind, mods, world, rank, raw.ctypes.data, n, out.ctypes.data)
+    return out
+
+
+class ShardedEngine:
+    """Collective engine: every rank calls submit*() with its slice of the request stream.
+
+    local_submit (optional) replaces the GPU engine by any callable req_bytes -> resp_bytes (the CPU tests
+    plug the oracle in to check the routing logic without a GPU)."""
+
+    def __init__(self, kind, device=None, local_submit=None, group=None, **cfg_over):
+        self.kind = kind
+        self.msg = wire.MSG_SIZE[kind]
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.cfg = default_cfg(kind, **cfg_over) if local_submit is None else None
+        self._cfg_over = cfg_over
+        self.local_submit = local_submit
+        self.engine = None
+        if local_submit is None:
+            self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+            self.engine = Engine(kind, device=self.device.index, n_shards=self.world, shard_id=self.rank, **cfg_over)
+        else:
+            self.device = torch.device("cpu")
+            from . import engine as _e
+            self.cfg = _e.DintCfg()
+            # only the sizing fields matter for routing
+            self.cfg.lock_slots = cfg_over.get("lock_slots", 36000000)
+            self.cfg.subs_sizing = cfg_over.get("subs_sizing", 7000000 if kind == wire.TATP else 2000000)
+            self.cfg.accts_sizing = cfg_over.get("accts_sizing", 24000000)
+        self.last_route_ms = 0.0
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    def populate(self):
+        self.engine.populate()       # dint_load keeps only this shard's keys
+
+    # ---- the collective request path -------------------------------------------------------------
+    def submit_tensor(self, req):
+        """req: uint8 tensor [n * msg] on this rank's device; returns the replies, same layout/order."""
+        n = req.numel() // self.msg
+        rec = req.view(n, self.msg)
+        if self.engine is not None:
+            owner = self.engine.route_owner(req)
+        else:
+            owner = torch.from_numpy(owners_cpu(self.kind, self.cfg, self.world, self.rank, req.numpy()))
+        # dispatch: stable partition by owner
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner.long(), minlength=self.world)[: self.world]
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()        # host sync: split sizes
+        send = rec.index_select(0, order).contiguous()
+        m = int(sum(rc))
+        recv = torch.empty((m, self.msg), dtype=torch.uint8, device=req.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+        # local step
+        if self.engine is not None:
+            out_local = torch.empty_like(recv)
+            if m:
+                self.engine.submit_tensor(recv.view(-1), out_local.view(-1))
+        else:
+            out_local = torch.from_numpy(np.asarray(self.local_submit(recv.numpy().reshape(-1)))).view(m, self.msg) if m else recv
+        # combine
+        back = torch.empty((n, self.msg), dtype=torch.uint8, device=req.device)
+        dist.all_to_all_single(back, out_local.contiguous(), output_split_sizes=sc, input_split_sizes=rc, group=self.group)
+        out = torch.empty_like(rec)
+        out.index_copy_(0, order, back)
+        return out.view(-1)
+
+    def submit(self, req_host):
+        """Host path: numpy uint8 in, numpy uint8 out (H2D, collective device step, D2H)."""
+        t = torch.from_numpy(np.ascontiguousarray(req_host, dtype=np.uint8).reshape(-1))
+        if self.engine is not None:
+            t = t.to(self.device, non_blocking=True)
+        out = self.submit_tensor(t)
+        return out.cpu().numpy()
+
+
+def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
+    """bench.py at N > 1: every rank drives its own 1,048,576 logical clients; requests are routed to the
+    owning shard over NCCL.  Returns the same result dict as bench.run_fasst."""
+    import time
+    from .workloads import Workload
+    import bench as B
+    dev = torch.device("cuda", torch.cuda.current_device())
+    steps, warmup = args.steps, max(args.warmup, 3)
+    n_steps = steps + warmup
+    msg = 9
+    se = ShardedEngine(wire.FASST, chunk=args.chunk)
+    wl = Workload(wire.FASST, n_clients=B.CLIENTS, seed=20230 + rank, **fam)
+    reqs = np.empty((n_steps, B.STEP_REQS * msg), dtype=np.uint8)
+    resps = np.empty_like(reqs)
+    committed = []
+    for s in range(n_steps):
+        before = wl.stats()["committed"]
+        for r in range(B.ROUNDS_PER_STEP):
+            q = wl.next()
+            a = se.submit(q)
+            wl.feed(a)
+            reqs[s, r * B.CLIENTS * msg:(r + 1) * B.CLIENTS * msg] = q
+            resps[s, r * B.CLIENTS * msg:(r + 1) * B.CLIENTS * msg] = a
+        committed.append(wl.stats()["committed"] - before)
+    wl_stats = wl.stats()
+    se.close()
+    # timed replay from fresh shards
+    se = ShardedEngine(wire.FASST, chunk=args.chunk)
+    d_req = torch.from_numpy(reqs).to(dev)
+    last = None
+    for s in range(warmup):
+        last = se.submit_tensor(d_req[s])
+    torch.cuda.synchronize(dev)
+    se.engine.reset_stats()
+    se.engine.profile(True)
+    sampler = B.ClockSampler(dev.index)
+    sampler.start()
+    dist_mod.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(warmup, n_steps):
+        last = se.submit_tensor(d_req[s])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dist_mod.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    se.engine.profile(False)
+    ok = bool((last.cpu().numpy() == resps[n_steps - 1]).all())
+    out = dict(ms=ms, kernel_times=se.engine.kernel_times(), stats=se.engine.stats(), clocks=clocks, parity_last_step=ok,
+               committed=sum(committed[warmup:]), requests=steps * B.STEP_REQS, wl_stats=wl_stats)
+    types = np.concatenate([resps[s].reshape(-1, msg)[:, 0] for s in range(warmup, n_steps)])
+    cnt = np.bincount(types, minlength=9)
+    out["alg_bytes"] = int(sum(B.FASST_BYTES[t] * int(cnt[t]) for t in B.FASST_BYTES))
+    # end to end: pinned host -> device -> collective step -> host
+    t_e2e = 0.0
+    se.close()
+    se = ShardedEngine(wire.FASST, chunk=args.chunk)
+    pin = torch.empty(B.STEP_REQS * msg, dtype=torch.uint8).pin_memory()
+    pout = torch.empty_like(pin).pin_memory()
+    for s in range(n_steps):
+        pin.numpy()[:] = reqs[s]
+        dist_mod.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        d = pin.to(dev, non_blocking=True)
+        o = se.submit_tensor(d)
+        pout.copy_(o, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        if s >= warmup:
+            t_e2e += time.perf_counter() - t0
+    out.update(e2e_s=t_e2e, e2e_parity=bool((pout.numpy() == resps[n_steps - 1]).all()))
+    se.close()
+    return out

@@ -126,6 +126,11 @@ int dint_submit(dint_engine *e, const void *req, uint64_t n, void *resp);
  * order them (the engine's state is one sequential history).  Request errors surface at the next
  * dint_sync()/dint_get_stats(). */
 int dint_submit_device(dint_engine *e, const void *req_dev, uint64_t n, void *resp_dev, void *cuda_stream);
+/* Multi-GPU routing helper: owner[i] = shard that owns request i's group
+ * (lock slot / bucket: fasthash64 % size % n_shards -- the same modulus the single server would use, so
+ * collision behaviour is unchanged by sharding); 0xFF for records no shard owns (invalid / log-only
+ * requests are served by whoever receives them: owner = shard_id).  Device pointers, async on stream. */
+int dint_route_owner(dint_engine *e, const void *req_dev, uint64_t n, uint8_t *owner_dev, void *cuda_stream);
 int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */
 
 /* ---- state inspection: parity of the final server state, not only of the wire ------------------ */
