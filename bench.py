@@ -43,37 +43,42 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~1 ms period; the timed region
+    is only tens of milliseconds long, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.max_mhz = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                f = [x.strip() for x in line.split(",")]
-                if len(f) == 6:
-                    self.samples.append(f)
-        except Exception:
-            pass
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                try:
+                    reasons = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), reasons))
+                time.sleep(0.001)
+        except Exception as ex:       # no NVML: report that rather than inventing numbers
+            self.samples.append((None, repr(ex)))
 
     def stop(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.kill()
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        self.join(timeout=2)
+        sm = sorted(s[0] for s in self.samples if isinstance(s[0], int))
+        bits = 0
+        for s in self.samples:
+            if isinstance(s[1], int):
+                bits |= s[1]
+        # NVML reason bits: 0x8 hw_slowdown, 0x40 hw_thermal_slowdown, 0x20 sw_thermal_slowdown, 0x4 sw_power_cap
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in names.items() if bits & b], "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -125,6 +130,7 @@ def run_fasst(args, torch, dist, rank, world, fam_name, fam, steps, warmup, do_e
         eng.profile(True)
         sampler = ClockSampler(dev.index)
         sampler.start()
+        time.sleep(0.01)
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -175,8 +181,8 @@ def run_fasst(args, torch, dist, rank, world, fam_name, fam, steps, warmup, do_e
             out.update(e2e_s=t_e2e, e2e_parity=ok2)
     # ---- CPU baseline: the unmodified reference server, one handler thread, bounded sample ----
     if do_cpu and rank == 0:
-        out["cpu_baseline"] = cpu_baseline(wire.FASST, reqs[0], committed[0] / STEP_REQS, threads=1, target_s=12.0,
-                                           check_against=resps[0])
+        out["cpu_baseline"] = cpu_baseline(wire.FASST, reqs[0], wl_stats["committed"] / wl_stats["requests"], threads=1,
+                                           target_s=12.0, check_against=resps[0])
     return out
 
 
@@ -246,8 +252,8 @@ def run_store_get(args, torch, rank, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dint_b200", choices=["dint_b200", "reference"])
     ap.add_argument("--chunk", type=int, default=1 << 20)
     ap.add_argument("--no-extra", action="store_true", help="skip the HOT and store GET side measurements")
@@ -360,7 +366,7 @@ def main_reference(args, rank, world):
     from dint_b200.workloads import Workload, REF
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # the same closed-loop trace shape, recorded against the CPU restatement (no GPU needed on this arm)
-    clients, rounds = 1 << 18, 8
+    clients, rounds = 1 << 16, 48          # long enough for transactions to complete (>= 11 rounds each)
     ora = O.Oracle(wire.FASST)
     wl = Workload(wire.FASST, n_clients=clients, seed=20230, **REF)
     reqs = []

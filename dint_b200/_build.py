@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
               ["-o", LIB, os.path.join(CSRC, "engine.cu")]
         subprocess.run(cmd, check=True)
-    wl_src = [os.path.join(CSRC, "workloads.cc")]
-    if os.path.exists(wl_src[0]) and (force or _newer(WL_LIB, wl_src + _sources((".h",)))):
+    wl_src = [os.path.join(CSRC, "workloads.cc"), os.path.join(CSRC, "txn_workloads.cc")]
+    if os.path.exists(wl_src[0]) and (force or _newer(WL_LIB, wl_src + _sources((".h", ".cuh")))):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", WL_LIB] + wl_src, check=True)
     return LIB

@@ -59,6 +59,12 @@ struct dint_engine {
   uint32_t* d_grp[2] = {nullptr, nullptr};   // group ids of the current / previous chunk
   uint64_t chunk_seq = 0;
   uint32_t prev_n = 0;                       // requests of the previous chunk whose flags are still set
+  // L2 persistence: the flag sets (+ lock_fasst lock bits) live in one arena that every launch maps
+  // with a persisting access-policy window, so the streaming request/reply traffic cannot evict it
+  uint8_t* hot_arena = nullptr;
+  size_t hot_bytes = 0;
+  bool use_window = false;
+  cudaAccessPolicyWindow window{};
   // stats
   dint_stats stats{};
   unsigned long long counters_seen[4] = {0, 0, 0, 0};
@@ -116,6 +122,23 @@ struct ProfScope {
 };
 
 // ---- per-chunk launch sequence ------------------------------------------------------------------------
+template <typename... Args>
+static cudaError_t launch_ex(dint_engine* e, void (*kern)(Args...), int grid, size_t smem, cudaStream_t s, bool coop,
+                             Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid < 1 ? 1 : grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (coop) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
+  if (e->use_window) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = e->window; na++; }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int KIND, bool HAS_LOG>
 static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
@@ -123,7 +146,7 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
     int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kThreads - 1) / (4 * kThreads));
     if (clr > want) want = clr;
     int grid = want < e->grid_classify ? want : e->grid_classify;
-    k_classify<KIND, HAS_LOG><<<grid < 1 ? 1 : grid, kThreads, e->smem_stage, s>>>(c);
+    CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, e->smem_stage, s, false, c));
   }
   if (HAS_LOG) {
     ProfScope ps(e, s, KT_LOGSCAN);
@@ -132,12 +155,11 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
     ProfScope ps(e, s, KT_APPLY);
     int grid = (int)c.n_tiles < e->grid_apply ? (int)c.n_tiles : e->grid_apply;
-    k_apply<KIND, HAS_LOG><<<grid, kThreads, e->smem_stage, s>>>(c);
+    CU(launch_ex(e, k_apply<KIND, HAS_LOG>, grid, e->smem_stage, s, false, c));
   }
   if (KIND != K_LOG) {   // the log server has no per-key state: nothing to order
     ProfScope ps(e, s, KT_ORDERED);
-    void* args[] = {(void*)&c};
-    CU(cudaLaunchCooperativeKernel((void*)k_ordered<KIND>, dim3(e->coop_grid), dim3(kThreads), args, 0, s));
+    CU(launch_ex(e, k_ordered<KIND>, e->coop_grid, 0, s, true, c));
   }
   CU(cudaGetLastError());
   return DINT_OK;
@@ -285,8 +307,7 @@ static int create_impl(dint_engine* e) {
       break;
     case DINT_FASST:
       groups = local_groups(cf.lock_slots);
-      if ((rc = dalloc(e, &c.lockbits, (groups + 31) / 32))) return rc;
-      if ((rc = dalloc(e, &c.ver, groups))) return rc;
+      if ((rc = dalloc(e, &c.ver, groups))) return rc;     // lock bits: in the hot arena, below
       break;
     case DINT_LOG:
       groups = 0;
@@ -308,8 +329,31 @@ static int create_impl(dint_engine* e) {
     uint32_t fl = 25;                                  // 2^25 nibbles = 16 MB per set: L2-resident
     while (fl > 10 && (1ULL << (fl - 1)) >= groups * 2 + 2048) fl--;   // tiny group spaces need less
     c.flags_mask = (1u << fl) - 1;
-    for (int i = 0; i < 2; i++)
-      if ((rc = dalloc(e, &e->d_flags[i], (size_t)1 << (fl - 3)))) return rc;
+    const size_t set_bytes = (size_t)4 << (fl - 3);
+    const size_t lock_bytes = (e->kind == DINT_FASST) ? (((groups + 31) / 32) * 4 + 255) / 256 * 256 : 0;
+    e->hot_bytes = 2 * set_bytes + lock_bytes;
+    if ((rc = dalloc(e, &e->hot_arena, e->hot_bytes))) return rc;
+    e->d_flags[0] = (uint32_t*)e->hot_arena;
+    e->d_flags[1] = (uint32_t*)(e->hot_arena + set_bytes);
+    if (lock_bytes) c.lockbits = (uint32_t*)(e->hot_arena + 2 * set_bytes);
+    // reserve L2 for it
+    int max_persist = 0, max_win = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+    const char* env = getenv("DINT_L2_PERSIST");
+    if ((!env || atoi(env) != 0) && max_persist > 0 && max_win > 0) {
+      size_t want = e->hot_bytes < (size_t)max_persist ? e->hot_bytes : (size_t)max_persist;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        e->window.base_ptr = e->hot_arena;
+        e->window.num_bytes = e->hot_bytes < (size_t)max_win ? e->hot_bytes : (size_t)max_win;
+        e->window.hitRatio = (float)((double)want / (double)e->window.num_bytes > 1.0 ? 1.0 : (double)want / (double)e->window.num_bytes);
+        e->window.hitProp = cudaAccessPropertyPersisting;
+        e->window.missProp = cudaAccessPropertyStreaming;
+        e->use_window = true;
+      } else cudaGetLastError();
+    }
+    const char* g = getenv("DINT_L2_FETCH");
+    if (g) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); cudaGetLastError(); }
   }
   uint32_t bits = 1;
   while ((1ULL << bits) < groups) bits++;

@@ -1,0 +1,65 @@
+"""-m gpu, needs >= 2 GPUs: the real NCCL path of dint_b200.shard with one GPU engine per rank, against ONE
+sequential oracle fed the rank-major concatenation."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, kind, n_per_rank, ret):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    import oracle_lib as O
+    import trace_gen as T
+    from dint_b200 import wire
+    from dint_b200.shard import ShardedEngine
+    try:
+        if kind == wire.FASST:
+            mk, cfg = (lambda r: T.fasst_random(n_per_rank, 3000, seed=5 + r)), {}
+        elif kind == wire.LOCK2PL:
+            mk, cfg = (lambda r: T.lock2pl_random(n_per_rank, 500, seed=5 + r)), {}
+        else:
+            mk, cfg = (lambda r: T.store_random(n_per_rank, 400, seed=5 + r)), dict(subs_populate=400)
+        se = ShardedEngine(kind, chunk=1 << 13, **cfg)
+        if kind == wire.STORE:
+            se.populate()
+        got1 = se.submit(mk(rank))
+        got2 = se.submit(mk(rank + 50))
+        seq = O.Oracle(kind, **cfg)
+        want1 = seq.process(np.concatenate([mk(r) for r in range(world)]))
+        want2 = seq.process(np.concatenate([mk(r + 50) for r in range(world)]))
+        msg = wire.MSG_SIZE[kind]
+        lo, hi = rank * n_per_rank * msg, (rank + 1) * n_per_rank * msg
+        ret[rank] = bool(np.array_equal(got1, want1[lo:hi]) and np.array_equal(got2, want2[lo:hi]))
+        se.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kind", [0, 1, 3])
+def test_sharded_nccl_world2(kind):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), kind, 20000, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}
