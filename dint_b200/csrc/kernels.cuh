@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
   const uint32_t nc = c.nc_total[0];
   if (nc == 0) return;                                // uniform across the grid: nothing listed
   cg::grid_group grid = cg::this_grid();
-  __shared__ uint64_t skeys[2048];                    // 16 KB: CTA sort [0,256), warp sorts [1024,1280); radix counters
+  __shared__ uint64_t skeys[(kThreads / 32) * kBucketCap];   // 16 KB: one 256-key slice per warp; radix counters in the fallback
   __shared__ uint32_t wsum[kThreads / 32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x;
@@ -350,53 +350,45 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
   const uint32_t overflow = c.nc_total[1];
 
   if (overflow == 0) {
-    // ---- bucket path: K2 already hashed every listed (group, index) pair into a bucket; buckets of
-    // <= 32 pairs are rank-sorted by one warp, larger ones bitonic-sorted by the CTA; no grid barrier.
-    uint64_t* wkeys = skeys + 1024 + warp_id() * 32;
-    for (uint32_t base = blockIdx.x * 8; base < P; base += gridDim.x * 8) {
-      const uint32_t b = base + warp_id();
-      const uint32_t m = b < P ? c.bcnt[b] : 0;
-      if (lane_id() == 0) wsum[warp_id()] = m;
-      if (m != 0 && m <= 32) {
-        const uint64_t key = lane_id() < m ? c.buckets[(size_t)b * kBucketCap + lane_id()] : ~0ULL;
+    // ---- bucket path: K2 already hashed every listed (group, index) pair into a bucket.  Warps work
+    // independently (no CTA or grid barrier): a warp sorts its bucket in its own 256-key slice of shared
+    // memory -- rank sort by shuffles up to 32 keys, bitonic above -- and replays the runs.
+    uint64_t* wkeys = skeys + warp_id() * kBucketCap;
+    const uint32_t lane = lane_id();
+    const uint32_t n_warps = gridDim.x * (kThreads / 32);
+    for (uint32_t b = blockIdx.x * (kThreads / 32) + warp_id(); b < P; b += n_warps) {
+      const uint32_t m = c.bcnt[b];
+      if (m == 0) continue;
+      const uint64_t* src = c.buckets + (size_t)b * kBucketCap;
+      if (m <= 32) {
+        const uint64_t key = lane < m ? src[lane] : ~0ULL;
         uint32_t rank = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) rank += (__shfl_sync(0xffffffffu, key, j) < key) ? 1u : 0u;   // keys are distinct
-        if (lane_id() < m) wkeys[rank] = key;
-        __syncwarp();
-        if (lane_id() < m && (lane_id() == 0 || (uint32_t)(wkeys[lane_id() - 1] >> 32) != (uint32_t)(wkeys[lane_id()] >> 32)))
-          replay_run<KIND>(c, wkeys, lane_id(), m);
-        __syncwarp();
-        if (lane_id() == 0) c.bcnt[b] = 0;
-      }
-      __syncthreads();
-      for (uint32_t k = 0; k < 8; k++) {
-        const uint32_t mk = wsum[k];
-        if (mk <= 32) continue;                       // uniform across the CTA
-        const uint32_t bk = base + k;
+        if (lane < m) wkeys[rank] = key;
+      } else {
         uint32_t npow = 64;
-        while (npow < mk) npow <<= 1;
-        for (uint32_t i = tid; i < npow; i += kThreads) skeys[i] = i < mk ? c.buckets[(size_t)bk * kBucketCap + i] : ~0ULL;
-        __syncthreads();
-        for (uint32_t kk = 2; kk <= npow; kk <<= 1) {
+        while (npow < m) npow <<= 1;
+        for (uint32_t i = lane; i < npow; i += 32) wkeys[i] = i < m ? src[i] : ~0ULL;
+        __syncwarp();
+        for (uint32_t kk = 2; kk <= npow; kk <<= 1)
           for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = tid; i < npow; i += kThreads) {
-              uint32_t ixj = i ^ j;
+            for (uint32_t i = lane; i < npow; i += 32) {
+              const uint32_t ixj = i ^ j;
               if (ixj > i) {
-                uint64_t a = skeys[i], bb = skeys[ixj];
-                bool up = (i & kk) == 0;
-                if ((a > bb) == up) { skeys[i] = bb; skeys[ixj] = a; }
+                const uint64_t a = wkeys[i], bb = wkeys[ixj];
+                const bool up = (i & kk) == 0;
+                if ((a > bb) == up) { wkeys[i] = bb; wkeys[ixj] = a; }
               }
             }
-            __syncthreads();
+            __syncwarp();
           }
-        }
-        for (uint32_t p = tid; p < mk; p += kThreads)
-          if (p == 0 || (uint32_t)(skeys[p - 1] >> 32) != (uint32_t)(skeys[p] >> 32)) replay_run<KIND>(c, skeys, p, mk);
-        __syncthreads();
-        if (tid == 0) c.bcnt[bk] = 0;
       }
-      __syncthreads();
+      __syncwarp();
+      for (uint32_t p = lane; p < m; p += 32)
+        if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, wkeys, p, m);
+      __syncwarp();
+      if (lane == 0) c.bcnt[b] = 0;
     }
   } else {
     // ---- fallback (skewed chunk): stable LSD radix sort of the whole list by group id --------------

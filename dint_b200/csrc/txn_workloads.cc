@@ -64,7 +64,7 @@ struct dint_txn {
   int kind;                 // 4 = tatp, 5 = smallbank
   uint32_t n_clients, G, subscribers, accounts, hot_accounts;
   std::vector<TatpClient> tc;
-  std::vector<uint8_t> sb_state;                         // smallbank clients (opaque, see below)
+  struct dint_sb* sb = nullptr;                          // smallbank clients
   uint64_t st_requests = 0, st_txns = 0, st_committed = 0, st_rounds = 0;
   uint64_t st_by_type[8] = {0}, st_commit_by_type[8] = {0};
 
@@ -78,10 +78,10 @@ struct dint_txn {
     m.b[1] = type; m.b[2] = table; put64(m.b + 3, key);
   }
   struct Out {
-    uint8_t* req; uint8_t* dst; uint32_t n = 0; uint32_t per_shard[8] = {0}; uint32_t G;
+    uint8_t* req; uint8_t* dst; uint32_t n = 0; uint32_t per_shard[8] = {0}; uint32_t G; uint32_t msz = TM;
     void push(const TMsg& m, uint32_t shard, bool set_ord) {
-      memcpy(req + (size_t)n * TM, m.b, TM);
-      if (set_ord) req[(size_t)n * TM] = (uint8_t)per_shard[shard % 8];    // msg->ord = j: index inside the shard's list
+      memcpy(req + (size_t)n * msz, m.b, msz);
+      if (set_ord) req[(size_t)n * msz] = (uint8_t)per_shard[shard % 8];    // msg->ord = j: index inside the shard's list
       per_shard[shard % 8]++;
       dst[n++] = (uint8_t)shard;
     }
@@ -344,36 +344,220 @@ struct dint_txn {
   }
 };
 
+// ================================================ SmallBank =========================================
+// wire: {ord@0, type@1, table@2, key@3, val@11[8] = {u32 magic; float bal}, ver@19}  (smallbank/udp/net.h:43-52)
+namespace {
+constexpr int SMSZ = 23;
+enum { S_ACQ_S = 0, S_ACQ_X = 1, S_REL_S = 2, S_REL_X = 3, S_COMMIT_PRIM = 4, S_COMMIT_BCK = 5, S_COMMIT_LOG = 6,
+       S_GRANT_S = 7, S_REJECT_S = 8, S_GRANT_X = 9, S_REJECT_X = 10 };
+enum { B_AMALGAMATE = 0, B_BALANCE, B_DEPOSIT, B_SEND, B_TRANSACT, B_WRITECHECK };
+enum { SP_ACQ = 0, SP_REL_ABORT, SP_LOG, SP_BCK, SP_PRIM, SP_RELEASE };
+struct SbRow { uint8_t table, excl, write, granted; uint64_t acct; TMsg m; };
+struct SbClient {
+  uint64_t seed;
+  uint8_t txn = 0, phase = 0, n_rows = 0, n_out = 0, rel_idx = 0;
+  SbRow r[3];
+};
+inline float get_bal(const TMsg& m) { float f; memcpy(&f, m.b + 11 + 4, 4); return f; }
+inline void set_bal(TMsg& m, float f) { memcpy(m.b + 11 + 4, &f, 4); }
+}  // namespace
+
+struct dint_sb {
+  dint_txn* base;
+  std::vector<SbClient> cl;
+  uint32_t accounts, hot_accounts, G;
+
+  void get_account(uint64_t* seed, uint64_t* a) const {                 // smallbank/udp/smallbank.h:24-30
+    if (fastrand(seed) % 100 < 90) *a = fastrand(seed) % hot_accounts; else *a = fastrand(seed) % accounts;
+  }
+  void get_two_accounts(uint64_t* seed, uint64_t* a0, uint64_t* a1) const {   // smallbank.h:32-46
+    const uint32_t n = (fastrand(seed) % 100 < 90) ? hot_accounts : accounts;
+    *a0 = fastrand(seed) % n;
+    *a1 = fastrand(seed) % n;
+    while (*a1 == *a0) *a1 = fastrand(seed) % n;
+  }
+  static void row(SbRow& r, uint8_t table, bool excl, bool write, uint64_t acct) {
+    r.table = table; r.excl = excl; r.write = write; r.granted = 0; r.acct = acct;
+  }
+  void begin(SbClient& c) {
+    static const uint8_t mix[100] = {
+#define R5(x) x, x, x, x, x
+#define R15(x) R5(x), R5(x), R5(x)
+        R15(B_AMALGAMATE), R15(B_BALANCE), R15(B_DEPOSIT), R15(B_SEND), R5(B_SEND), R5(B_SEND), R15(B_TRANSACT), R15(B_WRITECHECK)};
+#undef R15
+#undef R5
+    c.txn = mix[fastrand(&c.seed) % 100];
+    c.phase = SP_ACQ;
+    base->st_txns++;
+    base->st_by_type[c.txn]++;
+    uint64_t a0, a1;
+    switch (c.txn) {
+      case B_AMALGAMATE:       // client_udp_shard.cc:169-438: sav(a0) X, chk(a0) X, chk(a1) X, all written
+        get_two_accounts(&c.seed, &a0, &a1);
+        c.n_rows = 3; row(c.r[0], 0, true, true, a0); row(c.r[1], 1, true, true, a0); row(c.r[2], 1, true, true, a1);
+        break;
+      case B_BALANCE:          // :441-578: sav(a) S, chk(a) S, read only
+        get_account(&c.seed, &a0);
+        c.n_rows = 2; row(c.r[0], 0, false, false, a0); row(c.r[1], 1, false, false, a0);
+        break;
+      case B_DEPOSIT:          // :581-684: chk(a) X += 1.3
+        get_account(&c.seed, &a0);
+        c.n_rows = 1; row(c.r[0], 1, true, true, a0);
+        break;
+      case B_SEND:             // :687-932: chk(a0) X, chk(a1) X, move 5.0
+        get_two_accounts(&c.seed, &a0, &a1);
+        c.n_rows = 2; row(c.r[0], 1, true, true, a0); row(c.r[1], 1, true, true, a1);
+        break;
+      case B_TRANSACT:         // :935-1038: sav(a) X += 20.20
+        get_account(&c.seed, &a0);
+        c.n_rows = 1; row(c.r[0], 0, true, true, a0);
+        break;
+      default:                 // B_WRITECHECK :1041-1239: sav(a) S, chk(a) X -= 5 (+1 penalty)
+        get_account(&c.seed, &a0);
+        c.n_rows = 2; row(c.r[0], 0, false, false, a0); row(c.r[1], 1, true, true, a0);
+        break;
+    }
+  }
+  void finish(SbClient& c, bool ok) {
+    if (ok) { base->st_committed++; base->st_commit_by_type[c.txn]++; }
+    begin(c);
+  }
+  void emit(SbClient& c, dint_txn::Out& o) {
+    const uint32_t n0 = o.n;
+    memset(o.per_shard, 0, sizeof o.per_shard);
+    TMsg rr[3];
+    int nw = 0;
+    for (int i = 0; i < c.n_rows; i++) if (c.r[i].write) rr[nw++] = c.r[i].m;
+    switch (c.phase) {
+      case SP_ACQ:
+        for (int i = 0; i < c.n_rows; i++) {
+          TMsg m; memset(m.b, 0, sizeof m.b);
+          m.b[1] = c.r[i].excl ? S_ACQ_X : S_ACQ_S; m.b[2] = c.r[i].table; put64(m.b + 3, c.r[i].acct);
+          o.push(m, (uint32_t)(c.r[i].acct % G), c.n_rows > 1);
+        }
+        break;
+      case SP_REL_ABORT: {
+        TMsg m = c.r[c.rel_idx].m; m.b[1] = c.r[c.rel_idx].excl ? S_REL_X : S_REL_S;
+        o.push(m, (uint32_t)(c.r[c.rel_idx].acct % G), false);
+        break;
+      }
+      case SP_LOG: base->emit_log(o, rr, nw, S_COMMIT_LOG); break;
+      case SP_BCK: base->emit_bck(o, rr, nw, S_COMMIT_BCK); break;
+      case SP_PRIM: base->emit_prim(o, rr, nw, S_COMMIT_PRIM); break;
+      default:
+        for (int i = 0; i < c.n_rows; i++) {
+          TMsg m = c.r[i].m; m.b[1] = c.r[i].excl ? S_REL_X : S_REL_S;
+          o.push(m, (uint32_t)(c.r[i].acct % G), c.n_rows > 1);
+        }
+        break;
+    }
+    c.n_out = (uint8_t)(o.n - n0);
+  }
+  int next_granted(const SbClient& c, int from) const {
+    for (int i = from; i < c.n_rows; i++) if (c.r[i].granted) return i;
+    return -1;
+  }
+  void absorb(SbClient& c, const uint8_t* r) {
+    switch (c.phase) {
+      case SP_ACQ: {
+        bool all = true;
+        for (int i = 0; i < c.n_rows; i++) {
+          memcpy(c.r[i].m.b, r + (size_t)i * SMSZ, SMSZ);
+          const uint8_t t = c.r[i].m.b[1];
+          c.r[i].granted = (t == S_GRANT_S || t == S_GRANT_X);
+          all &= (bool)c.r[i].granted;
+        }
+        bool logic_abort = false;
+        if (all) {
+          TMsg& m0 = c.r[0].m;
+          switch (c.txn) {
+            case B_AMALGAMATE:
+              set_bal(c.r[2].m, get_bal(c.r[2].m) + (get_bal(c.r[0].m) + get_bal(c.r[1].m)));
+              set_bal(c.r[0].m, 0.f); set_bal(c.r[1].m, 0.f);
+              break;
+            case B_DEPOSIT: set_bal(m0, get_bal(m0) + 1.3f); break;
+            case B_SEND:
+              if (get_bal(c.r[0].m) < 5.0f) logic_abort = true;
+              else { set_bal(c.r[0].m, get_bal(c.r[0].m) - 5.0f); set_bal(c.r[1].m, get_bal(c.r[1].m) + 5.0f); }
+              break;
+            case B_TRANSACT: set_bal(m0, get_bal(m0) + 20.20f); break;
+            case B_WRITECHECK:
+              if (get_bal(c.r[0].m) + get_bal(c.r[1].m) < 5.0f) set_bal(c.r[1].m, get_bal(c.r[1].m) - 6.0f);
+              else set_bal(c.r[1].m, get_bal(c.r[1].m) - 5.0f);
+              break;
+            default: break;
+          }
+        }
+        if (!all || logic_abort) {
+          int g = next_granted(c, 0);
+          if (g < 0) finish(c, false); else { c.rel_idx = (uint8_t)g; c.phase = SP_REL_ABORT; }
+        } else if (c.txn == B_BALANCE) {
+          c.phase = SP_RELEASE;
+        } else {
+          for (int i = 0; i < c.n_rows; i++) if (c.r[i].write) put32(c.r[i].m.b + 19, get32(c.r[i].m.b + 19) + 1);   // ver++
+          c.phase = SP_LOG;
+        }
+        break;
+      }
+      case SP_REL_ABORT: {
+        int g = next_granted(c, c.rel_idx + 1);
+        if (g < 0) finish(c, false); else c.rel_idx = (uint8_t)g;
+        break;
+      }
+      case SP_LOG: c.phase = SP_BCK; break;
+      case SP_BCK: c.phase = SP_PRIM; break;
+      case SP_PRIM: c.phase = SP_RELEASE; break;
+      default: finish(c, true); break;
+    }
+  }
+};
+
 extern "C" {
 
 // kind 4 (tatp): n_clients logical clients with gids [gid0, gid0 + n_clients); G shards; `subscribers`
 // = kSubscriberNum of the key generator (reference 7,000,000; must equal the servers' population).
+// kind 5 (smallbank): `subscribers` = kAccountNum (reference 24,000,000), hot set = 4 % of it (960,000).
 dint_txn* dint_txn_create(int kind, uint32_t n_clients, uint32_t gid0, uint32_t n_shards, uint32_t subscribers) {
-  if (kind != 4 || n_clients == 0 || n_shards == 0 || n_shards > 8 || subscribers == 0) return nullptr;
+  if ((kind != 4 && kind != 5) || n_clients == 0 || n_shards == 0 || n_shards > 8 || subscribers < 3) return nullptr;
   dint_txn* w = new dint_txn();
   w->kind = kind; w->n_clients = n_clients; w->G = n_shards; w->subscribers = subscribers;
-  w->tc.resize(n_clients);
-  for (uint32_t i = 0; i < n_clients; i++) {
-    w->tc[i].seed = 0xdeadbeefULL + gid0 + i;                // client_udp_shard.cc:1121
-    w->begin_txn(w->tc[i]);
+  if (kind == 4) {
+    w->tc.resize(n_clients);
+    for (uint32_t i = 0; i < n_clients; i++) {
+      w->tc[i].seed = 0xdeadbeefULL + gid0 + i;              // client_udp_shard.cc:1121
+      w->begin_txn(w->tc[i]);
+    }
+  } else {
+    dint_sb* sb = new dint_sb();
+    sb->base = w; sb->G = n_shards; sb->accounts = subscribers;
+    sb->hot_accounts = (uint32_t)((uint64_t)subscribers * 960000 / 24000000);   // kHotAccountNum / kAccountNum
+    if (sb->hot_accounts < 2) sb->hot_accounts = 2;
+    sb->cl.resize(n_clients);
+    for (uint32_t i = 0; i < n_clients; i++) { sb->cl[i].seed = 0xdeadbeefULL + gid0 + i; sb->begin(sb->cl[i]); }
+    w->sb = sb;
   }
   return w;
 }
-void dint_txn_destroy(dint_txn* w) { delete w; }
-uint32_t dint_txn_max_round(const dint_txn* w) { return w->n_clients * 6; }
+void dint_txn_destroy(dint_txn* w) { if (w) delete w->sb; delete w; }
+uint32_t dint_txn_max_round(const dint_txn* w) { return w->n_clients * 9; }
 
 // emits one round; returns the number of wire records.  req: capacity dint_txn_max_round() records;
 // dst[i] = destination shard of record i.
 uint64_t dint_txn_next(dint_txn* w, void* req, uint8_t* dst) {
   dint_txn::Out o;
   o.req = (uint8_t*)req; o.dst = dst; o.G = w->G;
-  for (auto& c : w->tc) w->tatp_emit(c, o);
+  if (w->sb) { o.msz = SMSZ; for (auto& c : w->sb->cl) w->sb->emit(c, o); }
+  else for (auto& c : w->tc) w->tatp_emit(c, o);
   w->st_requests += o.n;
   w->st_rounds++;
   return o.n;
 }
 void dint_txn_feed(dint_txn* w, const void* resp) {
   const uint8_t* r = (const uint8_t*)resp;
+  if (w->sb) {
+    for (auto& c : w->sb->cl) { const uint32_t n = c.n_out; w->sb->absorb(c, r); r += (size_t)n * SMSZ; }
+    return;
+  }
   for (auto& c : w->tc) {
     const uint32_t n = c.n_out;          // absorb may start a new transaction and must not see its own n_out
     w->tatp_absorb(c, r);

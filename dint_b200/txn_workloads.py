@@ -17,6 +17,7 @@ from .wire import MSG_SIZE, TATP
 _lib = None
 TATP_TXN_NAMES = ["get_subscriber_data", "get_access_data", "get_new_destination", "update_subscriber_data",
                   "update_location", "insert_call_forwarding", "delete_call_forwarding"]
+SMALLBANK_TXN_NAMES = ["amalgamate", "balance", "deposit_checking", "send_payment", "transact_saving", "write_check"]
 
 
 def lib():
@@ -38,7 +39,11 @@ def lib():
 
 
 class TxnWorkload:
-    def __init__(self, kind, n_clients, n_shards=3, subscribers=7_000_000, gid0=0):
+    def __init__(self, kind, n_clients, n_shards=3, subscribers=None, gid0=0):
+        """subscribers: kSubscriberNum (tatp, reference 7,000,000) or kAccountNum (smallbank, 24,000,000) of the
+        key generators -- must match what the servers populated."""
+        if subscribers is None:
+            subscribers = 7_000_000 if kind == TATP else 24_000_000
         self.kind, self.msg, self.n_shards = kind, MSG_SIZE[kind], n_shards
         self.h = lib().dint_txn_create(kind, n_clients, gid0, n_shards, subscribers)
         if not self.h:
@@ -73,7 +78,8 @@ class TxnWorkload:
         out = (C.c_uint64 * 18)()
         lib().dint_txn_stats(self.h, out)
         d = {"requests": int(out[0]), "txns": int(out[1]), "committed": int(out[2]), "rounds": int(out[3])}
-        d["by_type"] = {TATP_TXN_NAMES[i]: (int(out[4 + i]), int(out[11 + i])) for i in range(7)}
+        names = TATP_TXN_NAMES if self.kind == TATP else SMALLBANK_TXN_NAMES
+        d["by_type"] = {n: (int(out[4 + i]), int(out[11 + i])) for i, n in enumerate(names)}
         return d
 
 

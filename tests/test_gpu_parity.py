@@ -163,6 +163,45 @@ def test_tatp_random(chunk, n_subs):
         assert np.array_equal(ring_got, ora.log_ring())
 
 
+# ---------------------------------------------------------------- closed-loop transaction drivers ----
+@pytest.mark.parametrize("kind,n,clients", [(wire.TATP, 3000, 2000), (wire.SMALLBANK, 5000, 1500)])
+def test_txn_drivers_closed_loop_three_shards(kind, n, clients):
+    """TATP (7 txn types) / SmallBank (6) clients against three shard servers: GPU engines must take the
+    same commit/abort decisions, reply for reply, as three oracle servers."""
+    from dint_b200.txn_workloads import TxnWorkload, Cluster
+    cfg = dict(subs_populate=n) if kind == wire.TATP else dict(accts_populate=n)
+    msg = wire.MSG_SIZE[kind]
+
+    def run(servers):
+        wl = TxnWorkload(kind, n_clients=clients, n_shards=3, subscribers=n)
+        cl = Cluster(servers, msg)
+        trace = []
+        for _ in range(80):
+            rq, dst = wl.next()
+            rs = cl.submit(rq, dst)
+            wl.feed(rs)
+            trace.append((rq.copy(), dst.copy(), rs.copy()))
+        return trace, wl.stats()
+
+    oras = [O.Oracle(kind, **cfg) for _ in range(3)]
+    want, st_want = run([o.process for o in oras])
+    engs = [Engine(kind, populate=True, chunk=4096, **cfg) for _ in range(3)]
+    try:
+        got, st_got = run([e.submit for e in engs])
+        for r, ((q1, d1, s1), (q2, d2, s2)) in enumerate(zip(want, got)):
+            assert np.array_equal(q1, q2) and np.array_equal(d1, d2), f"round {r}: clients diverged"
+            assert first_diff(s2, s1, msg) is None, f"round {r}: {first_diff(s2, s1, msg)}"
+        assert st_got == st_want and st_got["committed"] > 0
+        for e, o in zip(engs, oras):
+            for tb in range(5 if kind == wire.TATP else 2):
+                assert e.kv_count(tb) == o.kv_count(tb)
+            ring, appended = e.dump_log()
+            assert appended == o.log_appended() and np.array_equal(ring, o.log_ring())
+    finally:
+        for e in engs:
+            e.close()
+
+
 # ---------------------------------------------------------------- device path / edge cases -----------
 def test_device_path_and_empty():
     import torch

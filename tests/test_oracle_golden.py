@@ -122,3 +122,27 @@ def test_oracle_matches_live_reference_binary(kind, make):
     req = make()
     ref, _ = O.run_ref(kind, req)
     assert np.array_equal(O.Oracle(kind).process(req), ref)
+
+
+def test_txn_drivers_run_valid_protocols_against_oracle_shards():
+    """The TATP / SmallBank client state machines never send a request the reference would panic() on
+    (kvs_set / kvs_delete of a missing row, unknown type), commit a sane share of transactions, and are
+    deterministic."""
+    from dint_b200.txn_workloads import TxnWorkload, Cluster
+    for kind, n, cfg in [(wire.TATP, 2000, dict(subs_populate=2000)), (wire.SMALLBANK, 4000, dict(accts_populate=4000))]:
+        runs = []
+        for _ in range(2):
+            oras = [O.Oracle(kind, **cfg) for _ in range(3)]
+            wl = TxnWorkload(kind, n_clients=400, n_shards=3, subscribers=n)
+            cl = Cluster([o.process for o in oras], wire.MSG_SIZE[kind])
+            h = 0
+            for _ in range(100):
+                rq, dst = wl.next()
+                rs = cl.submit(rq, dst)          # raises if an oracle shard hits a panic() path
+                wl.feed(rs)
+                h = hash((h, rs.tobytes()))
+            runs.append((h, wl.stats()))
+        assert runs[0] == runs[1]
+        st = runs[0][1]
+        assert st["committed"] > 0.2 * st["txns"]
+        assert all(v[0] > 0 for v in st["by_type"].values())

@@ -65,6 +65,20 @@ def main():
     rd["key"] = [x[1] for x in u]
     req = np.concatenate([wire.as_bytes(rd), T.tatp_random(5000, 60, seed=6, oracle=ora)])
     save("tatp_sweep_random", wire.TATP, req, {"subs_populate": 60})
+    # closed-loop transaction drivers (tatp 7 txn types / smallbank 6), 3 shards: the request stream shard 0 saw
+    from dint_b200.txn_workloads import TxnWorkload, Cluster
+    for kind, name, n, clients, rounds, cfg in [
+            (wire.TATP, "tatp_closed_shard0", 400, 150, 60, {"subs_populate": 400}),
+            (wire.SMALLBANK, "smallbank_closed_shard0", 3000, 300, 60, {"accts_populate": 3000})]:
+        oras = [O.Oracle(kind, **cfg) for _ in range(3)]
+        wl = TxnWorkload(kind, n_clients=clients, n_shards=3, subscribers=n)
+        cl = Cluster([o.process for o in oras], wire.MSG_SIZE[kind])
+        shard0 = []
+        for _ in range(rounds):
+            rq, dst = wl.next()
+            shard0.append(rq.reshape(-1, wire.MSG_SIZE[kind])[dst == 0].reshape(-1).copy())
+            wl.feed(cl.submit(rq, dst))
+        save(name, kind, np.concatenate(shard0), cfg)
 
 
 if __name__ == "__main__":
