@@ -123,11 +123,11 @@ struct ProfScope {
 
 // ---- per-chunk launch sequence ------------------------------------------------------------------------
 template <typename... Args>
-static cudaError_t launch_ex(dint_engine* e, void (*kern)(Args...), int grid, size_t smem, cudaStream_t s, bool coop,
-                             Args... args) {
+static cudaError_t launch_ex(dint_engine* e, void (*kern)(Args...), int grid, int block, size_t smem, cudaStream_t s,
+                             bool coop, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid < 1 ? 1 : grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[2];
@@ -143,10 +143,10 @@ template <int KIND, bool HAS_LOG>
 static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
     ProfScope ps(e, s, KT_CLASSIFY);
-    int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kThreads - 1) / (4 * kThreads));
+    int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kTile - 1) / (4 * kTile));
     if (clr > want) want = clr;
     int grid = want < e->grid_classify ? want : e->grid_classify;
-    CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, e->smem_stage, s, false, c));
+    CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, kTile, e->smem_stage, s, false, c));
   }
   if (HAS_LOG) {
     ProfScope ps(e, s, KT_LOGSCAN);
@@ -155,11 +155,11 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
     ProfScope ps(e, s, KT_APPLY);
     int grid = (int)c.n_tiles < e->grid_apply ? (int)c.n_tiles : e->grid_apply;
-    CU(launch_ex(e, k_apply<KIND, HAS_LOG>, grid, e->smem_stage, s, false, c));
+    CU(launch_ex(e, k_apply<KIND, HAS_LOG>, grid, kTile, e->smem_stage, s, false, c));
   }
   if (KIND != K_LOG) {   // the log server has no per-key state: nothing to order
     ProfScope ps(e, s, KT_ORDERED);
-    CU(launch_ex(e, k_ordered<KIND>, e->coop_grid, 0, s, true, c));
+    CU(launch_ex(e, k_ordered<KIND>, e->coop_grid, kThreads, 0, s, true, c));
   }
   CU(cudaGetLastError());
   return DINT_OK;
@@ -186,10 +186,10 @@ static int grids_for(dint_engine* e) {
     CU(cudaFuncSetAttribute(k_classify<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
     CU(cudaFuncSetAttribute(k_apply<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
   }
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kThreads, e->smem_stage));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kTile, e->smem_stage));
   if (per_sm < 1) return set_err(DINT_EIO, "k_classify cannot be resident");
   e->grid_classify = per_sm * sms;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apply<KIND, HAS_LOG>, kThreads, e->smem_stage));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apply<KIND, HAS_LOG>, kTile, e->smem_stage));
   if (per_sm < 1) return set_err(DINT_EIO, "k_apply cannot be resident");
   e->grid_apply = per_sm * sms;
   if (KIND == K_LOG) { e->coop_grid = 1; return DINT_OK; }

@@ -32,8 +32,9 @@ namespace dint {
 
 enum Kind { K_LOCK2PL = 0, K_FASST = 1, K_LOG = 2, K_STORE = 3, K_TATP = 4, K_SMALLBANK = 5 };
 
-constexpr int kTile = 256;       // wire records per CTA in K1/K2
-constexpr int kThreads = 256;
+constexpr int kTile = 128;       // wire records per tile = threads per CTA in K1/K2 (16 CTAs, i.e. 16 independent
+                                 // latency chains, per SM)
+constexpr int kThreads = 256;    // threads per CTA of the other kernels (K3's radix passes rely on 256)
 constexpr int kMaxTables = 5;
 constexpr uint32_t kBucketCap = 256;    // K3: bucket capacity (sorted in shared memory)
 constexpr uint32_t kBucketFill = 64;    // K3: chunk / kBucketFill buckets (mean occupancy 64 if EVERY request were listed)
@@ -190,6 +191,13 @@ template <int KIND> DINT_D void mark_invalid(const Ctx& c, uint8_t* rec) {
   atomicAdd(&c.counters[0], 1ULL);
 }
 
+// Register-resident replay of a same-group run (K3).  For the lock servers a group's whole state is a
+// couple of words, so a run need not be replayed request by request against memory: every request's
+// fields are fetched up front IN PARALLEL (load_op), the run's owner walks the ops with the state in
+// registers (step), and the replies are written back IN PARALLEL (write_result) -- three memory round
+// trips per run instead of three per request.
+template <int KIND> struct FastReplay { static constexpr bool ok = false; };
+
 // =================================== lock_2pl =========================================================
 template <> DINT_D TypeInfo type_info<K_LOCK2PL>(const uint8_t* rec) {
   using W = Wire<K_LOCK2PL>;
@@ -232,6 +240,26 @@ DINT_D void apply_one<K_LOCK2PL>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, 
   }
 }
 
+template <> struct FastReplay<K_LOCK2PL> {
+  static constexpr bool ok = true;
+  using W = Wire<K_LOCK2PL>;
+  struct State { uint2 s; };
+  static DINT_D uint32_t load_op(const uint8_t* rec) { return (uint32_t)rec[W::TYPE] | ((uint32_t)rec[W::LTYPE] << 8); }
+  static DINT_D State load_state(const Ctx& c, uint32_t g) { return State{__ldcg(&c.cnt2[g])}; }
+  static DINT_D void store_state(const Ctx& c, uint32_t g, const State& st) { c.cnt2[g] = st.s; }
+  static DINT_D uint64_t step(State& st, uint32_t op) {             // lock_2pl/udp/server.cc:82-119
+    const uint32_t action = op & 255u, lt = op >> 8;
+    if (action == 0) {
+      if (lt == 0) { if (st.s.x == 0) { st.s.y++; return 2; } return 3; }
+      if (st.s.x == 0 && st.s.y == 0) { st.s.x++; return 2; }
+      return 3;
+    }
+    if (lt == 0) st.s.y--; else if (lt == 1) st.s.x--;
+    return 5;
+  }
+  static DINT_D void write_result(uint8_t* rec, uint64_t r) { rec[W::TYPE] = (uint8_t)r; }
+};
+
 // =================================== lock_fasst =======================================================
 template <> DINT_D TypeInfo type_info<K_FASST>(const uint8_t* rec) {
   uint8_t t = rec[Wire<K_FASST>::TYPE];
@@ -273,6 +301,31 @@ DINT_D void apply_one<K_FASST>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, co
     rec[W::TYPE] = 8;
   }
 }
+
+template <> struct FastReplay<K_FASST> {
+  static constexpr bool ok = true;
+  using W = Wire<K_FASST>;
+  struct State { uint32_t ver, lock, g; bool dirty_ver; };
+  static DINT_D uint32_t load_op(const uint8_t* rec) { return rec[W::TYPE]; }
+  static DINT_D State load_state(const Ctx& c, uint32_t g) {
+    return State{__ldcg(&c.ver[g]), (__ldcg(&c.lockbits[g >> 5]) >> (g & 31)) & 1u, g, false};
+  }
+  static DINT_D void store_state(const Ctx& c, uint32_t g, const State& st) {
+    if (st.dirty_ver) c.ver[g] = st.ver;
+    if (st.lock) bm_set(c.lockbits, g); else bm_clear_bit(c.lockbits, g);   // neighbours share the word: atomics
+  }
+  static DINT_D uint64_t step(State& st, uint32_t t) {               // lock_fasst/udp/server.cc:86-114
+    if (t == 0) return 4ull | ((uint64_t)st.ver << 8);
+    if (t == 1) { if (st.lock) return 6; st.lock = 1; return 5; }
+    if (t == 2) { st.lock = 0; return 7; }
+    st.ver++; st.dirty_ver = true; st.lock = 0;
+    return 8;
+  }
+  static DINT_D void write_result(uint8_t* rec, uint64_t r) {
+    rec[W::TYPE] = (uint8_t)r;
+    if ((uint8_t)r == 4) st_u32_unaligned(rec + W::VER, (uint32_t)(r >> 8));
+  }
+};
 
 // =================================== log_server =======================================================
 template <> DINT_D TypeInfo type_info<K_LOG>(const uint8_t* rec) {

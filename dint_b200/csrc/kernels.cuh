@@ -10,7 +10,7 @@ DINT_D uint32_t lane_id() { return threadIdx.x & 31; }
 DINT_D uint32_t warp_id() { return threadIdx.x >> 5; }
 
 // In-tile exclusive rank of `flag` in thread order; returns rank, writes the tile total to `total`.
-// `scratch` is kThreads/32 words of shared memory.  Contains __syncthreads().
+// `scratch` is kTile/32 words of shared memory.  Contains __syncthreads().  (K1/K2 only: kTile threads)
 DINT_D uint32_t tile_rank(bool flag, uint32_t* scratch, uint32_t& total) {
   uint32_t bal = __ballot_sync(0xffffffffu, flag);
   uint32_t in_warp = __popc(bal & ((1u << lane_id()) - 1u));
@@ -18,7 +18,7 @@ DINT_D uint32_t tile_rank(bool flag, uint32_t* scratch, uint32_t& total) {
   __syncthreads();
   uint32_t off = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; w++) {
+  for (int w = 0; w < kTile / 32; w++) {
     uint32_t v = scratch[w];
     if (w < (int)warp_id()) off += v;
     tot += v;
@@ -28,7 +28,7 @@ DINT_D uint32_t tile_rank(bool flag, uint32_t* scratch, uint32_t& total) {
   return off + in_warp;
 }
 
-// Two ranks with one pair of barriers (flag a in the low half-word of the per-warp counts, b in the high).
+// Two ranks with ONE barrier (flag a in the low half-word of the per-warp counts, b in the high).
 DINT_D void tile_rank2(bool a, bool b, uint32_t* scratch, uint32_t& ra, uint32_t& rb, uint32_t& ta, uint32_t& tb) {
   const uint32_t ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
   const uint32_t lt = (1u << lane_id()) - 1u;
@@ -36,12 +36,12 @@ DINT_D void tile_rank2(bool a, bool b, uint32_t* scratch, uint32_t& ra, uint32_t
   __syncthreads();
   uint32_t off = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; w++) {
+  for (int w = 0; w < kTile / 32; w++) {
     uint32_t v = scratch[w];
     if (w < (int)warp_id()) off += v;
     tot += v;
   }
-  __syncthreads();
+  // no trailing barrier: the caller alternates between two scratch arrays and has a CTA barrier per tile
   ra = (off & 0xffffu) + __popc(ba & lt);
   rb = (off >> 16) + __popc(bb & lt);
   ta = tot & 0xffffu;
@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uin
 // K1 classify (+ clears the flag words of the previous chunk)
 // ---------------------------------------------------------------------------------------------------
 template <int KIND, bool HAS_LOG>
-__global__ void __launch_bounds__(kThreads) k_classify(const Ctx c) {
+__global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   using W = Wire<KIND>;
   constexpr uint32_t NS = Stage<W::MSG>::N;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[kStages];
-  __shared__ uint32_t scratch[kThreads / 32];
+  __shared__ uint32_t scratch[kTile / 32];
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     if (blockIdx.x == 0) { c.nc_total[0] = 0; c.nc_total[1] = 0; }
@@ -142,12 +142,25 @@ __global__ void __launch_bounds__(kThreads) k_classify(const Ctx c) {
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
 
   // retire the previous chunk's flags: every word it touched is zeroed (all of that set's nibbles
-  // were written by that chunk, so whole-word stores are exact)
-  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < c.prev_n; i += gridDim.x * kThreads) {
-    uint32_t g = c.grp_prev[i];
-    if (g != kNoGroup) c.flags_prev[flag_word(c, g)] = 0;
+  // were written by that chunk, so whole-word stores are exact).  Loads are batched four deep so that
+  // the kernel start pays one memory latency, not one per element.
+  for (uint32_t i = blockIdx.x * kTile + threadIdx.x; i < c.prev_n; i += 4 * gridDim.x * kTile) {
+    uint32_t g[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t j = i + u * gridDim.x * kTile;
+      g[u] = j < c.prev_n ? __ldcg(&c.grp_prev[j]) : kNoGroup;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (g[u] != kNoGroup) c.flags_prev[flag_word(c, g[u])] = 0;
   }
 
+  // A writer needs the OLD nibble to learn whether it is the second writer of its class (-> W2).  Waiting
+  // for the atomic's return value would expose one L2 round trip per tile; the check is deferred by one
+  // tile instead (the value is consumed after the NEXT tile's atomics have been issued).
+  uint32_t pend_old = 0, pend_test = 0, pend_sh = 0;
+  uint32_t* pend_w = nullptr;
   for (uint32_t i = 0; i < it.n_my; i++) {
     // the stage that held tile i-1 is free (barrier at the end of iteration i-1): refill it now
     if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
@@ -155,6 +168,8 @@ __global__ void __launch_bounds__(kThreads) k_classify(const Ctx c) {
     const uint8_t* tile = acquire_tile<W::MSG>(c, smem, full, it, i, first, cnt);
     const bool valid = threadIdx.x < cnt;
     bool is_log = false;
+    uint32_t new_old = 0, new_test = 0, new_sh = 0;
+    uint32_t* new_w = nullptr;
     if (valid) {
       const uint8_t* rec = tile + threadIdx.x * W::MSG;
       TypeInfo ti = type_info<KIND>(rec);
@@ -167,15 +182,19 @@ __global__ void __launch_bounds__(kThreads) k_classify(const Ctx c) {
           if (ti.mask == C_RA) {
             atomicOr(w, F_R << sh);                      // no return value: a fire-and-forget RED
           } else {
-            uint32_t bits = ((ti.mask & C_RA) ? F_R : 0u) | ((ti.mask & C_WA) ? F_WA : 0u) | ((ti.mask & C_WL) ? F_WL : 0u);
-            uint32_t old = (atomicOr(w, bits << sh) >> sh) & 15u;
-            if (((ti.mask & C_WA) && (old & F_WA)) || ((ti.mask & C_WL) && (old & F_WL))) atomicOr(w, F_W2 << sh);
+            const uint32_t bits = ((ti.mask & C_RA) ? F_R : 0u) | ((ti.mask & C_WA) ? F_WA : 0u) | ((ti.mask & C_WL) ? F_WL : 0u);
+            new_old = atomicOr(w, bits << sh);
+            new_test = ((ti.mask & C_WA) ? F_WA : 0u) | ((ti.mask & C_WL) ? F_WL : 0u);
+            new_w = w;
+            new_sh = sh;
           }
         }
       }
       c.grp[first + threadIdx.x] = g;
       is_log = !ti.invalid && ti.is_log;
     }
+    if (pend_w && ((pend_old >> pend_sh) & pend_test)) atomicOr(pend_w, F_W2 << pend_sh);
+    pend_old = new_old; pend_test = new_test; pend_sh = new_sh; pend_w = new_w;
     if (HAS_LOG) {
       uint32_t total;
       (void)tile_rank(is_log, scratch, total);          // contains the CTA barriers that free the stage
@@ -184,6 +203,7 @@ __global__ void __launch_bounds__(kThreads) k_classify(const Ctx c) {
       __syncthreads();                                   // everyone is done reading this stage
     }
   }
+  if (pend_w && ((pend_old >> pend_sh) & pend_test)) atomicOr(pend_w, F_W2 << pend_sh);
 }
 
 // K1b: absolute append ordinal of every tile's first log append (single CTA).
@@ -224,12 +244,15 @@ __global__ void __launch_bounds__(kThreads) k_log_scan(const Ctx c) {
 // K2 apply
 // ---------------------------------------------------------------------------------------------------
 template <int KIND, bool HAS_LOG>
-__global__ void __launch_bounds__(kThreads) k_apply(const Ctx c) {
+__global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
   using W = Wire<KIND>;
   constexpr uint32_t NS = Stage<W::MSG>::N;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[kStages];
-  __shared__ uint32_t scratch[kThreads / 32];
+  __shared__ uint32_t scratch2[2][kTile / 32];
+  // lock servers: the group id K1 stored is all K2 needs of the key -- fetch it (coalesced, independent of
+  // the TMA stage) instead of re-hashing; KV servers need the hash itself to find the table entry
+  constexpr bool kGrpFromK1 = (KIND == K_LOCK2PL || KIND == K_FASST);
   if (threadIdx.x == 0)
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
   __syncthreads();
@@ -238,6 +261,12 @@ __global__ void __launch_bounds__(kThreads) k_apply(const Ctx c) {
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
 
   for (uint32_t i = 0; i < it.n_my; i++) {
+    uint32_t* scratch = scratch2[i & 1];
+    uint32_t g_k1 = kNoGroup;
+    if (kGrpFromK1) {
+      const uint32_t idx = it.tile(i) * kTile + threadIdx.x;
+      if (idx < c.n) g_k1 = __ldcg(&c.grp[idx]);
+    }
     if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) {
       // the stage that held tile i-1 is refilled as soon as its bulk store has finished READING it
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -255,7 +284,7 @@ __global__ void __launch_bounds__(kThreads) k_apply(const Ctx c) {
     if (valid) {
       ti = type_info<KIND>(rec);
       if (!ti.invalid && ti.mask) {
-        ki = key_info<KIND>(c, rec);                 // re-hash: cheaper than a dependent load of grp[]
+        if (kGrpFromK1) ki.grp = g_k1; else ki = key_info<KIND>(c, rec);
         if (ki.grp == kNoGroup) ti.invalid = true;   // not this shard's / bad table
       }
     }
@@ -343,6 +372,8 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
   if (nc == 0) return;                                // uniform across the grid: nothing listed
   cg::grid_group grid = cg::this_grid();
   __shared__ uint64_t skeys[(kThreads / 32) * kBucketCap];   // 16 KB: one 256-key slice per warp; radix counters in the fallback
+  __shared__ uint64_t sres[FastReplay<KIND>::ok ? (kThreads / 32) * kBucketCap : 1];   // replies of a run (fast replay)
+  __shared__ uint32_t sops[FastReplay<KIND>::ok ? (kThreads / 32) * kBucketCap : 1];   // request fields of a run
   __shared__ uint32_t wsum[kThreads / 32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x;
@@ -351,44 +382,99 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
 
   if (overflow == 0) {
     // ---- bucket path: K2 already hashed every listed (group, index) pair into a bucket.  Warps work
-    // independently (no CTA or grid barrier): a warp sorts its bucket in its own 256-key slice of shared
-    // memory -- rank sort by shuffles up to 32 keys, bitonic above -- and replays the runs.
+    // independently (no CTA or grid barrier).  A warp task = `gsz` adjacent buckets (a power of two chosen
+    // so that a task holds ~16 pairs: with few listed requests most buckets hold 0-2 pairs and one latency
+    // chain per bucket would dominate).  The task's pairs are gathered into the warp's 256-key slice of
+    // shared memory, sorted (rank sort by shuffles up to 32 keys, bitonic above; the keys carry the group
+    // id in their high half, so pairs of different buckets may be sorted together) and replayed.
     uint64_t* wkeys = skeys + warp_id() * kBucketCap;
+    uint64_t* wres = sres + (FastReplay<KIND>::ok ? warp_id() * kBucketCap : 0);
+    uint32_t* wops = sops + (FastReplay<KIND>::ok ? warp_id() * kBucketCap : 0);
     const uint32_t lane = lane_id();
     const uint32_t n_warps = gridDim.x * (kThreads / 32);
-    for (uint32_t b = blockIdx.x * (kThreads / 32) + warp_id(); b < P; b += n_warps) {
-      const uint32_t m = c.bcnt[b];
-      if (m == 0) continue;
-      const uint64_t* src = c.buckets + (size_t)b * kBucketCap;
-      if (m <= 32) {
-        const uint64_t key = lane < m ? src[lane] : ~0ULL;
-        uint32_t rank = 0;
+    uint32_t gsz = 1;
+    while (gsz < 32 && (uint64_t)nc * gsz * 2 <= (uint64_t)16 * P) gsz <<= 1;      // mean pairs per task <= ~16
+    const uint32_t n_tasks = (P + gsz - 1) / gsz;
+    for (uint32_t task = blockIdx.x * (kThreads / 32) + warp_id(); task < n_tasks; task += n_warps) {
+      const uint32_t b0 = task * gsz;
+      const uint32_t myb = b0 + lane;
+      const uint32_t cnt = (lane < gsz && myb < P) ? c.bcnt[myb] : 0;
+      uint32_t incl = cnt;                                   // inclusive prefix over the task's buckets
 #pragma unroll
-        for (int j = 0; j < 32; j++) rank += (__shfl_sync(0xffffffffu, key, j) < key) ? 1u : 0u;   // keys are distinct
-        if (lane < m) wkeys[rank] = key;
-      } else {
-        uint32_t npow = 64;
-        while (npow < m) npow <<= 1;
-        for (uint32_t i = lane; i < npow; i += 32) wkeys[i] = i < m ? src[i] : ~0ULL;
-        __syncwarp();
-        for (uint32_t kk = 2; kk <= npow; kk <<= 1)
-          for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < npow; i += 32) {
-              const uint32_t ixj = i ^ j;
-              if (ixj > i) {
-                const uint64_t a = wkeys[i], bb = wkeys[ixj];
-                const bool up = (i & kk) == 0;
-                if ((a > bb) == up) { wkeys[i] = bb; wkeys[ixj] = a; }
-              }
-            }
-            __syncwarp();
-          }
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += y;
       }
-      __syncwarp();
-      for (uint32_t p = lane; p < m; p += 32)
-        if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, wkeys, p, m);
-      __syncwarp();
-      if (lane == 0) c.bcnt[b] = 0;
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) continue;
+      // one pass when everything fits the slice, else bucket by bucket (each bucket alone always fits)
+      const uint32_t n_pass = total <= kBucketCap ? 1 : gsz;
+      for (uint32_t pass = 0; pass < n_pass; pass++) {
+        uint32_t m;
+        if (n_pass == 1) {
+          m = total;
+          for (uint32_t k = 0; k < gsz; k++) {               // gather bucket k at offset excl(k)
+            const uint32_t ck = __shfl_sync(0xffffffffu, cnt, k);
+            const uint32_t ek = __shfl_sync(0xffffffffu, incl, k) - ck;
+            const uint64_t* src = c.buckets + (size_t)(b0 + k) * kBucketCap;
+            for (uint32_t i = lane; i < ck; i += 32) wkeys[ek + i] = src[i];
+          }
+        } else {
+          m = __shfl_sync(0xffffffffu, cnt, pass);
+          const uint64_t* src = c.buckets + (size_t)(b0 + pass) * kBucketCap;
+          for (uint32_t i = lane; i < m; i += 32) wkeys[i] = src[i];
+        }
+        __syncwarp();
+        if (m == 0) continue;
+        if (m <= 32) {
+          const uint64_t key = lane < m ? wkeys[lane] : ~0ULL;
+          uint32_t rank = 0;
+#pragma unroll
+          for (int j = 0; j < 32; j++) rank += (__shfl_sync(0xffffffffu, key, j) < key) ? 1u : 0u;   // keys are distinct
+          __syncwarp();
+          if (lane < m) wkeys[rank] = key;
+        } else {
+          uint32_t npow = 64;
+          while (npow < m) npow <<= 1;
+          for (uint32_t i = m + lane; i < npow; i += 32) wkeys[i] = ~0ULL;
+          __syncwarp();
+          for (uint32_t kk = 2; kk <= npow; kk <<= 1)
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+              for (uint32_t i = lane; i < npow; i += 32) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                  const uint64_t a = wkeys[i], bb = wkeys[ixj];
+                  const bool up = (i & kk) == 0;
+                  if ((a > bb) == up) { wkeys[i] = bb; wkeys[ixj] = a; }
+                }
+              }
+              __syncwarp();
+            }
+        }
+        __syncwarp();
+        if constexpr (FastReplay<KIND>::ok) {
+          using FR = FastReplay<KIND>;
+          using Wq = Wire<KIND>;
+          for (uint32_t p = lane; p < m; p += 32) wops[p] = FR::load_op(c.resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG);
+          __syncwarp();
+          for (uint32_t p = lane; p < m; p += 32)
+            if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) {
+              const uint32_t g = (uint32_t)(wkeys[p] >> 32);
+              typename FR::State st = FR::load_state(c, g);
+              uint32_t q = p;
+              for (; q < m && (uint32_t)(wkeys[q] >> 32) == g; q++) wres[q] = FR::step(st, wops[q]);
+              FR::store_state(c, g, st);
+              if (q - p > 1) atomicMax(&c.counters[2], (unsigned long long)(q - p));
+            }
+          __syncwarp();
+          for (uint32_t p = lane; p < m; p += 32) FR::write_result(c.resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG, wres[p]);
+        } else {
+          for (uint32_t p = lane; p < m; p += 32)
+            if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, wkeys, p, m);
+        }
+        __syncwarp();
+      }
+      if (lane < gsz && myb < P && cnt) c.bcnt[myb] = 0;
     }
   } else {
     // ---- fallback (skewed chunk): stable LSD radix sort of the whole list by group id --------------
@@ -553,9 +639,33 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
       grid.sync();
       uint64_t* tmp = src; src = dst; dst = tmp;
     }
-    // replay: one thread per same-group run
-    for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-      if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, src, p, nc);
+    if constexpr (FastReplay<KIND>::ok) {
+      // replay in three passes: request fields of ALL listed requests (parallel) -> per-run walk with the
+      // group state in registers -> replies (parallel).  ops live in the (now free) clist, replies in `dst`.
+      using FR = FastReplay<KIND>;
+      using Wq = Wire<KIND>;
+      uint32_t* ops_g = c.clist;
+      uint64_t* res_g = dst;
+      for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
+        ops_g[p] = FR::load_op(c.resp + (size_t)(uint32_t)src[p] * Wq::MSG);
+      grid.sync();
+      for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
+        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) {
+          const uint32_t g = (uint32_t)(src[p] >> 32);
+          typename FR::State st = FR::load_state(c, g);
+          uint32_t q = p;
+          for (; q < nc && (uint32_t)(src[q] >> 32) == g; q++) res_g[q] = FR::step(st, ops_g[q]);
+          FR::store_state(c, g, st);
+          if (q - p > 1) atomicMax(&c.counters[2], (unsigned long long)(q - p));
+        }
+      grid.sync();
+      for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
+        FR::write_result(c.resp + (size_t)(uint32_t)src[p] * Wq::MSG, res_g[p]);
+    } else {
+      // replay: one thread per same-group run
+      for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
+        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, src, p, nc);
+    }
   }
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&c.counters[1], (unsigned long long)nc);
 }
