@@ -127,7 +127,7 @@ def run_fasst(args, torch, dist, rank, world, fam_name, fam, steps, warmup, do_e
         torch.cuda.synchronize(dev)
         ok &= bool((d_resp.cpu().numpy() == resps[warmup - 1]).all()) if warmup else True
         eng.reset_stats()
-        eng.profile(True)
+        eng.profile(Engine.PROF_APPLY)        # events around the dominant kernel only: all-kernel profiling costs ~20 %
         sampler = ClockSampler(dev.index)
         sampler.start()
         time.sleep(0.01)
@@ -149,6 +149,14 @@ def run_fasst(args, torch, dist, rank, world, fam_name, fam, steps, warmup, do_e
         st = eng.stats()
         ok &= bool((d_resp.cpu().numpy() == resps[n_steps - 1]).all())
         out.update(ms=ms, kernel_times=kt, stats=st, clocks=clocks, parity_last_step=ok)
+        # a second, fully profiled replay (not the timed one) for the per-kernel breakdown
+        eng.reset_stats()
+        eng.profile(True)
+        for s in range(warmup, n_steps):
+            eng.submit_tensor(d_req[s], d_resp)
+        torch.cuda.synchronize(dev)
+        eng.profile(False)
+        out["all_kernel_times"] = eng.kernel_times()
         del d_req
     timed_committed = sum(committed[warmup:])
     timed_reqs = steps * STEP_REQS
@@ -367,8 +375,8 @@ def main():
         return
     peak, peak_how = peaks()
     kt = res["kernel_times"]
-    dom = max(kt.items(), key=lambda kv: kv[1][1])
-    name, (nl, tot_ms) = dom
+    name = "k_apply"
+    nl, tot_ms = kt[name]
     avg_s = tot_ms / nl * 1e-3
     alg_per_launch = res["alg_bytes"] / nl
     achieved = alg_per_launch / avg_s / 1e9
@@ -396,7 +404,7 @@ def main():
         "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_how,
                      "avg_launch_us": avg_s * 1e6, "launches": nl, "algorithmic_bytes_per_launch": alg_per_launch,
-                     "all_kernels_ms": {k: round(v[1], 3) for k, v in kt.items()}},
+                     "all_kernels_ms_profiled_pass": {k: round(v[1], 3) for k, v in res.get("all_kernel_times", kt).items()}},
     }
     if e2e_s:
         line["e2e"] = {"value": committed / e2e_s, "unit": "txn/s", "h2d_bytes_per_step": STEP_REQS * 9 * world,

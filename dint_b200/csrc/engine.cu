@@ -59,6 +59,10 @@ struct dint_engine {
   uint32_t* d_grp[2] = {nullptr, nullptr};   // group ids of the current / previous chunk
   uint64_t chunk_seq = 0;
   uint32_t prev_n = 0;                       // requests of the previous chunk whose flags are still set
+  bool ord_pending = false;                  // the previous chunk's listed requests await their replay
+  uint8_t* ord_resp = nullptr;               //   ... and live in this reply array
+  uint32_t smem_classify = 0;                // K1: max(stages, ordered-replay slices)
+  uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
   // L2 persistence: the flag sets (+ lock_fasst lock bits) live in one arena that every launch maps
   // with a persisting access-policy window, so the streaming request/reply traffic cannot evict it
   uint8_t* hot_arena = nullptr;
@@ -69,7 +73,7 @@ struct dint_engine {
   dint_stats stats{};
   unsigned long long counters_seen[4] = {0, 0, 0, 0};
   // profiling
-  bool profiling = false;
+  uint32_t profiling = 0;          // bit k set: bracket launches of kernel k (KT_*) with CUDA events
   std::vector<EvPair> ev_pool;
   size_t ev_used = 0;
   double kt_ms[KT_NUM] = {0};
@@ -106,7 +110,7 @@ struct ProfScope {
   dint_engine* e; cudaStream_t s; EvPair* p = nullptr;
   ProfScope(dint_engine* e_, cudaStream_t s_, int which) : e(e_), s(s_) {
     e->stats.kernel_launches++;
-    if (!e->profiling) return;
+    if (!((e->profiling >> which) & 1u)) return;
     if (e->ev_used == e->ev_pool.size()) {
       if (e->ev_pool.size() >= 8192) { prof_flush(e); }
       else {
@@ -139,15 +143,19 @@ static cudaError_t launch_ex(dint_engine* e, void (*kern)(Args...), int grid, in
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// One chunk: K1 (classify this chunk + replay the previous chunk's listed requests), K2 (apply), and the
+// fallback launch that only does work when one of THIS chunk's buckets overflowed.  c.n == 0 = flush: K1
+// alone, replaying the last chunk's listed requests.
 template <int KIND, bool HAS_LOG>
 static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
     ProfScope ps(e, s, KT_CLASSIFY);
     int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kTile - 1) / (4 * kTile));
     if (clr > want) want = clr;
-    int grid = want < e->grid_classify ? want : e->grid_classify;
-    CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, kTile, e->smem_stage, s, false, c));
+    int grid = (want < e->grid_classify && !c.ord_pending) ? want : e->grid_classify;
+    CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, kTile, e->smem_classify, s, false, c));
   }
+  if (c.n == 0) { CU(cudaGetLastError()); return DINT_OK; }
   if (HAS_LOG) {
     ProfScope ps(e, s, KT_LOGSCAN);
     k_log_scan<<<1, kThreads, 0, s>>>(c);
@@ -159,7 +167,10 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   }
   if (KIND != K_LOG) {   // the log server has no per-key state: nothing to order
     ProfScope ps(e, s, KT_ORDERED);
-    CU(launch_ex(e, k_ordered<KIND>, e->coop_grid, kThreads, 0, s, true, c));
+    Ctx f = c;           // this chunk's own counters / replies
+    f.nc_ord = c.nc_cur;
+    f.ord_resp = c.resp;
+    CU(launch_ex(e, k_ordered<KIND>, e->coop_grid, kThreads, 0, s, true, f));
   }
   CU(cudaGetLastError());
   return DINT_OK;
@@ -186,7 +197,9 @@ static int grids_for(dint_engine* e) {
     CU(cudaFuncSetAttribute(k_classify<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
     CU(cudaFuncSetAttribute(k_apply<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
   }
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kTile, e->smem_stage));
+  e->smem_classify = e->smem_stage;
+  if (KIND != K_LOG && (kTile / 32) * OrdSlice<KIND>::BYTES > e->smem_classify) e->smem_classify = (kTile / 32) * OrdSlice<KIND>::BYTES;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kTile, e->smem_classify));
   if (per_sm < 1) return set_err(DINT_EIO, "k_classify cannot be resident");
   e->grid_classify = per_sm * sms;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_apply<KIND, HAS_LOG>, kTile, e->smem_stage));
@@ -200,27 +213,61 @@ static int grids_for(dint_engine* e) {
   return DINT_OK;
 }
 
-static int run_device(dint_engine* e, const uint8_t* req, uint64_t n, uint8_t* resp, cudaStream_t s) {
-  for (uint64_t off = 0; off < n; off += e->chunk) {
-    Ctx c = e->ctx;
-    c.n = (uint32_t)((n - off < e->chunk) ? (n - off) : e->chunk);
-    c.n_tiles = (c.n + kTile - 1) / kTile;
-    c.req = req + off * e->msg;
-    c.resp = resp + off * e->msg;
-    const int cur = (int)(e->chunk_seq & 1);
-    c.grp = e->d_grp[cur];
-    c.grp_prev = e->d_grp[cur ^ 1];
-    c.flags = e->d_flags[cur];
-    c.flags_prev = e->d_flags[cur ^ 1];
-    c.prev_n = e->prev_n;
-    int rc = launch_chunk(e, c, s);
-    if (rc) return rc;
-    e->chunk_seq++;
-    e->prev_n = c.n;
-    e->stats.chunks++;
-  }
+static void fill_chunk_ctx(dint_engine* e, Ctx& c) {
+  const int cur = (int)(e->chunk_seq & 1);
+  c.grp = e->d_grp[cur];
+  c.grp_prev = e->d_grp[cur ^ 1];
+  c.flags = e->d_flags[cur];
+  c.flags_prev = e->d_flags[cur ^ 1];
+  c.prev_n = e->prev_n;
+  c.nc_cur = e->d_nc + 2 * cur;
+  c.nc_ord = e->d_nc + 2 * (cur ^ 1);
+  c.ord_pending = e->ord_pending ? 1u : 0u;
+  c.ord_resp = e->ord_resp;
+}
+
+// one chunk (n <= e->chunk); leaves its listed requests pending until the next chunk or flush_ordered()
+static int submit_chunk(dint_engine* e, const uint8_t* req, uint32_t n, uint8_t* resp, cudaStream_t s) {
+  Ctx c = e->ctx;
+  c.n = n;
+  c.n_tiles = (n + kTile - 1) / kTile;
+  c.req = req;
+  c.resp = resp;
+  fill_chunk_ctx(e, c);
+  int rc = launch_chunk(e, c, s);
+  if (rc) return rc;
+  e->chunk_seq++;
+  e->prev_n = n;
+  e->ord_pending = e->kind != DINT_LOG;
+  e->ord_resp = resp;
+  e->stats.chunks++;
   e->stats.requests += n;
   return DINT_OK;
+}
+
+// replays the last chunk's listed requests (and retires its flags); after this every reply is final
+static int flush_ordered(dint_engine* e, cudaStream_t s) {
+  if (!e->ord_pending) return DINT_OK;
+  Ctx c = e->ctx;
+  c.n = 0;
+  c.n_tiles = 0;
+  c.req = nullptr;
+  c.resp = nullptr;
+  fill_chunk_ctx(e, c);
+  int rc = launch_chunk(e, c, s);
+  if (rc) return rc;
+  e->ord_pending = false;
+  e->prev_n = 0;                 // the flush also cleared that chunk's flags
+  return DINT_OK;
+}
+
+static int run_device(dint_engine* e, const uint8_t* req, uint64_t n, uint8_t* resp, cudaStream_t s) {
+  for (uint64_t off = 0; off < n; off += e->chunk) {
+    uint32_t cn = (uint32_t)((n - off < e->chunk) ? (n - off) : e->chunk);
+    int rc = submit_chunk(e, req + off * e->msg, cn, resp + off * e->msg, s);
+    if (rc) return rc;
+  }
+  return flush_ordered(e, s);
 }
 
 static int pull_counters(dint_engine* e) {
@@ -370,7 +417,7 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.clist, (size_t)e->max_tiles * kTile))) return rc;
   if ((rc = dalloc(e, &c.ccnt, e->max_tiles))) return rc;
   if ((rc = dalloc(e, &c.cprefix, e->max_tiles + 1))) return rc;
-  if ((rc = dalloc(e, &c.nc_total, 2))) return rc;
+  if ((rc = dalloc(e, &e->d_nc, 4))) return rc;
   {
     uint32_t lg = 0;
     while (((uint64_t)kBucketFill << lg) < ch) lg++;
@@ -483,25 +530,40 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
   const uint8_t* rq = (const uint8_t*)req;
   uint8_t* rs = (uint8_t*)resp;
   unsigned long long err_before = e->stats.errors;
-  // three-stage pipeline over chunks: H2D (s_in) | kernels (stream) | D2H (s_out), double buffered
+  // three-stage pipeline over chunks: H2D (s_in) | kernels (stream) | D2H (s_out), double buffered.  Chunk
+  // k's replies are final only after the launch that replays its listed requests: K1 of chunk k+1, or the
+  // flush after the last chunk -- so D2H(k) is ordered behind that.
   uint64_t k = 0;
+  uint64_t prev_off = 0, prev_bytes = 0;
+  auto copy_out_prev = [&](uint64_t kk) -> int {          // D2H of chunk kk-1 (buffer (kk-1)&1)
+    int pb = (int)((kk - 1) & 1);
+    CU(cudaEventRecord(e->ev_comp[pb], e->stream));
+    CU(cudaStreamWaitEvent(e->s_out, e->ev_comp[pb], 0));
+    CU(cudaMemcpyAsync(rs + prev_off, e->d_resp[pb], prev_bytes, cudaMemcpyDeviceToHost, e->s_out));
+    CU(cudaEventRecord(e->ev_out[pb], e->s_out));
+    return DINT_OK;
+  };
   for (uint64_t off = 0; off < n; off += e->chunk, k++) {
     int b = (int)(k & 1);
     uint64_t cn = (n - off < e->chunk) ? (n - off) : e->chunk;
     size_t bytes = (size_t)cn * e->msg;
-    if (k >= 2) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));     // kernels of chunk k-2 done with d_req[b]
+    if (k >= 2) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));     // everything that read d_req[b] (chunk k-2) is done
     CU(cudaMemcpyAsync(e->d_req[b], rq + off * e->msg, bytes, cudaMemcpyHostToDevice, e->s_in));
     CU(cudaEventRecord(e->ev_in[b], e->s_in));
     CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
     if (k >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0));    // D2H of chunk k-2 done with d_resp[b]
-    int rc = run_device(e, e->d_req[b], cn, e->d_resp[b], e->stream);
+    int rc = submit_chunk(e, e->d_req[b], (uint32_t)cn, e->d_resp[b], e->stream);
     if (rc) return rc;
-    CU(cudaEventRecord(e->ev_comp[b], e->stream));
-    CU(cudaStreamWaitEvent(e->s_out, e->ev_comp[b], 0));
-    CU(cudaMemcpyAsync(rs + off * e->msg, e->d_resp[b], bytes, cudaMemcpyDeviceToHost, e->s_out));
-    CU(cudaEventRecord(e->ev_out[b], e->s_out));
+    if (k >= 1 && (rc = copy_out_prev(k))) return rc;                   // chunk k-1 is final now
+    prev_off = off * e->msg;
+    prev_bytes = bytes;
     e->stats.h2d_bytes += bytes;
     e->stats.d2h_bytes += bytes;
+  }
+  {
+    int rc = flush_ordered(e, e->stream);
+    if (rc) return rc;
+    if (k >= 1 && (rc = copy_out_prev(k))) return rc;
   }
   CU(cudaStreamSynchronize(e->s_out));
   CU(cudaStreamSynchronize(e->stream));
@@ -584,7 +646,7 @@ int dint_profile(dint_engine* e, int enable) {
   CU(cudaSetDevice(e->device));
   CU(cudaDeviceSynchronize());
   int rc = prof_flush(e);
-  e->profiling = enable != 0;
+  e->profiling = enable < 0 ? 0u : (uint32_t)enable == 1u ? 0xffffffffu : (uint32_t)enable;   // 1 = all kernels; else a bit mask
   return rc;
 }
 int dint_kernel_times(dint_engine* e, dint_kernel_time* out, int max_entries) {

@@ -18,11 +18,16 @@
 //                 directly, one thread each, against the HBM-resident state and their tile is
 //                 written back with one bulk store.  The others are listed, in index order, for K3.
 //                 Persistent CTAs run a 3-stage TMA pipeline over the tiles.
-//   K3 ordered  : one cooperative launch.  K2 hashes the listed (group, index) pairs into buckets of
-//                 <= 256; each bucket is sorted in shared memory (a warp for <= 32 pairs, else a CTA) and every
-//                 same-group run is replayed in index order by one thread using the very same
-//                 per-request function as K2.  Heavily skewed chunks that overflow a bucket fall
-//                 back to a stable LSD radix sort over the whole list.
+//   ordered replay: K2 hashes the listed (group, index) pairs into buckets of <= 128.  The NEXT launch of
+//                 K1 (or a flush launch at the end of a submit call) replays them while it classifies
+//                 the next chunk: a warp gathers a few adjacent buckets into its slice of shared memory,
+//                 sorts the pairs (rank sort by shuffles up to 32, bitonic above) and replays every
+//                 same-group run in index order -- request fields fetched in parallel, the group's state
+//                 walked in registers, replies written in parallel (lock servers), or request by request
+//                 with the very same apply_one as K2 (KV servers).  No grid-wide barrier is involved.
+//   K3 fallback : heavily skewed chunks that overflow a bucket (HOT: 4800 ids) are instead sorted whole
+//                 by a stable LSD radix sort (cooperative launch, grid barriers) and replayed; the
+//                 launch exits at once when no bucket overflowed.
 //
 // apply_one<KIND>() below is therefore the single statement of each server's request semantics.
 #pragma once
@@ -36,7 +41,7 @@ constexpr int kTile = 128;       // wire records per tile = threads per CTA in K
                                  // latency chains, per SM)
 constexpr int kThreads = 256;    // threads per CTA of the other kernels (K3's radix passes rely on 256)
 constexpr int kMaxTables = 5;
-constexpr uint32_t kBucketCap = 256;    // K3: bucket capacity (sorted in shared memory)
+constexpr uint32_t kBucketCap = 128;    // ordered replay: bucket capacity (sorted in a warp's slice of shared memory)
 constexpr uint32_t kBucketFill = 64;    // K3: chunk / kBucketFill buckets (mean occupancy 64 if EVERY request were listed)
 constexpr int kStages = 3;              // TMA pipeline depth of the persistent K1/K2 CTAs
 
@@ -97,7 +102,10 @@ struct Ctx {
   uint32_t* clist;         // [n_tiles][kTile] indices of listed requests, tile-segmented
   uint32_t* ccnt;          // [n_tiles] listed requests per tile
   uint32_t* cprefix;       // [n_tiles+1] exclusive prefix of ccnt (K3 general path)
-  uint32_t* nc_total;      // [2]: [0] listed requests of this chunk, [1] bucket overflows
+  uint32_t* nc_cur;        // [2] of THIS chunk: [0] listed requests, [1] bucket overflows (K1 resets, K2 counts)
+  const uint32_t* nc_ord;  // [2] of the chunk whose listed requests are replayed by this launch
+  uint8_t* ord_resp;       // reply array of that chunk (K2 left the listed requests' bytes there)
+  uint32_t ord_pending;    // 1: a previous chunk still has listed requests to replay (done inside K1)
   uint64_t* buckets;       // [2^bucket_log2][kBucketCap] (group << 32 | index), filled by K2
   uint32_t* bcnt;          // [2^bucket_log2]
   uint32_t bucket_log2;

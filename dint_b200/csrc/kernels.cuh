@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uin
   owner[i] = (uint8_t)o;
 }
 
+// ordered replay (defined below): per-warp shared-memory slice and the replay itself
+template <int KIND> struct OrdSlice {
+  static constexpr uint32_t BYTES = kBucketCap * (FastReplay<KIND>::ok ? (8 + 8 + 4) : 8);
+};
+template <int KIND> DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch);
+
 // ---------------------------------------------------------------------------------------------------
 // K1 classify (+ clears the flag words of the previous chunk)
 // ---------------------------------------------------------------------------------------------------
@@ -134,9 +140,18 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   __shared__ uint32_t scratch[kTile / 32];
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
-    if (blockIdx.x == 0) { c.nc_total[0] = 0; c.nc_total[1] = 0; }
+    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; }
   }
   __syncthreads();
+  // The previous chunk's listed requests are replayed by this launch too (their buckets were filled by its
+  // K2; a bucket overflow was already handled by the fallback launch).  Odd CTAs replay first and classify
+  // afterwards, even CTAs the other way round, so the latency-bound replay overlaps classification.
+  const bool do_ord = c.ord_pending && c.nc_ord[0] != 0 && c.nc_ord[1] == 0;
+  const bool ord_first = (blockIdx.x & 1u) != 0;
+  if (do_ord && ord_first) {
+    ordered_buckets<KIND>(c, smem);
+    __syncthreads();
+  }
   const TileIter it = tile_iter(c.n_tiles);
   if (threadIdx.x == 0)
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
@@ -204,6 +219,10 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     }
   }
   if (pend_w && ((pend_old >> pend_sh) & pend_test)) atomicOr(pend_w, F_W2 << pend_sh);
+  if (do_ord && !ord_first) {
+    __syncthreads();                                     // the stages double as the replay's scratch
+    ordered_buckets<KIND>(c, smem);
+  }
 }
 
 // K1b: absolute append ordinal of every tile's first log append (single CTA).
@@ -316,11 +335,11 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
         const uint32_t b = bucket_of(ki.grp, c.bucket_log2);
         const uint32_t pos = atomicAdd(&c.bcnt[b], 1u);
         if (pos < kBucketCap) c.buckets[(size_t)b * kBucketCap + pos] = ((uint64_t)ki.grp << 32) | idx;
-        else atomicAdd(&c.nc_total[1], 1u);
+        else atomicAdd(&c.nc_cur[1], 1u);
       }
       if (threadIdx.x == 0) {
         c.ccnt[t] = n_list;
-        if (n_list) atomicAdd(&c.nc_total[0], n_list);
+        if (n_list) atomicAdd(&c.nc_cur[0], n_list);
       }
     }
     if (valid) {
@@ -349,14 +368,14 @@ constexpr int kSortItems = 8;                         // items per thread per ra
 constexpr int kSortTile = kThreads * kSortItems;      // 2048
 
 template <int KIND>
-DINT_D void replay_run(const Ctx& c, const uint64_t* sorted, uint32_t p, uint32_t nc) {
+DINT_D void replay_run(const Ctx& c, uint8_t* resp, const uint64_t* sorted, uint32_t p, uint32_t nc) {
   using W = Wire<KIND>;
   const uint32_t g = (uint32_t)(sorted[p] >> 32);
   uint32_t len = 0;
   for (uint32_t q = p; q < nc; q++) {
     uint64_t e = sorted[q];
     if ((uint32_t)(e >> 32) != g) break;
-    uint8_t* rec = c.resp + (size_t)(uint32_t)e * W::MSG;     // K2 left the request bytes here
+    uint8_t* rec = resp + (size_t)(uint32_t)e * W::MSG;       // K2 left the request bytes here
     const TypeInfo ti = type_info<KIND>(rec);
     const KeyInfo ki = key_info<KIND>(c, rec);
     const Pre<KIND> pf = prefetch<KIND>(c, rec, ki, ti);      // fetched AFTER the previous request of the run
@@ -366,36 +385,28 @@ DINT_D void replay_run(const Ctx& c, const uint64_t* sorted, uint32_t p, uint32_
   if (len > 1) atomicMax(&c.counters[2], (unsigned long long)len);
 }
 
+// Ordered replay of the listed requests of a finished chunk (see engine.cuh).  Called by every warp of the
+// grid; `scratch` = blockDim.x/32 slices of OrdSlice<KIND>::BYTES.
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
-  const uint32_t nc = c.nc_total[0];
-  if (nc == 0) return;                                // uniform across the grid: nothing listed
-  cg::grid_group grid = cg::this_grid();
-  __shared__ uint64_t skeys[(kThreads / 32) * kBucketCap];   // 16 KB: one 256-key slice per warp; radix counters in the fallback
-  __shared__ uint64_t sres[FastReplay<KIND>::ok ? (kThreads / 32) * kBucketCap : 1];   // replies of a run (fast replay)
-  __shared__ uint32_t sops[FastReplay<KIND>::ok ? (kThreads / 32) * kBucketCap : 1];   // request fields of a run
-  __shared__ uint32_t wsum[kThreads / 32];
-  __shared__ uint32_t s_carry;
-  const uint32_t tid = threadIdx.x;
-  const uint32_t P = 1u << c.bucket_log2;
-  const uint32_t overflow = c.nc_total[1];
-
-  if (overflow == 0) {
-    // ---- bucket path: K2 already hashed every listed (group, index) pair into a bucket.  Warps work
+DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch) {
+    // K2 already hashed every listed (group, index) pair into a bucket.  Warps work
     // independently (no CTA or grid barrier).  A warp task = `gsz` adjacent buckets (a power of two chosen
     // so that a task holds ~16 pairs: with few listed requests most buckets hold 0-2 pairs and one latency
     // chain per bucket would dominate).  The task's pairs are gathered into the warp's 256-key slice of
     // shared memory, sorted (rank sort by shuffles up to 32 keys, bitonic above; the keys carry the group
     // id in their high half, so pairs of different buckets may be sorted together) and replayed.
-    uint64_t* wkeys = skeys + warp_id() * kBucketCap;
-    uint64_t* wres = sres + (FastReplay<KIND>::ok ? warp_id() * kBucketCap : 0);
-    uint32_t* wops = sops + (FastReplay<KIND>::ok ? warp_id() * kBucketCap : 0);
+    uint64_t* wkeys = (uint64_t*)(scratch + (size_t)warp_id() * OrdSlice<KIND>::BYTES);
+    uint64_t* wres = wkeys + kBucketCap;                       // fast replay only
+    uint32_t* wops = (uint32_t*)(wkeys + 2 * kBucketCap);      // fast replay only
     const uint32_t lane = lane_id();
-    const uint32_t n_warps = gridDim.x * (kThreads / 32);
+    const uint32_t warps_per_cta = blockDim.x / 32;
+    const uint32_t n_warps = gridDim.x * warps_per_cta;
+    const uint32_t P = 1u << c.bucket_log2;
+    const uint32_t nc = c.nc_ord[0];
     uint32_t gsz = 1;
     while (gsz < 32 && (uint64_t)nc * gsz * 2 <= (uint64_t)16 * P) gsz <<= 1;      // mean pairs per task <= ~16
     const uint32_t n_tasks = (P + gsz - 1) / gsz;
-    for (uint32_t task = blockIdx.x * (kThreads / 32) + warp_id(); task < n_tasks; task += n_warps) {
+    for (uint32_t task = blockIdx.x * warps_per_cta + warp_id(); task < n_tasks; task += n_warps) {
       const uint32_t b0 = task * gsz;
       const uint32_t myb = b0 + lane;
       const uint32_t cnt = (lane < gsz && myb < P) ? c.bcnt[myb] : 0;
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
         if constexpr (FastReplay<KIND>::ok) {
           using FR = FastReplay<KIND>;
           using Wq = Wire<KIND>;
-          for (uint32_t p = lane; p < m; p += 32) wops[p] = FR::load_op(c.resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG);
+          for (uint32_t p = lane; p < m; p += 32) wops[p] = FR::load_op(c.ord_resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG);
           __syncwarp();
           for (uint32_t p = lane; p < m; p += 32)
             if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) {
@@ -467,16 +478,30 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
               if (q - p > 1) atomicMax(&c.counters[2], (unsigned long long)(q - p));
             }
           __syncwarp();
-          for (uint32_t p = lane; p < m; p += 32) FR::write_result(c.resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG, wres[p]);
+          for (uint32_t p = lane; p < m; p += 32) FR::write_result(c.ord_resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG, wres[p]);
         } else {
           for (uint32_t p = lane; p < m; p += 32)
-            if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, wkeys, p, m);
+            if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, c.ord_resp, wkeys, p, m);
         }
         __syncwarp();
       }
       if (lane < gsz && myb < P && cnt) c.bcnt[myb] = 0;
     }
-  } else {
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c.counters[1], (unsigned long long)c.nc_ord[0]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
+  const uint32_t nc = c.nc_ord[0];
+  const uint32_t overflow = c.nc_ord[1];
+  if (nc == 0 || overflow == 0) return;               // the bucket path (inside the next K1) handles this chunk
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint64_t skeys[2048];                    // radix counters
+  __shared__ uint32_t wsum[kThreads / 32];
+  __shared__ uint32_t s_carry;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t P = 1u << c.bucket_log2;
+  {
     // ---- fallback (skewed chunk): stable LSD radix sort of the whole list by group id --------------
     for (uint32_t b = blockIdx.x * kThreads + tid; b < P; b += gridDim.x * kThreads) c.bcnt[b] = 0;
     // (0) exclusive prefix of the per-tile list lengths (CTA 0)
@@ -647,7 +672,7 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
       uint32_t* ops_g = c.clist;
       uint64_t* res_g = dst;
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        ops_g[p] = FR::load_op(c.resp + (size_t)(uint32_t)src[p] * Wq::MSG);
+        ops_g[p] = FR::load_op(c.ord_resp + (size_t)(uint32_t)src[p] * Wq::MSG);
       grid.sync();
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
         if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) {
@@ -660,11 +685,11 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
         }
       grid.sync();
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        FR::write_result(c.resp + (size_t)(uint32_t)src[p] * Wq::MSG, res_g[p]);
+        FR::write_result(c.ord_resp + (size_t)(uint32_t)src[p] * Wq::MSG, res_g[p]);
     } else {
       // replay: one thread per same-group run
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, src, p, nc);
+        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, c.ord_resp, src, p, nc);
     }
   }
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&c.counters[1], (unsigned long long)nc);

@@ -269,8 +269,11 @@ class Engine:
     def reset_stats(self):
         lib().dint_reset_stats(self.h)
 
+    PROF_CLASSIFY, PROF_LOG_SCAN, PROF_APPLY, PROF_ORDERED, PROF_LOAD = 1, 2, 4, 8, 16
+
     def profile(self, enable=True):
-        rc = lib().dint_profile(self.h, 1 if enable else 0)
+        """True/1 = time every kernel with CUDA events, False/0 = off, or a mask of Engine.PROF_*."""
+        rc = lib().dint_profile(self.h, int(enable))
         if rc != 0:
             raise DintError(rc, "dint_profile")
 

@@ -167,7 +167,7 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
         last = se.submit_tensor(d_req[s])
     torch.cuda.synchronize(dev)
     se.engine.reset_stats()
-    se.engine.profile(True)
+    se.engine.profile(Engine.PROF_APPLY)
     sampler = B.ClockSampler(dev.index)
     sampler.start()
     dist_mod.barrier()

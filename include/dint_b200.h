@@ -148,7 +148,9 @@ uint32_t dint_log_entry_size(int kind);
 
 int dint_get_stats(dint_engine *e, dint_stats *s);
 void dint_reset_stats(dint_engine *e);
-int dint_profile(dint_engine *e, int enable);            /* per-kernel CUDA-event timing on/off */
+/* per-kernel CUDA-event timing: 0 = off, 1 = every kernel, otherwise a bit mask over
+ * {1<<0 k_classify, 1<<1 k_log_scan, 1<<2 k_apply, 1<<3 k_ordered, 1<<4 k_kv_load} */
+int dint_profile(dint_engine *e, int enable);
 int dint_kernel_times(dint_engine *e, dint_kernel_time *out, int max_entries);  /* returns #entries */
 const char *dint_last_error(void);
 

@@ -17,6 +17,13 @@ def probe(kind, req, reps=5, **cfg):
         for _ in range(2):
             eng.submit_tensor(d, out)
         torch.cuda.synchronize()
+        # wall time without per-kernel event profiling
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.submit_tensor(d, out)
+        e1.record(); torch.cuda.synchronize()
+        ms_noprof = e0.elapsed_time(e1) / reps
         eng.reset_stats(); eng.profile(True)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -26,7 +33,7 @@ def probe(kind, req, reps=5, **cfg):
         ms = e0.elapsed_time(e1) / reps
         eng.sync()
         kt = eng.kernel_times(); st = eng.stats()
-        print(f"{wire.KIND_NAMES[kind]:10s} n={n} chunk={eng.cfg.chunk} {ms:8.3f} ms/pass  {n/ms/1e3:9.1f} Mreq/s  conflicted={st['conflicted']/reps:.0f} max_run={st['max_run']}")
+        print(f"{wire.KIND_NAMES[kind]:10s} n={n} chunk={eng.cfg.chunk} {ms:8.3f} ms/pass (unprofiled {ms_noprof:.3f} ms = {n/ms_noprof/1e3:.0f} Mreq/s)  {n/ms/1e3:9.1f} Mreq/s  conflicted={st['conflicted']/reps:.0f} max_run={st['max_run']}")
         for k, (l, t) in kt.items():
             print(f"      {k:12s} launches={l:5d} avg={t/l*1e3:9.1f} us total={t:8.3f} ms")
 
