@@ -550,9 +550,18 @@ struct KvBatch {
   int table;
   std::function<int(int, const uint64_t*, const void*, uint64_t)> sink;
   int rc = 0;
-  KvBatch(int table_, uint32_t valsz_, std::function<int(int, const uint64_t*, const void*, uint64_t)> s)
-      : valsz(valsz_), table(table_), sink(std::move(s)) { keys.reserve(1 << 20); vals.reserve((size_t)valsz << 20); }
+  KvBatch(int table_, uint32_t valsz_, std::function<int(int, const uint64_t*, const void*, uint64_t)> s, const dint_cfg& cf)
+      : valsz(valsz_), table(table_), sink(std::move(s)), G(cf.txn_shards), gid(cf.txn_shard_id) {
+    keys.reserve(1 << 20);
+    vals.reserve((size_t)valsz << 20);
+  }
+  uint32_t G = 0, gid = 0;                           // replica filter (dint_cfg.txn_shards / txn_shard_id)
+  std::vector<uint8_t> dummy;
   uint8_t* add(uint64_t key) {                       // returns the zeroed value slot
+    if (G > 3) {                                     // not one of this key's three replica holders: drop it
+      const uint32_t p = (uint32_t)(key % G), d = (gid + G - p) % G;
+      if (d > 2) { dummy.assign(valsz, 0); return dummy.data(); }
+    }
     if (keys.size() == (1u << 20)) flush();
     keys.push_back(key);
     vals.resize(vals.size() + valsz, 0);
@@ -570,7 +579,7 @@ struct KvBatch {
 // data_b[1..], tatp_callfwd_val_t.numberx[1..]) are zero here -- as they read back from oracle/_ref.
 inline int kv_populate(int kind, const dint_cfg& cf, std::function<int(int, const uint64_t*, const void*, uint64_t)> sink) {
   if (kind == DINT_STORE) {                          // store/udp/tatp.h:45-66
-    KvBatch b(0, 40, sink);
+    KvBatch b(0, 40, sink, cf);
     uint64_t seed = 0xdeadbeef;
     for (uint32_t s = 0; s < cf.subs_populate; s++)
       for (uint64_t sf = 1; sf <= 4; sf++)
@@ -583,7 +592,7 @@ inline int kv_populate(int kind, const dint_cfg& cf, std::function<int(int, cons
     return b.rc;
   }
   if (kind == DINT_SMALLBANK) {                      // smallbank/udp/smallbank.h:105-127
-    KvBatch sav(0, 8, sink), chk(1, 8, sink);
+    KvBatch sav(0, 8, sink, cf), chk(1, 8, sink, cf);
     const float bal = 1000000000.0f;
     for (uint32_t a = 0; a < cf.accts_populate; a++) {
       uint8_t* v = sav.add(a);
@@ -599,7 +608,7 @@ inline int kv_populate(int kind, const dint_cfg& cf, std::function<int(int, cons
   if (kind != DINT_TATP) return DINT_OK;
   const uint32_t N = cf.subs_populate;
   {                                                  // tatp/udp/tatp.h:285-311 subscriber
-    KvBatch b(0, 40, sink);
+    KvBatch b(0, 40, sink, cf);
     uint64_t seed = 0xdeadbeef;
     for (uint32_t s = 0; s < N; s++) {
       uint8_t* v = b.add(s);
@@ -616,7 +625,7 @@ inline int kv_populate(int kind, const dint_cfg& cf, std::function<int(int, cons
     if (b.rc) return b.rc;
   }
   {                                                  // :314-329 secondary subscriber
-    KvBatch b(1, 40, sink);
+    KvBatch b(1, 40, sink, cf);
     for (uint32_t s = 0; s < N; s++) {
       uint8_t* v = b.add(tatp_sub_nbr_of(s));
       memcpy(v, &s, 4);
@@ -626,7 +635,7 @@ inline int kv_populate(int kind, const dint_cfg& cf, std::function<int(int, cons
     if (b.rc) return b.rc;
   }
   {                                                  // :332-357 access info
-    KvBatch b(2, 40, sink);
+    KvBatch b(2, 40, sink, cf);
     uint64_t seed = 0xdeadbeef;
     for (uint32_t s = 0; s < N; s++) {
       uint8_t ty[4];
@@ -637,7 +646,7 @@ inline int kv_populate(int kind, const dint_cfg& cf, std::function<int(int, cons
     if (b.rc) return b.rc;
   }
   {                                                  // :360-412 special facility + call forwarding
-    KvBatch sf(3, 40, sink), cfw(4, 40, sink);
+    KvBatch sf(3, 40, sink, cf), cfw(4, 40, sink, cf);
     uint64_t seed = 0xdeadbeef;
     for (uint32_t s = 0; s < N; s++) {
       uint8_t ty[4];

@@ -518,7 +518,8 @@ extern "C" {
 // = kSubscriberNum of the key generator (reference 7,000,000; must equal the servers' population).
 // kind 5 (smallbank): `subscribers` = kAccountNum (reference 24,000,000), hot set = 4 % of it (960,000).
 dint_txn* dint_txn_create(int kind, uint32_t n_clients, uint32_t gid0, uint32_t n_shards, uint32_t subscribers) {
-  if ((kind != 4 && kind != 5) || n_clients == 0 || n_shards == 0 || n_shards > 8 || subscribers < 3) return nullptr;
+  // primary + 2 distinct backups need >= 3 shards; 1 = everything on one server (three copies of each write)
+  if ((kind != 4 && kind != 5) || n_clients == 0 || n_shards == 0 || n_shards == 2 || n_shards > 8 || subscribers < 3) return nullptr;
   dint_txn* w = new dint_txn();
   w->kind = kind; w->n_clients = n_clients; w->G = n_shards; w->subscribers = subscribers;
   if (kind == 4) {

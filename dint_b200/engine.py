@@ -19,7 +19,8 @@ class DintCfg(C.Structure):
     _fields_ = [("lock_slots", C.c_uint32), ("log_ring", C.c_uint32), ("subs_sizing", C.c_uint32),
                 ("subs_populate", C.c_uint32), ("accts_sizing", C.c_uint32), ("accts_populate", C.c_uint32),
                 ("n_shards", C.c_uint32), ("shard_id", C.c_uint32), ("chunk", C.c_uint32),
-                ("kv_capacity_log2", C.c_uint32 * 5), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("kv_capacity_log2", C.c_uint32 * 5), ("flags", C.c_uint32), ("txn_shards", C.c_uint32),
+                ("txn_shard_id", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class DintStats(C.Structure):

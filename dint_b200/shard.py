@@ -60,7 +60,10 @@ class ShardedEngine:
     local_submit (optional) replaces the GPU engine by any callable req_bytes -> resp_bytes (the CPU tests
     plug the oracle in to check the routing logic without a GPU)."""
 
-    def __init__(self, kind, device=None, local_submit=None, group=None, **cfg_over):
+    def __init__(self, kind, device=None, local_submit=None, group=None, by_dst=False, **cfg_over):
+        """by_dst=True: tatp / smallbank placement -- the CLIENT names the destination shard of every record
+        (primary key % G, backups, log); each rank is one complete `server_shard` (n_shards = 1) that
+        populates only the keys it is a replica holder of (cfg txn_shards = world)."""
         self.kind = kind
         self.msg = wire.MSG_SIZE[kind]
         self.group = group
@@ -72,7 +75,10 @@ class ShardedEngine:
         self.engine = None
         if local_submit is None:
             self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-            self.engine = Engine(kind, device=self.device.index, n_shards=self.world, shard_id=self.rank, **cfg_over)
+            if by_dst:
+                self.engine = Engine(kind, device=self.device.index, txn_shards=self.world, txn_shard_id=self.rank, **cfg_over)
+            else:
+                self.engine = Engine(kind, device=self.device.index, n_shards=self.world, shard_id=self.rank, **cfg_over)
         else:
             self.device = torch.device("cpu")
             from . import engine as _e
@@ -92,11 +98,14 @@ class ShardedEngine:
         self.engine.populate()       # dint_load keeps only this shard's keys
 
     # ---- the collective request path -------------------------------------------------------------
-    def submit_tensor(self, req):
-        """req: uint8 tensor [n * msg] on this rank's device; returns the replies, same layout/order."""
+    def submit_tensor(self, req, dst=None):
+        """req: uint8 tensor [n * msg] on this rank's device; returns the replies, same layout/order.
+        dst: optional uint8 tensor [n] of client-chosen destination shards (tatp / smallbank)."""
         n = req.numel() // self.msg
         rec = req.view(n, self.msg)
-        if self.engine is not None:
+        if dst is not None:
+            owner = dst
+        elif self.engine is not None:
             owner = self.engine.route_owner(req)
         else:
             owner = torch.from_numpy(owners_cpu(self.kind, self.cfg, self.world, self.rank, req.numpy()))
@@ -124,12 +133,14 @@ class ShardedEngine:
         out.index_copy_(0, order, back)
         return out.view(-1)
 
-    def submit(self, req_host):
+    def submit(self, req_host, dst_host=None):
         """Host path: numpy uint8 in, numpy uint8 out (H2D, collective device step, D2H)."""
         t = torch.from_numpy(np.ascontiguousarray(req_host, dtype=np.uint8).reshape(-1))
+        d = None if dst_host is None else torch.from_numpy(np.ascontiguousarray(dst_host, dtype=np.uint8))
         if self.engine is not None:
             t = t.to(self.device, non_blocking=True)
-        out = self.submit_tensor(t)
+            d = None if d is None else d.to(self.device, non_blocking=True)
+        out = self.submit_tensor(t, d)
         return out.cpu().numpy()
 
 

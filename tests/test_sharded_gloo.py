@@ -88,3 +88,59 @@ def test_owner_host_twin_matches_reference_slot():
     rec = wire.as_records(wire.FASST, req)
     want = np.array([ora.lock_slot(0, int(l)) % 8 for l in rec["lid"]], dtype=np.uint8)
     assert np.array_equal(own, want)
+
+
+def _txn_worker(rank, world, port, kind, n, clients, rounds, ret):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as O
+    from dint_b200 import wire
+    from dint_b200.shard import ShardedEngine
+    from dint_b200.txn_workloads import TxnWorkload, Cluster
+    try:
+        cfg = dict(subs_populate=n) if kind == wire.TATP else dict(accts_populate=n)
+        msg = wire.MSG_SIZE[kind]
+        ora = O.Oracle(kind, **cfg)                              # this rank IS shard `rank`
+        se = ShardedEngine(kind, local_submit=ora.process, by_dst=True)
+        wl = TxnWorkload(kind, n_clients=clients, n_shards=world, subscribers=n, gid0=rank * clients)
+        got = []
+        for _ in range(rounds):
+            rq, dst = wl.next()
+            rs = se.submit(rq, dst)
+            wl.feed(rs)
+            got.append(rs.copy())
+        # expectation: all ranks' clients in ONE process against `world` oracle shards, rank-major per round
+        oras = [O.Oracle(kind, **cfg) for _ in range(world)]
+        cl = Cluster([o.process for o in oras], msg)
+        wls = [TxnWorkload(kind, n_clients=clients, n_shards=world, subscribers=n, gid0=r * clients) for r in range(world)]
+        ok = True
+        for i in range(rounds):
+            parts = [w.next() for w in wls]
+            rq = np.concatenate([p[0] for p in parts])
+            dst = np.concatenate([p[1] for p in parts])
+            rs = cl.submit(rq, dst)
+            off = 0
+            for r, (w, p) in enumerate(zip(wls, parts)):
+                seg = rs[off:off + p[0].size]
+                off += p[0].size
+                w.feed(seg)
+                if r == rank:
+                    ok &= bool(np.array_equal(seg, got[i]))
+        ret[rank] = ok and wl.stats() == wls[rank].stats() and wl.stats()["committed"] > 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,n", [(4, 1500), (5, 3000)])
+def test_txn_routing_by_client_chosen_shard_world3(kind, n):
+    """tatp / smallbank: the client names the destination shard (primary, backups, log); three ranks = the
+    reference's three shard servers must reproduce a single-process three-shard cluster reply for reply.
+    (The primary + 2 backups scheme needs >= 3 shards: with 2, backup (p+2) % G would be the primary.)"""
+    world = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_txn_worker, args=(world, _free_port(), kind, n, 300, 40, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: True for r in range(world)}
