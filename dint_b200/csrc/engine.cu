@@ -36,6 +36,7 @@ enum { KT_CLASSIFY = 0, KT_LOGSCAN, KT_APPLY, KT_ORDERED, KT_LOAD, KT_NUM };
 static const char* kKernelNames[KT_NUM] = {"k_classify", "k_log_scan", "k_apply", "k_ordered", "k_kv_load"};
 
 struct EvPair { cudaEvent_t a, b; int which; };
+constexpr int kHostBufs = 4;      // device staging buffers of the host path (dint_submit)
 
 struct dint_engine {
   int kind = 0;
@@ -48,9 +49,10 @@ struct dint_engine {
   Ctx ctx{};                       // device pointers + constants; per-launch fields filled per chunk
   std::vector<void*> allocs;       // everything to cudaFree
   cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-  uint8_t* d_req[2] = {nullptr, nullptr};
-  uint8_t* d_resp[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in[2]{}, ev_comp[2]{}, ev_out[2]{};
+  uint8_t* d_req[kHostBufs] = {nullptr};
+  uint8_t* d_resp[kHostBufs] = {nullptr};
+  cudaEvent_t ev_in[kHostBufs]{}, ev_comp[kHostBufs]{}, ev_out[kHostBufs]{};
+  uint32_t host_chunk = 0;                   // requests per host-path slice
   int coop_grid = 0;
   int grid_classify = 0, grid_apply = 0;     // persistent CTAs (SMs x resident CTAs per SM)
   uint32_t smem_stage = 0;                   // dynamic shared memory of K1/K2: kStages staged tiles
@@ -63,6 +65,8 @@ struct dint_engine {
   uint8_t* ord_resp = nullptr;               //   ... and live in this reply array
   uint32_t smem_classify = 0;                // K1: max(stages, ordered-replay slices)
   uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
+  uint32_t* d_route = nullptr;               // multi-GPU dispatch scratch (per-tile per-shard counts)
+  uint32_t route_tiles = 0;
   // L2 persistence: the flag sets (+ lock_fasst lock bits) live in one arena that every launch maps
   // with a persisting access-policy window, so the streaming request/reply traffic cannot evict it
   uint8_t* hot_arena = nullptr;
@@ -279,6 +283,16 @@ static int pull_counters(dint_engine* e) {
   return DINT_OK;
 }
 
+template <int MSG>
+static void route_scatter_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, uint32_t world, const uint32_t* tb, uint8_t* out,
+                            uint32_t* perm, uint32_t tiles, cudaStream_t s) {
+  k_route_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, out, perm);
+}
+template <int MSG>
+static void route_unpermute_t(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out, cudaStream_t s) {
+  k_route_unpermute<MSG><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(sorted, perm, n, out);
+}
+
 // ======================================================================================================
 extern "C" {
 
@@ -313,8 +327,9 @@ void dint_destroy(dint_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
+  if (e->d_route) cudaFree(e->d_route);
   for (auto& ep : e->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < kHostBufs; i++) {
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
@@ -332,7 +347,7 @@ static int create_impl(dint_engine* e) {
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < kHostBufs; i++) {
     CU(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
@@ -469,6 +484,12 @@ int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
   if (cf.shard_id >= cf.n_shards || cf.lock_slots == 0) { delete e; return set_err(DINT_EINVAL, "bad shard/lock_slots"); }
   if (cf.chunk == 0) cf.chunk = 1u << 20;
   e->chunk = (cf.chunk + kTile - 1) / kTile * kTile;
+  {
+    const char* hc = getenv("DINT_HOST_CHUNK");
+    uint32_t want = hc ? (uint32_t)atoi(hc) : (1u << 18);
+    if (want < (uint32_t)kTile) want = kTile;
+    e->host_chunk = want < e->chunk ? (want + kTile - 1) / kTile * kTile : e->chunk;
+  }
   e->msg = kMsgSize[kind];
   e->has_log = kLogEntry[kind] != 0;
   int rc = create_impl(e);
@@ -497,6 +518,56 @@ int dint_route_owner(dint_engine* e, const void* req_dev, uint64_t n, uint8_t* o
   return DINT_OK;
 }
 
+int dint_route_partition(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards,
+                         void* sorted_dev, uint32_t* perm_dev, uint32_t* counts_dev, void* cuda_stream) {
+  if (!e || n_shards == 0 || n_shards > kMaxShards || n > 0xffffffffULL) return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const uint32_t tiles = (uint32_t)((n + kThreads - 1) / kThreads);
+  if (tiles > e->route_tiles) {                          // scratch: per-tile per-shard counts + totals
+    if (e->d_route) { CU(cudaFree(e->d_route)); e->d_route = nullptr; }
+    e->route_tiles = tiles + tiles / 2 + 64;
+    CU(cudaMalloc(&e->d_route, ((size_t)e->route_tiles * kMaxShards + 3 * kMaxShards) * sizeof(uint32_t)));
+  }
+  uint32_t* totals = e->d_route;                         // [0..8) counts, [8..16) starts, [16] n
+  uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
+  if (n == 0) { CU(cudaMemsetAsync(counts_dev, 0, n_shards * sizeof(uint32_t), s)); return DINT_OK; }
+  e->stats.kernel_launches += 3;
+  k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
+  k_route_scan<<<1, kThreads, 0, s>>>(tilecnt, tiles, n_shards, totals);
+  const uint8_t* rq = (const uint8_t*)req_dev;
+  uint8_t* out = (uint8_t*)sorted_dev;
+  switch (e->msg) {
+    case 6: route_scatter_t<6>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
+    case 9: route_scatter_t<9>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
+    case 23: route_scatter_t<23>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
+    case 53: route_scatter_t<53>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
+    default: route_scatter_t<55>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
+  }
+  CU(cudaMemcpyAsync(counts_dev, totals, n_shards * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+int dint_route_unpermute(dint_engine* e, const void* sorted_dev, const uint32_t* perm_dev, uint64_t n, void* out_dev, void* cuda_stream) {
+  if (!e || n > 0xffffffffULL) return set_err(DINT_EINVAL, "bad argument");
+  if (n == 0) return DINT_OK;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  e->stats.kernel_launches++;
+  const uint8_t* in = (const uint8_t*)sorted_dev;
+  uint8_t* out = (uint8_t*)out_dev;
+  switch (e->msg) {
+    case 6: route_unpermute_t<6>(in, perm_dev, (uint32_t)n, out, s); break;
+    case 9: route_unpermute_t<9>(in, perm_dev, (uint32_t)n, out, s); break;
+    case 23: route_unpermute_t<23>(in, perm_dev, (uint32_t)n, out, s); break;
+    case 53: route_unpermute_t<53>(in, perm_dev, (uint32_t)n, out, s); break;
+    default: route_unpermute_t<55>(in, perm_dev, (uint32_t)n, out, s); break;
+  }
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
 int dint_sync(dint_engine* e) {
   if (!e) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));
@@ -519,42 +590,45 @@ int dint_submit_device(dint_engine* e, const void* req_dev, uint64_t n, void* re
 int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
   if (!e || (n && (!req || !resp))) return set_err(DINT_EINVAL, "null argument");
   CU(cudaSetDevice(e->device));
+  // the host path moves data in slices of `hchunk` requests through a ring of kHostBufs device buffers:
+  // small slices keep the PCIe fill/drain bubbles short, the ring keeps both copy engines and the SMs busy
+  const uint32_t hchunk = e->host_chunk;
   if (!e->d_req[0]) {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kHostBufs; i++) {
       int rc;
-      if ((rc = dalloc(e, &e->d_req[i], (size_t)e->chunk * e->msg + 16, false))) return rc;
-      if ((rc = dalloc(e, &e->d_resp[i], (size_t)e->chunk * e->msg + 16, false))) return rc;
+      if ((rc = dalloc(e, &e->d_req[i], (size_t)hchunk * e->msg + 16, false))) return rc;
+      if ((rc = dalloc(e, &e->d_resp[i], (size_t)hchunk * e->msg + 16, false))) return rc;
     }
   }
   CU(cudaDeviceSynchronize());     // order after anything submitted on user streams
   const uint8_t* rq = (const uint8_t*)req;
   uint8_t* rs = (uint8_t*)resp;
   unsigned long long err_before = e->stats.errors;
-  // three-stage pipeline over chunks: H2D (s_in) | kernels (stream) | D2H (s_out), double buffered.  Chunk
-  // k's replies are final only after the launch that replays its listed requests: K1 of chunk k+1, or the
-  // flush after the last chunk -- so D2H(k) is ordered behind that.
+  // three-stage pipeline: H2D (s_in) | kernels (stream) | D2H (s_out).  Slice k's replies are final only
+  // after the launch that replays its listed requests -- K1 of slice k+1, or the flush after the last
+  // slice -- so D2H(k) is ordered behind that.
   uint64_t k = 0;
   uint64_t prev_off = 0, prev_bytes = 0;
-  auto copy_out_prev = [&](uint64_t kk) -> int {          // D2H of chunk kk-1 (buffer (kk-1)&1)
-    int pb = (int)((kk - 1) & 1);
+  auto copy_out_prev = [&](uint64_t kk) -> int {          // D2H of slice kk-1
+    int pb = (int)((kk - 1) % kHostBufs);
     CU(cudaEventRecord(e->ev_comp[pb], e->stream));
     CU(cudaStreamWaitEvent(e->s_out, e->ev_comp[pb], 0));
     CU(cudaMemcpyAsync(rs + prev_off, e->d_resp[pb], prev_bytes, cudaMemcpyDeviceToHost, e->s_out));
     CU(cudaEventRecord(e->ev_out[pb], e->s_out));
     return DINT_OK;
   };
-  for (uint64_t off = 0; off < n; off += e->chunk, k++) {
-    int b = (int)(k & 1);
-    uint64_t cn = (n - off < e->chunk) ? (n - off) : e->chunk;
+  for (uint64_t off = 0; off < n; off += hchunk, k++) {
+    int b = (int)(k % kHostBufs);
+    uint64_t cn = (n - off < hchunk) ? (n - off) : hchunk;
     size_t bytes = (size_t)cn * e->msg;
-    if (k >= 2) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));     // everything that read d_req[b] (chunk k-2) is done
+    if (k >= (uint64_t)kHostBufs) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));   // slice k-kHostBufs no longer read
     CU(cudaMemcpyAsync(e->d_req[b], rq + off * e->msg, bytes, cudaMemcpyHostToDevice, e->s_in));
     CU(cudaEventRecord(e->ev_in[b], e->s_in));
     CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
-    if (k >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0));    // D2H of chunk k-2 done with d_resp[b]
+    if (k >= (uint64_t)kHostBufs) CU(cudaStreamWaitEvent(e->stream, e->ev_out[b], 0)); // its replies have left d_resp[b]
     int rc = submit_chunk(e, e->d_req[b], (uint32_t)cn, e->d_resp[b], e->stream);
     if (rc) return rc;
-    if (k >= 1 && (rc = copy_out_prev(k))) return rc;                   // chunk k-1 is final now
+    if (k >= 1 && (rc = copy_out_prev(k))) return rc;                   // slice k-1 is final now
     prev_off = off * e->msg;
     prev_bytes = bytes;
     e->stats.h2d_bytes += bytes;

@@ -122,6 +122,98 @@ __global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uin
   owner[i] = (uint8_t)o;
 }
 
+// ---- multi-GPU dispatch: stable partition of a batch by owner shard -------------------------------------
+// (1) k_route_count: per 256-record tile, how many records go to each shard;  (2) k_route_scan (one CTA):
+// exclusive offsets -- shard-major, then tile order -- and the per-shard totals;  (3) k_route_scatter: every
+// record is copied to its slot (stable inside a shard: tile order, then thread order) and the inverse
+// permutation is recorded.  Afterwards the wire records sit grouped by destination, ready for the exchange.
+constexpr int kMaxShards = 8;
+__global__ void __launch_bounds__(kThreads) k_route_count(const uint8_t* owner, uint32_t n, uint32_t world, uint32_t* tilecnt) {
+  __shared__ uint32_t cnt[kMaxShards];
+  if (threadIdx.x < kMaxShards) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t o = i < n ? owner[i] : 0xffu;
+  const uint32_t peers = __match_any_sync(0xffffffffu, o);
+  if (o < world && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&cnt[o], (uint32_t)__popc(peers));
+  __syncthreads();
+  if (threadIdx.x < world) tilecnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];   // shard-major
+}
+__global__ void __launch_bounds__(kThreads) k_route_scan(uint32_t* tilecnt, uint32_t n_tiles, uint32_t world, uint32_t* totals) {
+  __shared__ uint32_t wsum[kThreads / 32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const uint32_t total_items = n_tiles * world;         // shard-major order = final layout order
+  uint32_t shard_start = 0;
+  for (uint32_t base = 0; base < total_items; base += kThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < total_items ? tilecnt[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((int)lane_id() >= o) x += y;
+    }
+    if (lane_id() == 31) wsum[warp_id()] = x;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+      if (w < (int)warp_id()) woff += wsum[w];
+      tot += wsum[w];
+    }
+    const uint32_t excl = carry + woff + (x - v);
+    if (i < total_items) {
+      tilecnt[i] = excl;
+      if (i % n_tiles == 0) totals[kMaxShards + i / n_tiles] = excl;     // start offset of each shard's segment
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  (void)shard_start;
+  if (threadIdx.x == 0) totals[2 * kMaxShards] = carry;                   // n routed
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const uint32_t start = totals[kMaxShards + threadIdx.x];
+    const uint32_t end = threadIdx.x + 1 < world ? totals[kMaxShards + threadIdx.x + 1] : carry;
+    totals[threadIdx.x] = end - start;                                     // records per shard
+  }
+}
+template <int MSG>
+__global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, const uint8_t* owner, uint32_t n, uint32_t world,
+                                                            const uint32_t* tilebase, uint8_t* out, uint32_t* perm) {
+  __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (threadIdx.x < (kThreads / 32) * kMaxShards) ((uint32_t*)wcnt)[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t o = i < n ? owner[i] : 0xffu;
+  const uint32_t peers = __match_any_sync(0xffffffffu, o);
+  const uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
+  if (o < world && before == 0) wcnt[warp_id()][o] = __popc(peers);
+  __syncthreads();
+  if (o < world) {
+    uint32_t pos = tilebase[(size_t)o * gridDim.x + blockIdx.x] + before;
+    for (uint32_t w = 0; w < warp_id(); w++) pos += wcnt[w][o];
+    const uint8_t* src = req + (size_t)i * MSG;
+    uint8_t* dst = out + (size_t)pos * MSG;
+#pragma unroll
+    for (int b = 0; b < MSG; b++) dst[b] = src[b];
+    perm[pos] = i;
+  }
+}
+// combine: replies arrive in partition order; put each back at its original index
+template <int MSG>
+__global__ void __launch_bounds__(kThreads) k_route_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {
+  const uint32_t pos = blockIdx.x * kThreads + threadIdx.x;
+  if (pos >= n) return;
+  const uint8_t* src = sorted + (size_t)pos * MSG;
+  uint8_t* dst = out + (size_t)perm[pos] * MSG;
+#pragma unroll
+  for (int b = 0; b < MSG; b++) dst[b] = src[b];
+}
+
 // ordered replay (defined below): per-warp shared-memory slice and the replay itself
 template <int KIND> struct OrdSlice {
   static constexpr uint32_t BYTES = kBucketCap * (FastReplay<KIND>::ok ? (8 + 8 + 4) : 8);
@@ -490,6 +582,47 @@ DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch) {
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c.counters[1], (unsigned long long)c.nc_ord[0]);
 }
 
+// ---- parallel replay of lock_fasst runs (fallback path) ------------------------------------------------
+// A lock_fasst request acts on its slot's (lock, ver) as  lock' in {lock, 0, 1},  ver' = ver + d :
+//   kRead (id, +0)   kAcquireLock (set 1, +0)   kAbort (set 0, +0)   kCommit (set 0, +1)
+// (lock_fasst/udp/server.cc:86-114).  Such maps compose associatively, so the state every request of a run
+// SEES is an exclusive segmented scan over the sorted list -- a run of tens of thousands of requests on one
+// hot slot (HOT: 4800 ids, Zipf) is then replayed by the whole grid instead of by one thread.
+// Encoding: bits 0-31 d, bits 32-33 lock map (0 id, 1 set 0, 2 set 1), bit 34 segment head.
+DINT_D uint64_t fx_of(uint32_t type, bool head) {
+  const uint64_t lt = (type == 0) ? 0ull : (type == 1) ? 2ull : 1ull;
+  return (uint64_t)(type == 3 ? 1u : 0u) | (lt << 32) | ((uint64_t)(head ? 1u : 0u) << 34);
+}
+DINT_D uint64_t fx_compose(uint64_t a, uint64_t b) {        // a then b, segment-aware
+  if ((b >> 34) & 1ull) return b;
+  const uint64_t lt = ((b >> 32) & 3ull) ? ((b >> 32) & 3ull) : ((a >> 32) & 3ull);
+  return (uint64_t)((uint32_t)a + (uint32_t)b) | (lt << 32) | (a & (1ull << 34));
+}
+constexpr uint64_t kFxId = 0ull;
+
+// inclusive scan of `x` over the CTA in thread order (fx_compose); returns the inclusive value and leaves the
+// CTA total in *total.  sh: 8 words of shared memory.
+DINT_D uint64_t fx_block_scan(uint64_t x, uint64_t* sh, uint64_t* total) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((int)lane_id() >= o) x = fx_compose(y, x);
+  }
+  if (lane_id() == 31) sh[warp_id()] = x;
+  __syncthreads();
+  uint64_t pre = kFxId;
+  bool have = false;
+  uint64_t tot = kFxId;
+  for (int w = 0; w < kThreads / 32; w++) {
+    const uint64_t v = sh[w];
+    if (w < (int)warp_id()) { pre = have ? fx_compose(pre, v) : v; have = true; }
+    tot = w ? fx_compose(tot, v) : v;
+  }
+  __syncthreads();
+  *total = tot;
+  return have ? fx_compose(pre, x) : x;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
   const uint32_t nc = c.nc_ord[0];
@@ -664,7 +797,109 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
       grid.sync();
       uint64_t* tmp = src; src = dst; dst = tmp;
     }
-    if constexpr (FastReplay<KIND>::ok) {
+    if constexpr (KIND == K_FASST) {
+      // parallel replay by segmented scan (see fx_of): tile aggregates -> carries -> replies
+      using FR = FastReplay<K_FASST>;
+      using Wq = Wire<K_FASST>;
+      uint64_t* tile_agg = (uint64_t*)c.ghist;                 // [n_st], free after the sort
+      uint64_t* sh_scan = skeys;                               // 8 words
+      auto load8 = [&](uint32_t T, uint64_t (&f)[kSortItems], uint32_t (&ty)[kSortItems], uint32_t& cnt) {
+        const uint32_t base = T * kSortTile + tid * kSortItems;   // blocked: thread t owns 8 consecutive entries
+        cnt = base < nc ? min((uint32_t)kSortItems, nc - base) : 0;
+#pragma unroll
+        for (int k = 0; k < kSortItems; k++) {
+          if ((uint32_t)k < cnt) {
+            const uint32_t p = base + k;
+            const uint64_t e = src[p];
+            ty[k] = FR::load_op(c.ord_resp + (size_t)(uint32_t)e * Wq::MSG);
+            const bool head = p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(e >> 32);
+            f[k] = fx_of(ty[k], head);
+          } else { ty[k] = 0; f[k] = kFxId; }
+        }
+      };
+      // (1) per-tile aggregates
+      for (uint32_t T = blockIdx.x; T < n_st; T += gridDim.x) {
+        uint64_t f[kSortItems]; uint32_t ty[kSortItems]; uint32_t cnt;
+        load8(T, f, ty, cnt);
+        uint64_t agg = f[0];
+#pragma unroll
+        for (int k = 1; k < kSortItems; k++) if ((uint32_t)k < cnt) agg = fx_compose(agg, f[k]);
+        uint64_t total;
+        (void)fx_block_scan(agg, sh_scan, &total);
+        if (tid == 0) tile_agg[T] = total;
+      }
+      grid.sync();
+      // (2) exclusive scan of the tile aggregates (CTA 0, sequential over <= a few hundred tiles per thread-chunk)
+      if (blockIdx.x == 0 && tid == 0) {
+        uint64_t run = kFxId;
+        bool have = false;
+        for (uint32_t T = 0; T < n_st; T++) {
+          const uint64_t a = tile_agg[T];
+          tile_agg[T] = have ? run : (1ull << 34);           // "nothing before": behaves as a segment head
+          run = have ? fx_compose(run, a) : a;
+          have = true;
+        }
+      }
+      grid.sync();
+      // (3) replies: every entry derives the state it sees from its exclusive prefix
+      for (uint32_t T = blockIdx.x; T < n_st; T += gridDim.x) {
+        uint64_t f[kSortItems]; uint32_t ty[kSortItems]; uint32_t cnt;
+        load8(T, f, ty, cnt);
+        uint64_t agg = f[0];
+#pragma unroll
+        for (int k = 1; k < kSortItems; k++) if ((uint32_t)k < cnt) agg = fx_compose(agg, f[k]);
+        uint64_t total;
+        const uint64_t incl = fx_block_scan(agg, sh_scan, &total);
+        // exclusive prefix of this thread's first entry = carry(tile) o (inclusive of the previous thread)
+        uint64_t prev_thread = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane_id() == 0) prev_thread = kFxId;               // patched below from shared memory
+        __shared__ uint64_t s_warp_last[kThreads / 32];
+        if (lane_id() == 31) s_warp_last[warp_id()] = incl;
+        __syncthreads();
+        const uint64_t carry = tile_agg[T];
+        uint64_t pre;
+        if (tid == 0) pre = carry;
+        else {
+          const uint64_t before = lane_id() == 0 ? s_warp_last[warp_id() - 1] : prev_thread;
+          pre = ((carry >> 34) & 1ull) && carry == (1ull << 34) ? before : fx_compose(carry, before);
+        }
+        __syncthreads();
+        const uint32_t base = T * kSortTile + tid * kSortItems;
+#pragma unroll
+        for (int k = 0; k < kSortItems; k++) {
+          if ((uint32_t)k < cnt) {
+            const uint32_t p = base + k;
+            const uint64_t e = src[p];
+            const uint32_t g = (uint32_t)(e >> 32);
+            const bool head = (f[k] >> 34) & 1ull;
+            const uint64_t ex = head ? kFxId : pre;            // exclusive prefix inside the run
+            typename FR::State st = FR::load_state(c, g);
+            const uint32_t lt = (uint32_t)(ex >> 32) & 3u;
+            if (!head) {
+              if (lt) st.lock = (lt == 2u);
+              st.ver += (uint32_t)ex;
+              st.dirty_ver = (uint32_t)ex != 0;
+            }
+            const uint64_t r = FR::step(st, ty[k]);
+            FR::write_result(c.ord_resp + (size_t)(uint32_t)e * Wq::MSG, r);
+            // the run's final state is written only after EVERY entry has read the initial one (next pass)
+            const bool last = p + 1 == nc || (uint32_t)(src[p + 1] >> 32) != g;
+            if (last) dst[p] = (uint64_t)st.ver | ((uint64_t)st.lock << 32) | ((uint64_t)(st.dirty_ver ? 1u : 0u) << 33);
+            pre = head ? f[k] : fx_compose(pre, f[k]);
+          }
+        }
+      }
+      grid.sync();
+      // (4) final state of every run
+      for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads) {
+        const uint32_t g = (uint32_t)(src[p] >> 32);
+        if (p + 1 == nc || (uint32_t)(src[p + 1] >> 32) != g) {
+          const uint64_t v = dst[p];
+          typename FR::State st{(uint32_t)v, (uint32_t)(v >> 32) & 1u, g, ((v >> 33) & 1ull) != 0};
+          FR::store_state(c, g, st);
+        }
+      }
+    } else if constexpr (FastReplay<KIND>::ok) {
       // replay in three passes: request fields of ALL listed requests (parallel) -> per-run walk with the
       // group state in registers -> replies (parallel).  ops live in the (now free) clist, replies in `dst`.
       using FR = FastReplay<KIND>;

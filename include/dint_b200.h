@@ -136,6 +136,15 @@ int dint_submit_device(dint_engine *e, const void *req_dev, uint64_t n, void *re
  * collision behaviour is unchanged by sharding); 0xFF for records no shard owns (invalid / log-only
  * requests are served by whoever receives them: owner = shard_id).  Device pointers, async on stream. */
 int dint_route_owner(dint_engine *e, const void *req_dev, uint64_t n, uint8_t *owner_dev, void *cuda_stream);
+/* Dispatch / combine for the multi-GPU exchange.  dint_route_partition: stable partition of n wire records by
+ * owner_dev[i] (< n_shards; from dint_route_owner, or chosen by the client as in tatp / smallbank) into
+ * sorted_dev (grouped by shard, each group in original order); perm_dev[pos] = original index;
+ * counts_dev[0..n_shards) = records per shard.  dint_route_unpermute: out_dev[perm[pos]] = sorted_dev[pos].
+ * All pointers are device pointers; asynchronous on cuda_stream. */
+int dint_route_partition(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
+                         void *sorted_dev, uint32_t *perm_dev, uint32_t *counts_dev, void *cuda_stream);
+int dint_route_unpermute(dint_engine *e, const void *sorted_dev, const uint32_t *perm_dev, uint64_t n, void *out_dev,
+                         void *cuda_stream);
 int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */
 
 /* ---- state inspection: parity of the final server state, not only of the wire ------------------ */
