@@ -243,3 +243,35 @@ def test_engine_reproduces_reference_golden(name):
     with Engine(kind, populate=True, chunk=2048, **cfg) as eng:
         ours = eng.submit(req)
     assert G.mismatch(kind, ours, resp) is None, G.mismatch(kind, ours, resp)
+
+
+# ---------------------------------------------------------------- multi-GPU dispatch kernels (1 GPU) -----
+@pytest.mark.parametrize("kind,world", [(wire.FASST, 2), (wire.FASST, 8), (wire.STORE, 3), (wire.TATP, 5)])
+def test_route_owner_partition_unpermute(kind, world):
+    """k_route_owner / k_route_count+scan+scatter / k_route_unpermute against numpy: owner = the slot one
+    server would compute, modulo the shard count; the partition is stable; unpermute is its inverse."""
+    import torch
+    from dint_b200.shard import owners_cpu
+    n = 70001
+    cfg = {}
+    if kind == wire.FASST:
+        req = T.fasst_random(n, 10**6, seed=3)
+    elif kind == wire.STORE:
+        req = T.store_random(n, 500, seed=3)
+        cfg = dict(subs_populate=500)
+    else:
+        req = T.tatp_random(n, 20, seed=3)
+        cfg = dict(subs_populate=20)
+    msg = wire.MSG_SIZE[kind]
+    with Engine(kind, n_shards=world, shard_id=1, **cfg) as eng:
+        d = torch.from_numpy(req).cuda()
+        owner = eng.route_owner(d)
+        want_owner = owners_cpu(kind, eng.cfg, world, 1, req)
+        assert np.array_equal(owner.cpu().numpy(), want_owner)
+        srt, perm, counts = eng.route_partition(d, owner, world)
+        order = np.argsort(want_owner, kind="stable")
+        assert np.array_equal(perm.cpu().numpy().astype(np.int64), order)
+        assert np.array_equal(counts.cpu().numpy(), np.bincount(want_owner, minlength=world)[:world])
+        assert np.array_equal(srt.cpu().numpy().reshape(-1, msg), req.reshape(-1, msg)[order])
+        back = eng.route_unpermute(srt, perm)
+        assert np.array_equal(back.cpu().numpy(), req)
