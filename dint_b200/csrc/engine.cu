@@ -284,9 +284,9 @@ static int pull_counters(dint_engine* e) {
 }
 
 template <int MSG>
-static void route_scatter_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, uint32_t world, const uint32_t* tb, uint8_t* out,
-                            uint32_t* perm, uint32_t tiles, cudaStream_t s) {
-  k_route_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, out, perm);
+static void route_scatter_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, uint32_t world, const uint32_t* tb,
+                            const uint32_t* totals, uint8_t* out, uint32_t* perm, uint32_t tiles, cudaStream_t s) {
+  k_route_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, totals, out, perm);
 }
 template <int MSG>
 static void route_unpermute_t(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out, cudaStream_t s) {
@@ -529,20 +529,20 @@ int dint_route_partition(dint_engine* e, const void* req_dev, const uint8_t* own
     e->route_tiles = tiles + tiles / 2 + 64;
     CU(cudaMalloc(&e->d_route, ((size_t)e->route_tiles * kMaxShards + 3 * kMaxShards) * sizeof(uint32_t)));
   }
-  uint32_t* totals = e->d_route;                         // [0..8) counts, [8..16) starts, [16] n
+  uint32_t* totals = e->d_route;                         // [0..8) records per shard
   uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
   if (n == 0) { CU(cudaMemsetAsync(counts_dev, 0, n_shards * sizeof(uint32_t), s)); return DINT_OK; }
   e->stats.kernel_launches += 3;
   k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
-  k_route_scan<<<1, kThreads, 0, s>>>(tilecnt, tiles, n_shards, totals);
+  k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
   const uint8_t* rq = (const uint8_t*)req_dev;
   uint8_t* out = (uint8_t*)sorted_dev;
   switch (e->msg) {
-    case 6: route_scatter_t<6>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
-    case 9: route_scatter_t<9>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
-    case 23: route_scatter_t<23>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
-    case 53: route_scatter_t<53>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
-    default: route_scatter_t<55>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, out, perm_dev, tiles, s); break;
+    case 6: route_scatter_t<6>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, totals, out, perm_dev, tiles, s); break;
+    case 9: route_scatter_t<9>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, totals, out, perm_dev, tiles, s); break;
+    case 23: route_scatter_t<23>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, totals, out, perm_dev, tiles, s); break;
+    case 53: route_scatter_t<53>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, totals, out, perm_dev, tiles, s); break;
+    default: route_scatter_t<55>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, totals, out, perm_dev, tiles, s); break;
   }
   CU(cudaMemcpyAsync(counts_dev, totals, n_shards * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
   CU(cudaGetLastError());

@@ -139,16 +139,16 @@ __global__ void __launch_bounds__(kThreads) k_route_count(const uint8_t* owner, 
   __syncthreads();
   if (threadIdx.x < world) tilecnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];   // shard-major
 }
-__global__ void __launch_bounds__(kThreads) k_route_scan(uint32_t* tilecnt, uint32_t n_tiles, uint32_t world, uint32_t* totals) {
+__global__ void __launch_bounds__(kThreads) k_route_scan(uint32_t* tilecnt, uint32_t n_tiles, uint32_t* totals) {
+  // one CTA per shard: exclusive scan of that shard's row of per-tile counts, row total -> totals[shard]
   __shared__ uint32_t wsum[kThreads / 32];
   __shared__ uint32_t carry;
+  uint32_t* row = tilecnt + (size_t)blockIdx.x * n_tiles;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  const uint32_t total_items = n_tiles * world;         // shard-major order = final layout order
-  uint32_t shard_start = 0;
-  for (uint32_t base = 0; base < total_items; base += kThreads) {
+  for (uint32_t base = 0; base < n_tiles; base += kThreads) {
     const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < total_items ? tilecnt[i] : 0;
+    const uint32_t v = i < n_tiles ? row[i] : 0;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -163,27 +163,17 @@ __global__ void __launch_bounds__(kThreads) k_route_scan(uint32_t* tilecnt, uint
       if (w < (int)warp_id()) woff += wsum[w];
       tot += wsum[w];
     }
-    const uint32_t excl = carry + woff + (x - v);
-    if (i < total_items) {
-      tilecnt[i] = excl;
-      if (i % n_tiles == 0) totals[kMaxShards + i / n_tiles] = excl;     // start offset of each shard's segment
-    }
+    if (i < n_tiles) row[i] = carry + woff + (x - v);
     __syncthreads();
     if (threadIdx.x == 0) carry += tot;
     __syncthreads();
   }
-  (void)shard_start;
-  if (threadIdx.x == 0) totals[2 * kMaxShards] = carry;                   // n routed
-  __syncthreads();
-  if (threadIdx.x < world) {
-    const uint32_t start = totals[kMaxShards + threadIdx.x];
-    const uint32_t end = threadIdx.x + 1 < world ? totals[kMaxShards + threadIdx.x + 1] : carry;
-    totals[threadIdx.x] = end - start;                                     // records per shard
-  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 template <int MSG>
 __global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, const uint8_t* owner, uint32_t n, uint32_t world,
-                                                            const uint32_t* tilebase, uint8_t* out, uint32_t* perm) {
+                                                            const uint32_t* tilebase, const uint32_t* totals, uint8_t* out,
+                                                            uint32_t* perm) {
   __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
   const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
   if (threadIdx.x < (kThreads / 32) * kMaxShards) ((uint32_t*)wcnt)[threadIdx.x] = 0;
@@ -196,6 +186,7 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, 
   if (o < world) {
     uint32_t pos = tilebase[(size_t)o * gridDim.x + blockIdx.x] + before;
     for (uint32_t w = 0; w < warp_id(); w++) pos += wcnt[w][o];
+    for (uint32_t q = 0; q < o; q++) pos += totals[q];                 // start of shard o's segment
     const uint8_t* src = req + (size_t)i * MSG;
     uint8_t* dst = out + (size_t)pos * MSG;
 #pragma unroll
