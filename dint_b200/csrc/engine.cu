@@ -289,6 +289,11 @@ static void route_scatter_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, ui
   k_route_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, totals, out, perm);
 }
 template <int MSG>
+static void route_scatter_slabs_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, uint32_t world, uint32_t cap, const uint32_t* tb,
+                                  uint8_t* slabs, uint32_t* perm, uint32_t* overflow, uint32_t tiles, cudaStream_t s) {
+  k_route_scatter_slabs<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, cap, tb, slabs, perm, overflow);
+}
+template <int MSG>
 static void route_unpermute_t(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out, cudaStream_t s) {
   k_route_unpermute<MSG><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(sorted, perm, n, out);
 }
@@ -545,6 +550,39 @@ int dint_route_partition(dint_engine* e, const void* req_dev, const uint8_t* own
     default: route_scatter_t<55>(rq, owner_dev, (uint32_t)n, n_shards, tilecnt, totals, out, perm_dev, tiles, s); break;
   }
   CU(cudaMemcpyAsync(counts_dev, totals, n_shards * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+int dint_route_partition_slabs(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards,
+                               uint32_t cap, void* slabs_dev, uint32_t* perm_dev, uint32_t* overflow_dev, void* cuda_stream) {
+  if (!e || n_shards == 0 || n_shards > kMaxShards || n > 0xffffffffULL || cap == 0) return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const uint32_t tiles = (uint32_t)((n + kThreads - 1) / kThreads);
+  if (tiles > e->route_tiles) {
+    if (e->d_route) { CU(cudaFree(e->d_route)); e->d_route = nullptr; }
+    e->route_tiles = tiles + tiles / 2 + 64;
+    CU(cudaMalloc(&e->d_route, ((size_t)e->route_tiles * kMaxShards + 3 * kMaxShards) * sizeof(uint32_t)));
+  }
+  uint32_t* totals = e->d_route;
+  uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
+  const size_t slots = (size_t)n_shards * cap;
+  CU(cudaMemsetAsync(slabs_dev, 0xFE, slots * e->msg, s));          // padding records
+  CU(cudaMemsetAsync(perm_dev, 0xFF, slots * sizeof(uint32_t), s));  // 0xffffffff = padding slot
+  if (n == 0) return DINT_OK;
+  e->stats.kernel_launches += 3;
+  k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
+  k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
+  const uint8_t* rq = (const uint8_t*)req_dev;
+  uint8_t* out = (uint8_t*)slabs_dev;
+  switch (e->msg) {
+    case 6: route_scatter_slabs_t<6>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
+    case 9: route_scatter_slabs_t<9>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
+    case 23: route_scatter_slabs_t<23>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
+    case 53: route_scatter_slabs_t<53>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
+    default: route_scatter_slabs_t<55>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
+  }
   CU(cudaGetLastError());
   return DINT_OK;
 }

@@ -168,6 +168,9 @@ struct KeyInfo {
   uint32_t grp;     // local group id, kNoGroup when the record is not this shard's
 };
 constexpr uint32_t kNoGroup = 0xffffffffu;
+// Padding record of the fixed-capacity multi-GPU exchange (shard.py): type byte 0xFE, no reference server
+// ever sees it.  It touches nothing, is answered unchanged, and is not an error.
+constexpr uint8_t kPadType = 0xFE;
 
 template <int KIND> DINT_D TypeInfo type_info(const uint8_t* rec);
 template <int KIND> DINT_D KeyInfo key_info(const Ctx& c, const uint8_t* rec);

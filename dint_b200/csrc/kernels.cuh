@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uin
   const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
   const uint8_t* rec = req + (size_t)i * W::MSG;
-  const TypeInfo ti = type_info<KIND>(rec);
+  const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
   uint32_t o = c.shard_id;                          // no per-key state touched: serve it where it arrived
   if (!ti.invalid && ti.mask) {
     uint32_t gglobal;                               // the slot / bucket / lock_hash ONE server would compute
@@ -194,13 +194,42 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, 
     perm[pos] = i;
   }
 }
+// Fixed-capacity variant for the exchange without a host round trip: shard o's records go to slab o
+// (`cap` records each; the rest of a slab stays padding); a record that does not fit raises *overflow.
+template <int MSG>
+__global__ void __launch_bounds__(kThreads) k_route_scatter_slabs(const uint8_t* req, const uint8_t* owner, uint32_t n,
+                                                                  uint32_t world, uint32_t cap, const uint32_t* tilebase,
+                                                                  uint8_t* slabs, uint32_t* perm, uint32_t* overflow) {
+  __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (threadIdx.x < (kThreads / 32) * kMaxShards) ((uint32_t*)wcnt)[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t o = i < n ? owner[i] : 0xffu;
+  const uint32_t peers = __match_any_sync(0xffffffffu, o);
+  const uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
+  if (o < world && before == 0) wcnt[warp_id()][o] = __popc(peers);
+  __syncthreads();
+  if (o < world) {
+    uint32_t r = tilebase[(size_t)o * gridDim.x + blockIdx.x] + before;
+    for (uint32_t w = 0; w < warp_id(); w++) r += wcnt[w][o];
+    if (r >= cap) { atomicAdd(overflow, 1u); return; }
+    const uint32_t pos = o * cap + r;
+    const uint8_t* src = req + (size_t)i * MSG;
+    uint8_t* dst = slabs + (size_t)pos * MSG;
+#pragma unroll
+    for (int b = 0; b < MSG; b++) dst[b] = src[b];
+    perm[pos] = i;
+  }
+}
 // combine: replies arrive in partition order; put each back at its original index
 template <int MSG>
 __global__ void __launch_bounds__(kThreads) k_route_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {
   const uint32_t pos = blockIdx.x * kThreads + threadIdx.x;
   if (pos >= n) return;
+  const uint32_t idx = perm[pos];
+  if (idx == 0xffffffffu) return;                        // padding slot of a slab
   const uint8_t* src = sorted + (size_t)pos * MSG;
-  uint8_t* dst = out + (size_t)perm[pos] * MSG;
+  uint8_t* dst = out + (size_t)idx * MSG;
 #pragma unroll
   for (int b = 0; b < MSG; b++) dst[b] = src[b];
 }
@@ -270,7 +299,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     uint32_t* new_w = nullptr;
     if (valid) {
       const uint8_t* rec = tile + threadIdx.x * W::MSG;
-      TypeInfo ti = type_info<KIND>(rec);
+      TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
       uint32_t g = kNoGroup;
       if (!ti.invalid && ti.mask) {
         g = key_info<KIND>(c, rec).grp;
@@ -383,7 +412,8 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
     KeyInfo ki{0, 0, kNoGroup};
     Pre<KIND> pf;
     bool listed = false;
-    if (valid) {
+    const bool pad = valid && rec[W::TYPE] == kPadType;
+    if (valid && !pad) {
       ti = type_info<KIND>(rec);
       if (!ti.invalid && ti.mask) {
         if (kGrpFromK1) ki.grp = g_k1; else ki = key_info<KIND>(c, rec);
@@ -425,7 +455,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
         if (n_list) atomicAdd(&c.nc_cur[0], n_list);
       }
     }
-    if (valid) {
+    if (valid && !pad) {
       if (ti.invalid) mark_invalid<KIND>(c, rec);
       else if (!listed) apply_one<KIND>(c, rec, ki, pf, log_ord, log_keep);
       // listed: the record leaves this kernel unchanged; K3 rewrites it in place in resp

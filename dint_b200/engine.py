@@ -38,7 +38,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_partition_slabs", "dint_route_unpermute", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod",
@@ -67,6 +67,7 @@ def lib():
     L.dint_submit_device.restype = i32; L.dint_submit_device.argtypes = [vp, vp, u64, vp, vp]
     L.dint_route_owner.restype = i32; L.dint_route_owner.argtypes = [vp, vp, u64, vp, vp]
     L.dint_route_partition.restype = i32; L.dint_route_partition.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp]
+    L.dint_route_partition_slabs.restype = i32; L.dint_route_partition_slabs.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp, vp, vp]
     L.dint_route_unpermute.restype = i32; L.dint_route_unpermute.argtypes = [vp, vp, vp, u64, vp, vp]
     L.dint_sync.restype = i32; L.dint_sync.argtypes = [vp]
     L.dint_kv_get.restype = i32; L.dint_kv_get.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]
@@ -239,11 +240,26 @@ class Engine:
             raise DintError(rc, "dint_route_partition")
         return out, perm, counts
 
+    def route_partition_slabs(self, req, owner, n_shards, cap, overflow):
+        """Fixed-capacity dispatch: returns (slabs uint8 [n_shards*cap*msg], perm int32 [n_shards*cap]); `overflow`
+        (int32 CUDA tensor of 1) is incremented on the device for every record that did not fit."""
+        import torch
+        n = owner.numel()
+        slabs = torch.empty(n_shards * cap * self.msg, dtype=torch.uint8, device=req.device)
+        perm = torch.empty(n_shards * cap, dtype=torch.int32, device=req.device)
+        s = torch.cuda.current_stream(req.device).cuda_stream
+        rc = lib().dint_route_partition_slabs(self.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, n_shards, cap,
+                                              C.c_void_p(slabs.data_ptr()), C.c_void_p(perm.data_ptr()),
+                                              C.c_void_p(overflow.data_ptr()), C.c_void_p(s) if s else None)
+        if rc != 0:
+            raise DintError(rc, "dint_route_partition_slabs")
+        return slabs, perm
+
     def route_unpermute(self, sorted_resp, perm, out=None):
         import torch
         n = perm.numel()
         if out is None:
-            out = torch.empty_like(sorted_resp)
+            out = torch.empty_like(sorted_resp)     # pass `out` (n_original * msg bytes) when perm has padding slots
         s = torch.cuda.current_stream(sorted_resp.device).cuda_stream
         rc = lib().dint_route_unpermute(self.h, C.c_void_p(sorted_resp.data_ptr()), C.c_void_p(perm.data_ptr()), n,
                                         C.c_void_p(out.data_ptr()), C.c_void_p(s) if s else None)

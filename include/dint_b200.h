@@ -143,6 +143,13 @@ int dint_route_owner(dint_engine *e, const void *req_dev, uint64_t n, uint8_t *o
  * All pointers are device pointers; asynchronous on cuda_stream. */
 int dint_route_partition(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
                          void *sorted_dev, uint32_t *perm_dev, uint32_t *counts_dev, void *cuda_stream);
+/* Fixed-capacity dispatch (no host round trip for the split sizes): records of shard o go to slab o of `cap`
+ * records inside slabs_dev (n_shards * cap records, pre-filled with padding by this call: every byte 0xFE --
+ * a padding record is answered unchanged and touches nothing); perm_dev (n_shards * cap entries) maps slab
+ * positions to original indices (0xffffffff = padding); *overflow_dev is incremented for every record that
+ * did not fit (the caller must then repeat the batch through dint_route_partition). */
+int dint_route_partition_slabs(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
+                               uint32_t cap, void *slabs_dev, uint32_t *perm_dev, uint32_t *overflow_dev, void *cuda_stream);
 int dint_route_unpermute(dint_engine *e, const void *sorted_dev, const uint32_t *perm_dev, uint64_t n, void *out_dev,
                          void *cuda_stream);
 int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */
