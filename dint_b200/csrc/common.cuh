@@ -172,6 +172,19 @@ DINT_D void st_words_unaligned(uint8_t* p, const uint32_t (&v)[NW]) {
     if ((uint32_t)b < mis) t[b] = (uint8_t)(v[NW - 1] >> (32 - sh + 8 * b));
 }
 
+// Copy one packed wire record of MSG bytes between arbitrary byte addresses with word-wide accesses.
+template <int MSG>
+DINT_D void copy_record(uint8_t* dst, const uint8_t* src) {
+  constexpr int NW = MSG / 4, TAIL = MSG % 4;
+  if constexpr (NW > 0) {
+    uint32_t w[NW];
+    ld_words_unaligned<NW>(src, w);
+    st_words_unaligned<NW>(dst, w);
+  }
+#pragma unroll
+  for (int b = 0; b < TAIL; b++) dst[NW * 4 + b] = src[NW * 4 + b];
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA 1-D bulk copies (cp.async.bulk; SASS UBLKCP).  Sizes and both addresses are 16-byte multiples.
 // ------------------------------------------------------------------------------------------------

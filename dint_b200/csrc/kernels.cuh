@@ -187,10 +187,7 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, 
     uint32_t pos = tilebase[(size_t)o * gridDim.x + blockIdx.x] + before;
     for (uint32_t w = 0; w < warp_id(); w++) pos += wcnt[w][o];
     for (uint32_t q = 0; q < o; q++) pos += totals[q];                 // start of shard o's segment
-    const uint8_t* src = req + (size_t)i * MSG;
-    uint8_t* dst = out + (size_t)pos * MSG;
-#pragma unroll
-    for (int b = 0; b < MSG; b++) dst[b] = src[b];
+    copy_record<MSG>(out + (size_t)pos * MSG, req + (size_t)i * MSG);
     perm[pos] = i;
   }
 }
@@ -214,10 +211,7 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter_slabs(const uint8_t*
     for (uint32_t w = 0; w < warp_id(); w++) r += wcnt[w][o];
     if (r >= cap) { atomicAdd(overflow, 1u); return; }
     const uint32_t pos = o * cap + r;
-    const uint8_t* src = req + (size_t)i * MSG;
-    uint8_t* dst = slabs + (size_t)pos * MSG;
-#pragma unroll
-    for (int b = 0; b < MSG; b++) dst[b] = src[b];
+    copy_record<MSG>(slabs + (size_t)pos * MSG, req + (size_t)i * MSG);
     perm[pos] = i;
   }
 }
@@ -228,10 +222,7 @@ __global__ void __launch_bounds__(kThreads) k_route_unpermute(const uint8_t* sor
   if (pos >= n) return;
   const uint32_t idx = perm[pos];
   if (idx == 0xffffffffu) return;                        // padding slot of a slab
-  const uint8_t* src = sorted + (size_t)pos * MSG;
-  uint8_t* dst = out + (size_t)idx * MSG;
-#pragma unroll
-  for (int b = 0; b < MSG; b++) dst[b] = src[b];
+  copy_record<MSG>(out + (size_t)idx * MSG, sorted + (size_t)pos * MSG);
 }
 
 // ordered replay (defined below): per-warp shared-memory slice and the replay itself
