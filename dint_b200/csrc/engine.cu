@@ -587,6 +587,86 @@ int dint_route_partition_slabs(dint_engine* e, const void* req_dev, const uint8_
   return DINT_OK;
 }
 
+int dint_p2p_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
+                      uint32_t cap, const dint_peer_ptrs* inbox_ptrs, const dint_peer_ptrs* sig_ptrs, uint32_t epoch,
+                      uint32_t* perm_dev, uint32_t* flags_dev, void* cuda_stream) {
+  if (!e || !inbox_ptrs || !sig_ptrs || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 || n > 0xffffffffULL)
+    return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const uint32_t tiles = (uint32_t)((n + kThreads - 1) / kThreads);
+  if (tiles + 1 > e->route_tiles) {
+    if (e->d_route) { CU(cudaFree(e->d_route)); e->d_route = nullptr; }
+    e->route_tiles = tiles + tiles / 2 + 64;
+    CU(cudaMalloc(&e->d_route, ((size_t)e->route_tiles * kMaxShards + 3 * kMaxShards) * sizeof(uint32_t)));
+  }
+  uint32_t* totals = e->d_route;
+  uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
+  PeerPtrs in{}, sg{};
+  for (uint32_t i = 0; i < kMaxShards; i++) { in.p[i] = inbox_ptrs->p[i]; sg.p[i] = sig_ptrs->p[i]; }
+  e->stats.kernel_launches += 4;
+  if (n) {
+    k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
+    k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
+  } else {
+    CU(cudaMemsetAsync(totals, 0, kMaxShards * sizeof(uint32_t), s));
+  }
+  const uint64_t slots = (uint64_t)n_shards * cap;
+  const uint32_t grid = (uint32_t)(((n > slots ? n : slots) + kThreads - 1) / kThreads);
+  const uint8_t* rq = (const uint8_t*)req_dev;
+  switch (e->msg) {
+    case 6: k_route_scatter_p2p<6><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
+    case 9: k_route_scatter_p2p<9><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
+    case 23: k_route_scatter_p2p<23><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
+    case 53: k_route_scatter_p2p<53><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
+    default: k_route_scatter_p2p<55><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
+  }
+  k_p2p_signal<<<1, 32, 0, s>>>(sg, n_shards, rank, epoch);
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+int dint_p2p_wait(dint_engine* e, const uint32_t* local_sig_dev, uint32_t n_shards, uint32_t epoch, uint32_t* flags_dev, void* cuda_stream) {
+  if (!e || !local_sig_dev || n_shards == 0 || n_shards > kMaxShards) return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  e->stats.kernel_launches++;
+  k_p2p_wait<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(local_sig_dev, n_shards, epoch, flags_dev + 1);
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+int dint_p2p_signal(dint_engine* e, const dint_peer_ptrs* sig_ptrs, uint32_t n_shards, uint32_t rank, uint32_t epoch, void* cuda_stream) {
+  if (!e || !sig_ptrs || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards) return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  PeerPtrs sg{};
+  for (uint32_t i = 0; i < kMaxShards; i++) sg.p[i] = sig_ptrs->p[i];
+  e->stats.kernel_launches++;
+  k_p2p_signal<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(sg, n_shards, rank, epoch);
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+int dint_p2p_combine(dint_engine* e, const dint_peer_ptrs* outbox_ptrs, const uint32_t* perm_dev, uint32_t n_shards, uint32_t rank,
+                     uint32_t cap, void* out_dev, void* cuda_stream) {
+  if (!e || !outbox_ptrs || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards) return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  PeerPtrs ob{};
+  for (uint32_t i = 0; i < kMaxShards; i++) ob.p[i] = outbox_ptrs->p[i];
+  const uint32_t grid = (uint32_t)(((uint64_t)n_shards * cap + kThreads - 1) / kThreads);
+  uint8_t* out = (uint8_t*)out_dev;
+  e->stats.kernel_launches++;
+  switch (e->msg) {
+    case 6: k_route_unpermute_p2p<6><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
+    case 9: k_route_unpermute_p2p<9><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
+    case 23: k_route_unpermute_p2p<23><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
+    case 53: k_route_unpermute_p2p<53><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
+    default: k_route_unpermute_p2p<55><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
+  }
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
 int dint_route_unpermute(dint_engine* e, const void* sorted_dev, const uint32_t* perm_dev, uint64_t n, void* out_dev, void* cuda_stream) {
   if (!e || n > 0xffffffffULL) return set_err(DINT_EINVAL, "bad argument");
   if (n == 0) return DINT_OK;

@@ -215,6 +215,85 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter_slabs(const uint8_t*
     perm[pos] = i;
   }
 }
+// ---- fused dispatch / combine over NVLink peer memory ----------------------------------------------------
+// Every rank owns a symmetric buffer {inbox[world][cap], outbox[world][cap], signals} that its peers map
+// (torch symmetric memory / CUDA IPC).  Dispatch: the partition kernel stores each record straight into the
+// OWNER's inbox slab for this source (remote stores over NVLink; no staging copy, no NCCL call); the padding
+// slots of every slab get the padding type byte.  Combine: the inverse-permutation kernel loads each reply
+// straight from the owner's outbox.  Ordering across GPUs: epoch counters written with system-scope
+// release stores after the data (k_p2p_signal) and polled with acquire loads (k_p2p_wait).
+struct PeerPtrs { uint64_t p[kMaxShards]; };
+
+template <int MSG>
+__global__ void __launch_bounds__(kThreads) k_route_scatter_p2p(const uint8_t* req, const uint8_t* owner, uint32_t n, uint32_t world,
+                                                                uint32_t me, uint32_t cap, const uint32_t* tilebase,
+                                                                const uint32_t* totals, PeerPtrs inbox, uint32_t* perm,
+                                                                uint32_t* overflow) {
+  __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  if (threadIdx.x < (kThreads / 32) * kMaxShards) ((uint32_t*)wcnt)[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t n_tiles = (n + kThreads - 1) / kThreads;
+  const uint32_t o = i < n ? owner[i] : 0xffu;
+  const uint32_t peers = __match_any_sync(0xffffffffu, o);
+  const uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
+  if (o < world && before == 0) wcnt[warp_id()][o] = __popc(peers);
+  __syncthreads();
+  if (o < world) {
+    uint32_t r = tilebase[(size_t)o * n_tiles + blockIdx.x] + before;
+    for (uint32_t w = 0; w < warp_id(); w++) r += wcnt[w][o];
+    if (r >= cap) atomicAdd(overflow, 1u);
+    else {
+      uint8_t* slab = (uint8_t*)inbox.p[o] + (size_t)me * cap * MSG;        // my slab inside the owner's inbox
+      copy_record<MSG>(slab + (size_t)r * MSG, req + (size_t)i * MSG);
+      perm[o * cap + r] = i;
+    }
+  }
+  // padding: slot j of slab o is padding when j >= totals[o]
+  const uint32_t slot = i;
+  if (slot < world * cap) {
+    const uint32_t so = slot / cap, sj = slot - so * cap;
+    if (sj >= totals[so]) {
+      uint8_t* rec = (uint8_t*)inbox.p[so] + ((size_t)me * cap + sj) * MSG;
+#pragma unroll
+      for (int b = 0; b < MSG; b++) rec[b] = kPadType;
+      perm[slot] = 0xffffffffu;
+    }
+  }
+}
+template <int MSG>
+__global__ void __launch_bounds__(kThreads) k_route_unpermute_p2p(PeerPtrs outbox, const uint32_t* perm, uint32_t world, uint32_t me,
+                                                                  uint32_t cap, uint8_t* out) {
+  const uint32_t pos = blockIdx.x * kThreads + threadIdx.x;
+  if (pos >= world * cap) return;
+  const uint32_t idx = perm[pos];
+  if (idx == 0xffffffffu) return;
+  const uint32_t o = pos / cap, r = pos - o * cap;
+  const uint8_t* src = (const uint8_t*)outbox.p[o] + ((size_t)me * cap + r) * MSG;   // my slab inside the owner's outbox
+  copy_record<MSG>(out + (size_t)idx * MSG, src);
+}
+// after the data: tell every peer that epoch `e` of this rank's slab is complete
+__global__ void k_p2p_signal(PeerPtrs sig, uint32_t world, uint32_t me, uint32_t epoch) {
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    volatile uint32_t* flag = (volatile uint32_t*)sig.p[threadIdx.x] + me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+  }
+}
+// before consuming: wait until every peer has signalled epoch `e` (bounded spin: ~4 s, then *timeout = 1)
+__global__ void k_p2p_wait(const uint32_t* my_sig, uint32_t world, uint32_t epoch, uint32_t* timeout) {
+  if (threadIdx.x < world) {
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_sig + threadIdx.x) : "memory");
+      if (clock64() - t0 > 8000000000LL) { atomicExch(timeout, 1u); break; }
+    } while ((int32_t)(v - epoch) < 0);
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
 // combine: replies arrive in partition order; put each back at its original index
 template <int MSG>
 __global__ void __launch_bounds__(kThreads) k_route_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {

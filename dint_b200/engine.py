@@ -29,6 +29,17 @@ class DintStats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
 
 
+class DintPeerPtrs(C.Structure):
+    _fields_ = [("p", C.c_uint64 * 8)]
+
+    @classmethod
+    def of(cls, ptrs):
+        o = cls()
+        for i, v in enumerate(ptrs):
+            o.p[i] = int(v)
+        return o
+
+
 class DintKernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("total_ms", C.c_double)]
 
@@ -38,7 +49,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_partition_slabs", "dint_route_unpermute", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_partition_slabs", "dint_route_unpermute", "dint_p2p_dispatch", "dint_p2p_wait", "dint_p2p_signal", "dint_p2p_combine", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod",
@@ -68,6 +79,11 @@ def lib():
     L.dint_route_owner.restype = i32; L.dint_route_owner.argtypes = [vp, vp, u64, vp, vp]
     L.dint_route_partition.restype = i32; L.dint_route_partition.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp]
     L.dint_route_partition_slabs.restype = i32; L.dint_route_partition_slabs.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp, vp, vp]
+    pp = C.POINTER(DintPeerPtrs)
+    L.dint_p2p_dispatch.restype = i32; L.dint_p2p_dispatch.argtypes = [vp, vp, vp, u64, u32, u32, u32, pp, pp, u32, vp, vp, vp]
+    L.dint_p2p_wait.restype = i32; L.dint_p2p_wait.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.dint_p2p_signal.restype = i32; L.dint_p2p_signal.argtypes = [vp, pp, u32, u32, u32, vp]
+    L.dint_p2p_combine.restype = i32; L.dint_p2p_combine.argtypes = [vp, pp, vp, u32, u32, u32, vp, vp]
     L.dint_route_unpermute.restype = i32; L.dint_route_unpermute.argtypes = [vp, vp, vp, u64, vp, vp]
     L.dint_sync.restype = i32; L.dint_sync.argtypes = [vp]
     L.dint_kv_get.restype = i32; L.dint_kv_get.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]

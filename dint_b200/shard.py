@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import wire
-from .engine import Engine, default_cfg
+from .engine import Engine, default_cfg, lib, DintPeerPtrs, DintError
 
 
 def group_moduli(kind, cfg):
@@ -61,7 +61,7 @@ class ShardedEngine:
     plug the oracle in to check the routing logic without a GPU)."""
 
     def __init__(self, kind, device=None, local_submit=None, group=None, by_dst=False, use_slabs=False, strict=True,
-                 slab_slack=None, **cfg_over):
+                 slab_slack=None, use_p2p=False, p2p_max_n=1 << 20, **cfg_over):
         """by_dst=True: tatp / smallbank placement -- the CLIENT names the destination shard of every record
         (primary key % G, backups, log); each rank is one complete `server_shard` (n_shards = 1) that
         populates only the keys it is a replica holder of (cfg txn_shards = world)."""
@@ -91,6 +91,77 @@ class ShardedEngine:
         self.use_slabs, self.strict = use_slabs, strict
         self.slab_slack = slab_slack if slab_slack is not None else (1.5 if by_dst else 1.02)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device) if self.engine is not None else None
+        self.use_p2p = False
+        if use_p2p and self.engine is not None:
+            self._init_p2p(p2p_max_n)
+
+    # ---- fused dispatch / combine over NVLink peer memory -------------------------------------------
+    def _cap(self, n):
+        mean = (n + self.world - 1) // self.world
+        cap = int(mean * self.slab_slack) + int(8 * (mean ** 0.5)) + 64
+        return (cap + 15) // 16 * 16
+
+    def _init_p2p(self, max_n):
+        """Symmetric buffer per rank: inbox [world][cap] | outbox [world][cap] | signal words, mapped by all peers
+        (torch symmetric memory = CUDA IPC + peer access over NVLink)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        W = self.world
+        self.p2p_max_n = max_n
+        region = (W * self._cap(max_n) * self.msg + 255) // 256 * 256
+        self.p2p_region = region
+        self.sym = symm_mem.empty(2 * region + 4096, dtype=torch.uint8, device=self.device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.sym_hdl = symm_mem.rendezvous(self.sym, group=grp.group_name)
+        self.sym.zero_()
+        torch.cuda.synchronize(self.device)
+        self.sym_hdl.barrier()
+        ptrs = list(self.sym_hdl.buffer_ptrs)
+        self.p_inbox = DintPeerPtrs.of(ptrs)
+        self.p_outbox = DintPeerPtrs.of([p + region for p in ptrs])
+        self.p_sigreq = DintPeerPtrs.of([p + 2 * region for p in ptrs])
+        self.p_sigrsp = DintPeerPtrs.of([p + 2 * region + 256 for p in ptrs])
+        self.my_sigreq = self.sym.data_ptr() + 2 * region
+        self.my_sigrsp = self.sym.data_ptr() + 2 * region + 256
+        self.p2p_flags = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        self.use_p2p = True
+
+    def _submit_gpu_p2p(self, req, n, dst):
+        """Dispatch = remote stores into the owners' inboxes, combine = remote loads from their outboxes; epoch
+        flags order the phases across GPUs.  No NCCL call, no host round trip.  Every rank must pass the same n."""
+        eng, W, L = self.engine, self.world, lib()
+        cap = self._cap(n)
+        self.epoch += 1
+        e = self.epoch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        sp = C.c_void_p(s) if s else None
+        owner = dst if dst is not None else eng.route_owner(req)
+        perm = torch.empty(W * cap, dtype=torch.int32, device=self.device)
+        fl = C.c_void_p(self.p2p_flags.data_ptr())
+        rc = L.dint_p2p_dispatch(eng.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, W, self.rank, cap,
+                                 C.byref(self.p_inbox), C.byref(self.p_sigreq), e, C.c_void_p(perm.data_ptr()), fl, sp)
+        if rc == 0:
+            rc = L.dint_p2p_wait(eng.h, C.c_void_p(self.my_sigreq), W, e, fl, sp)
+        if rc != 0:
+            raise DintError(rc, "dint_p2p_dispatch/wait")
+        nb = W * cap * self.msg
+        eng.submit_tensor(self.sym[:nb], self.sym[self.p2p_region:self.p2p_region + nb])
+        rc = L.dint_p2p_signal(eng.h, C.byref(self.p_sigrsp), W, self.rank, e, sp)
+        if rc == 0:
+            rc = L.dint_p2p_wait(eng.h, C.c_void_p(self.my_sigrsp), W, e, fl, sp)
+        out = torch.empty(n * self.msg, dtype=torch.uint8, device=self.device)
+        if rc == 0:
+            rc = L.dint_p2p_combine(eng.h, C.byref(self.p_outbox), C.c_void_p(perm.data_ptr()), W, self.rank, cap,
+                                    C.c_void_p(out.data_ptr()), sp)
+        if rc != 0:
+            raise DintError(rc, "dint_p2p_signal/wait/combine")
+        return out
+
+    def check_p2p(self):
+        """(overflowed records, timed-out waits) since the last check; both must be 0 for the results to stand."""
+        v = self.p2p_flags.tolist()
+        self.p2p_flags.zero_()
+        return v[0], v[1]
 
     def close(self):
         if self.engine is not None:
@@ -154,6 +225,11 @@ class ShardedEngine:
         return v != 0
 
     def _submit_gpu(self, req, n, dst):
+        if self.use_p2p and 0 < n <= self.p2p_max_n:
+            out = self._submit_gpu_p2p(req, n, dst)
+            if self.strict and self.check_p2p() != (0, 0):
+                raise RuntimeError("p2p exchange overflowed a slab or timed out")
+            return out
         if self.use_slabs and n >= self.world * 1024:
             out = self._submit_gpu_slabs(req, n, dst)
             if not self.strict:

@@ -150,6 +150,26 @@ int dint_route_partition(dint_engine *e, const void *req_dev, const uint8_t *own
  * did not fit (the caller must then repeat the batch through dint_route_partition). */
 int dint_route_partition_slabs(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
                                uint32_t cap, void *slabs_dev, uint32_t *perm_dev, uint32_t *overflow_dev, void *cuda_stream);
+/* Fused dispatch / combine over NVLink peer memory (one process per GPU; the buffers are each rank's
+ * symmetric-memory regions mapped into this process).  inbox_ptrs[o] / outbox_ptrs[o] / sig_ptrs[o]: device
+ * pointers to rank o's inbox [n_shards][cap] records, outbox (same shape) and signal words [n_shards] u32.
+ *   dint_p2p_dispatch: partitions n records by owner and STORES them into the owners' inboxes (slab `rank`),
+ *     pads the slabs, then release-signals epoch to every peer's sig[rank].
+ *   dint_p2p_wait:    blocks the stream until local_sig[0..n_shards) have all reached epoch (acquire).
+ *   dint_p2p_signal:  release-signals epoch to every peer's sig[rank] (replies ready in my outbox).
+ *   dint_p2p_combine: LOADS this rank's replies from the owners' outboxes into out_dev at their original
+ *     indices (perm_dev from dint_p2p_dispatch).
+ * *flags_dev (2 x u32): [0] += records that did not fit a slab, [1] = 1 if a wait timed out. */
+typedef struct dint_peer_ptrs { uint64_t p[8]; } dint_peer_ptrs;
+int dint_p2p_dispatch(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
+                      uint32_t cap, const dint_peer_ptrs *inbox_ptrs, const dint_peer_ptrs *sig_ptrs, uint32_t epoch,
+                      uint32_t *perm_dev, uint32_t *flags_dev, void *cuda_stream);
+int dint_p2p_wait(dint_engine *e, const uint32_t *local_sig_dev, uint32_t n_shards, uint32_t epoch, uint32_t *flags_dev,
+                  void *cuda_stream);
+int dint_p2p_signal(dint_engine *e, const dint_peer_ptrs *sig_ptrs, uint32_t n_shards, uint32_t rank, uint32_t epoch,
+                    void *cuda_stream);
+int dint_p2p_combine(dint_engine *e, const dint_peer_ptrs *outbox_ptrs, const uint32_t *perm_dev, uint32_t n_shards, uint32_t rank,
+                     uint32_t cap, void *out_dev, void *cuda_stream);
 int dint_route_unpermute(dint_engine *e, const void *sorted_dev, const uint32_t *perm_dev, uint64_t n, void *out_dev,
                          void *cuda_stream);
 int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kind, n_per_rank, use_slabs, ret):
+def _worker(rank, world, port, kind, n_per_rank, mode, ret):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -40,7 +40,7 @@ def _worker(rank, world, port, kind, n_per_rank, use_slabs, ret):
             mk, cfg = (lambda r: T.lock2pl_random(n_per_rank, 500, seed=5 + r)), {}
         else:
             mk, cfg = (lambda r: T.store_random(n_per_rank, 400, seed=5 + r)), dict(subs_populate=400)
-        se = ShardedEngine(kind, chunk=1 << 13, use_slabs=use_slabs, **cfg)
+        se = ShardedEngine(kind, chunk=1 << 13, use_slabs=(mode == 'slabs'), use_p2p=(mode == 'p2p'), p2p_max_n=n_per_rank, **cfg)
         if kind == wire.STORE:
             se.populate()
         got1 = se.submit(mk(rank))
@@ -57,10 +57,12 @@ def _worker(rank, world, port, kind, n_per_rank, use_slabs, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("use_slabs", [False, True], ids=["exact", "slabs"])
+@pytest.mark.parametrize("mode", ["exact", "slabs", "p2p"])
 @pytest.mark.parametrize("kind", [0, 1, 3])
-def test_sharded_nccl_world2(kind, use_slabs):
+def test_sharded_nccl_world2(kind, mode):
+    """exact = variable-count NCCL all-to-all; slabs = fixed-capacity NCCL exchange with padding records;
+    p2p = fused dispatch / combine through NVLink peer memory (no NCCL on the data path)."""
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), kind, 20000, use_slabs, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), kind, 20000, mode, ret), nprocs=2, join=True)
     assert dict(ret) == {0: True, 1: True}

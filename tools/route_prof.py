@@ -42,7 +42,19 @@ e0 = ev()
 for it in range(20):
     se.submit_tensor(req)
 e1 = ev(); torch.cuda.synchronize()
+# fused P2P path
+sp = ShardedEngine(wire.FASST, chunk=n + n // 2, use_p2p=True, p2p_max_n=n, strict=False)
+for it in range(5):
+    o2 = sp.submit_tensor(req)
+torch.cuda.synchronize(); dist.barrier()
+p0 = ev()
+for it in range(20):
+    o2 = sp.submit_tensor(req)
+p1 = ev(); torch.cuda.synchronize()
+p2p_us = p0.elapsed_time(p1) / 20 * 1e3
+p2p_flags = sp.check_p2p()
 if rank == 0:
+    print("p2p back-to-back submit_tensor: %.1f us per call" % p2p_us, "flags", p2p_flags)
     print("per-phase us (1M requests per rank, world=%d):" % world, {k: round(v / 20 * 1e3, 1) for k, v in acc.items()})
     print("back-to-back submit_tensor: %.1f us per call" % (e0.elapsed_time(e1) / 20 * 1e3), "overflow", se.check_overflow())
 dist.destroy_process_group()
