@@ -554,8 +554,27 @@ int dint_route_partition(dint_engine* e, const void* req_dev, const uint8_t* own
   return DINT_OK;
 }
 
+// first pass of a dispatch: per-tile per-shard counts, with the owners either given (client-chosen) or computed here
+static int route_first_pass(dint_engine* e, const uint8_t* rq, uint8_t* owner_dev, bool compute_owner, uint32_t n, uint32_t n_shards,
+                            uint32_t* tilecnt, cudaStream_t s) {
+  const uint32_t tiles = (n + kThreads - 1) / kThreads;
+  if (!compute_owner) { k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, n, n_shards, tilecnt); return DINT_OK; }
+  if (n_shards != e->ctx.n_shards) return set_err(DINT_EINVAL, "owner computation needs n_shards == cfg.n_shards");
+  switch (e->kind) {
+    case DINT_LOCK2PL: k_route_owner_count<K_LOCK2PL><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
+    case DINT_FASST: k_route_owner_count<K_FASST><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
+    case DINT_LOG: k_route_owner_count<K_LOG><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
+    case DINT_STORE: k_route_owner_count<K_STORE><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
+    case DINT_TATP: k_route_owner_count<K_TATP><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
+    default: k_route_owner_count<K_SMALLBANK><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
+  }
+  return DINT_OK;
+}
+
 int dint_route_partition_slabs(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards,
                                uint32_t cap, void* slabs_dev, uint32_t* perm_dev, uint32_t* overflow_dev, void* cuda_stream) {
+  const bool compute_owner = (n_shards & 0x80000000u) != 0;
+  n_shards &= 0x7fffffffu;
   if (!e || n_shards == 0 || n_shards > kMaxShards || n > 0xffffffffULL || cap == 0) return set_err(DINT_EINVAL, "bad argument");
   CU(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)cuda_stream;
@@ -572,7 +591,11 @@ int dint_route_partition_slabs(dint_engine* e, const void* req_dev, const uint8_
   CU(cudaMemsetAsync(perm_dev, 0xFF, slots * sizeof(uint32_t), s));  // 0xffffffff = padding slot
   if (n == 0) return DINT_OK;
   e->stats.kernel_launches += 3;
-  k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
+  {
+    // flag bit 31 of n_shards: "owner_dev is scratch, compute the owners from the keys"
+    int rc = route_first_pass(e, (const uint8_t*)req_dev, (uint8_t*)owner_dev, compute_owner, (uint32_t)n, n_shards, tilecnt, s);
+    if (rc) return rc;
+  }
   k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
   const uint8_t* rq = (const uint8_t*)req_dev;
   uint8_t* out = (uint8_t*)slabs_dev;
@@ -590,6 +613,8 @@ int dint_route_partition_slabs(dint_engine* e, const void* req_dev, const uint8_
 int dint_p2p_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
                       uint32_t cap, const dint_peer_ptrs* inbox_ptrs, const dint_peer_ptrs* sig_ptrs, uint32_t epoch,
                       uint32_t* perm_dev, uint32_t* flags_dev, void* cuda_stream) {
+  const bool compute_owner = (n_shards & 0x80000000u) != 0;
+  n_shards &= 0x7fffffffu;
   if (!e || !inbox_ptrs || !sig_ptrs || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 || n > 0xffffffffULL)
     return set_err(DINT_EINVAL, "bad argument");
   CU(cudaSetDevice(e->device));
@@ -606,7 +631,8 @@ int dint_p2p_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owner_
   for (uint32_t i = 0; i < kMaxShards; i++) { in.p[i] = inbox_ptrs->p[i]; sg.p[i] = sig_ptrs->p[i]; }
   e->stats.kernel_launches += 4;
   if (n) {
-    k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
+    int rc = route_first_pass(e, (const uint8_t*)req_dev, (uint8_t*)owner_dev, compute_owner, (uint32_t)n, n_shards, tilecnt, s);
+    if (rc) return rc;
     k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
   } else {
     CU(cudaMemsetAsync(totals, 0, kMaxShards * sizeof(uint32_t), s));

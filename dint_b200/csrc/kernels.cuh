@@ -310,6 +310,36 @@ template <int KIND> struct OrdSlice {
 };
 template <int KIND> DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch);
 
+// owner + per-tile per-shard counts in one pass (the first pass of the dispatch)
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_route_owner_count(const Ctx c, const uint8_t* req, uint32_t n, uint8_t* owner,
+                                                                uint32_t* tilecnt) {
+  using W = Wire<KIND>;
+  __shared__ uint32_t cnt[kMaxShards];
+  if (threadIdx.x < kMaxShards) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  uint32_t o = 0xffu;
+  if (i < n) {
+    const uint8_t* rec = req + (size_t)i * W::MSG;
+    const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
+    o = c.shard_id;
+    if (!ti.invalid && ti.mask) {
+      uint32_t gglobal;
+      if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
+      else if constexpr (KIND == K_STORE) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[0].lock_mod);
+      else if constexpr (KIND == K_TATP || KIND == K_SMALLBANK) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[rec[W::TABLE]].lock_mod);
+      else gglobal = c.shard_id;
+      o = gglobal - (uint32_t)fast_div(gglobal, c.shard_div) * c.n_shards;
+    }
+    owner[i] = (uint8_t)o;
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, o);
+  if (o < c.n_shards && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&cnt[o], (uint32_t)__popc(peers));
+  __syncthreads();
+  if (threadIdx.x < c.n_shards) tilecnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1 classify (+ clears the flag words of the previous chunk)
 // ---------------------------------------------------------------------------------------------------

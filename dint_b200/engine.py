@@ -261,8 +261,9 @@ class Engine:
         (int32 CUDA tensor of 1) is incremented on the device for every record that did not fit."""
         import torch
         n = owner.numel()
-        slabs = torch.empty(n_shards * cap * self.msg, dtype=torch.uint8, device=req.device)
-        perm = torch.empty(n_shards * cap, dtype=torch.int32, device=req.device)
+        ns = n_shards & 0x7fffffff                        # bit 31 = DINT_ROUTE_COMPUTE_OWNER
+        slabs = torch.empty(ns * cap * self.msg, dtype=torch.uint8, device=req.device)
+        perm = torch.empty(ns * cap, dtype=torch.int32, device=req.device)
         s = torch.cuda.current_stream(req.device).cuda_stream
         rc = lib().dint_route_partition_slabs(self.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, n_shards, cap,
                                               C.c_void_p(slabs.data_ptr()), C.c_void_p(perm.data_ptr()),

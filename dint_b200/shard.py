@@ -135,10 +135,11 @@ class ShardedEngine:
         e = self.epoch
         s = torch.cuda.current_stream(self.device).cuda_stream
         sp = C.c_void_p(s) if s else None
-        owner = dst if dst is not None else eng.route_owner(req)
+        owner = dst if dst is not None else torch.empty(n, dtype=torch.uint8, device=self.device)
+        wflag = W if dst is not None else (W | 0x80000000)
         perm = torch.empty(W * cap, dtype=torch.int32, device=self.device)
         fl = C.c_void_p(self.p2p_flags.data_ptr())
-        rc = L.dint_p2p_dispatch(eng.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, W, self.rank, cap,
+        rc = L.dint_p2p_dispatch(eng.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, wflag, self.rank, cap,
                                  C.byref(self.p_inbox), C.byref(self.p_sigreq), e, C.c_void_p(perm.data_ptr()), fl, sp)
         if rc == 0:
             rc = L.dint_p2p_wait(eng.h, C.c_void_p(self.my_sigreq), W, e, fl, sp)
@@ -207,8 +208,11 @@ class ShardedEngine:
         mean = (n + W - 1) // W
         cap = int(mean * self.slab_slack) + int(8 * (mean ** 0.5)) + 64
         cap = (cap + 15) // 16 * 16
-        owner = dst if dst is not None else eng.route_owner(req)
-        slabs, perm = eng.route_partition_slabs(req, owner, W, cap, self.overflow)
+        if dst is not None:
+            slabs, perm = eng.route_partition_slabs(req, dst, W, cap, self.overflow)
+        else:                                              # owners computed inside the first dispatch pass
+            scratch = torch.empty(n, dtype=torch.uint8, device=req.device)
+            slabs, perm = eng.route_partition_slabs(req, scratch, W | 0x80000000, cap, self.overflow)
         recv = torch.empty_like(slabs)
         dist.all_to_all_single(recv, slabs, group=self.group)
         out_local = torch.empty_like(recv)

@@ -147,7 +147,10 @@ int dint_route_partition(dint_engine *e, const void *req_dev, const uint8_t *own
  * records inside slabs_dev (n_shards * cap records, pre-filled with padding by this call: every byte 0xFE --
  * a padding record is answered unchanged and touches nothing); perm_dev (n_shards * cap entries) maps slab
  * positions to original indices (0xffffffff = padding); *overflow_dev is incremented for every record that
- * did not fit (the caller must then repeat the batch through dint_route_partition). */
+ * did not fit (the caller must then repeat the batch through dint_route_partition).
+ * For dint_route_partition_slabs and dint_p2p_dispatch: OR-ing DINT_ROUTE_COMPUTE_OWNER into n_shards makes the call
+ * compute the owners itself (as dint_route_owner would) into owner_dev, which is then a scratch buffer of n bytes. */
+#define DINT_ROUTE_COMPUTE_OWNER 0x80000000u
 int dint_route_partition_slabs(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
                                uint32_t cap, void *slabs_dev, uint32_t *perm_dev, uint32_t *overflow_dev, void *cuda_stream);
 /* Fused dispatch / combine over NVLink peer memory (one process per GPU; the buffers are each rank's
