@@ -248,6 +248,10 @@ class ShardedEngine:
             keep.extend([scratch, slabs, perm, recv])
             return recv, perm, ev, n
 
+        if not hasattr(self, "_ret"):
+            self._ret = torch.cuda.Stream(self.device)
+        ret = self._ret
+        ret.wait_stream(main)
         outs = []
         nxt = dispatch(reqs[0])
         for k in range(len(reqs)):
@@ -256,14 +260,19 @@ class ShardedEngine:
                 nxt = dispatch(reqs[k + 1])
             main.wait_event(ev)
             out_local = torch.empty_like(recv)
-            eng.submit_tensor(recv, out_local)
-            back = torch.empty_like(recv)
-            dist.all_to_all_single(back, out_local, group=self.group)
-            out = torch.empty(n * self.msg, dtype=torch.uint8, device=self.device)
-            outs.append(eng.route_unpermute(back, perm, out))
+            eng.submit_tensor(recv, out_local)               # main stream: the engine sees the batches in order
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(ret):                     # replies travel back while the next batch computes
+                ret.wait_event(done)
+                back = torch.empty_like(recv)
+                dist.all_to_all_single(back, out_local, group=self.group)
+                out = torch.empty(n * self.msg, dtype=torch.uint8, device=self.device)
+                outs.append(eng.route_unpermute(back, perm, out))
             keep.extend([out_local, back])
-        side.wait_stream(main)          # the side stream's buffers stay referenced until everything is enqueued
-        self._keep = keep
+        main.wait_stream(ret)
+        main.wait_stream(side)
+        self._keep = keep               # buffers of the side streams stay referenced until the next call
         return outs
 
     def check_overflow(self):
