@@ -257,23 +257,26 @@ def run_store_get(args, torch, rank, steps, warmup):
             "kernel_ms": {k: v[1] for k, v in kt.items()}}
 
 
-def run_tatp(args, torch, rank, rounds_timed=12, rounds_warm=8, clients=1 << 20, subscribers=7_000_000):
-    """TATP full transaction mix (35/35/10/2/14/2/2), the reference's closed-loop client state machines
+def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, clients=1 << 20):
+    """Full transaction mixes driven by the reference's closed-loop client state machines
     (dint_b200/csrc/txn_workloads.cc) against THREE shard servers (primary key % 3 + 2 backups + log on all
-    three, as tatp/caladan/client_udp_shard.cc) -- here three engines resident on one GPU, each holding the
-    reference's full 7,000,000-subscriber population."""
+    three, as {tatp,smallbank}/caladan/client_udp_shard.cc) -- here three engines resident on one GPU, each
+    holding the reference's full population (tatp: 7,000,000 subscribers, mix 35/35/10/2/14/2/2; smallbank:
+    24,000,000 accounts, 4 % hot accounts drawing 90 % of the transactions, mix 15/15/15/25/15/15)."""
     from dint_b200 import Engine, wire
     from dint_b200.txn_workloads import TxnWorkload, Cluster, partition_by_shard
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    msg, G = 55, 3
+    kind = wire.TATP if kind_name == "tatp" else wire.SMALLBANK
+    subscribers = 7_000_000 if kind == wire.TATP else 24_000_000
+    msg, G = wire.MSG_SIZE[kind], 3
     t0 = time.time()
 
     def make():
-        return [Engine(wire.TATP, device=dev.index, chunk=args.chunk, populate=True, subs_populate=subscribers) for _ in range(G)]
+        return [Engine(kind, device=dev.index, chunk=args.chunk, populate=True) for _ in range(G)]
 
     engs = make()
     t_pop = time.time() - t0
-    wl = TxnWorkload(wire.TATP, n_clients=clients, n_shards=G, subscribers=subscribers, gid0=rank * clients)
+    wl = TxnWorkload(kind, n_clients=clients, n_shards=G, subscribers=subscribers, gid0=rank * clients)
     cl = Cluster([e.submit for e in engs], msg)
     rec, committed, nreq = [], [], []
     for r in range(rounds_warm + rounds_timed):
@@ -316,8 +319,10 @@ def run_tatp(args, torch, rank, rounds_timed=12, rounds_warm=8, clients=1 << 20,
         e.close()
     tc = sum(committed[rounds_warm:])
     tr = sum(nreq[rounds_warm:])
-    return {"workload": f"TATP mix, {clients} closed-loop clients, 3 shard servers x {subscribers} subscribers on one GPU, "
+    return {"workload": f"{kind_name} mix, {clients} closed-loop clients, 3 shard servers x {subscribers} "
+                        f"{'subscribers' if kind == wire.TATP else 'accounts'} on one GPU, "
                         f"{rounds_timed} protocol rounds timed (device-resident replay of the recorded closed-loop trace)",
+            "abort_rate": 1.0 - st["committed"] / max(1, st["txns"]),
             "txn_per_s": tc / (ms * 1e-3), "requests_per_s": tr / (ms * 1e-3), "requests_per_txn": st["requests"] / max(1, st["txns"]),
             "commit_rate_by_type": {k: round(v[1] / max(1, v[0]), 4) for k, v in st["by_type"].items()},
             "replies_bit_exact": ok, "gpu_launches": launches, "conflicted_fraction": conflicted / max(1, tr),
@@ -423,7 +428,8 @@ def main():
                 "conflicted_fraction": hot["stats"]["conflicted"] / max(1, hot["stats"]["requests"]),
                 "replies_bit_exact": bool(hot["parity_last_step"])}}
             line["extra"]["store_get"] = run_store_get(args, torch, rank, max(3, args.steps // 2), 3)
-            line["extra"]["tatp"] = run_tatp(args, torch, rank)
+            line["extra"]["tatp"] = run_txn(args, torch, rank, "tatp")
+            line["extra"]["smallbank"] = run_txn(args, torch, rank, "smallbank")
         except Exception as ex:  # side measurements must never cost the headline line
             line.setdefault("extra", {})["error"] = repr(ex)
     print(json.dumps(line))

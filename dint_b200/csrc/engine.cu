@@ -75,7 +75,6 @@ struct dint_engine {
   cudaAccessPolicyWindow window{};
   // stats
   dint_stats stats{};
-  unsigned long long counters_seen[4] = {0, 0, 0, 0};
   // profiling
   uint32_t profiling = 0;          // bit k set: bracket launches of kernel k (KT_*) with CUDA events
   std::vector<EvPair> ev_pool;

@@ -68,7 +68,7 @@ typedef struct dint_cfg {
   uint32_t shard_id;
   uint32_t chunk;          /* requests per internal launch group (0 = default 1<<20) */
   uint32_t kv_capacity_log2[5]; /* per-table open-addressing capacity (0 = auto: >= 2x expected keys) */
-  uint32_t flags;          /* DINT_F_* */
+  uint32_t flags;          /* reserved, must be 0 */
   uint32_t txn_shards;     /* tatp / smallbank replica placement (tatp/caladan/client_udp_shard.cc:187,490-531 generalised
                               from 3 to G shards): 0 or 1 = this server holds every key (the reference: all three
                               shards populate everything); G > 3: dint_populate() keeps only keys whose primary
@@ -76,8 +76,6 @@ typedef struct dint_cfg {
   uint32_t txn_shard_id;
   uint32_t reserved[2];
 } dint_cfg;
-
-#define DINT_F_GRAPH 1u    /* replay the per-chunk launch sequence through a CUDA graph */
 
 typedef struct dint_engine dint_engine;
 
