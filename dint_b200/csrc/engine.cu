@@ -200,6 +200,7 @@ static int grids_for(dint_engine* e) {
     CU(cudaFuncSetAttribute(k_classify<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
     CU(cudaFuncSetAttribute(k_apply<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
   }
+  { const char* pad = getenv("DINT_APPLY_SMEM_PAD"); if (pad) e->smem_stage += (uint32_t)atoi(pad); }   // occupancy experiments
   e->smem_classify = e->smem_stage;
   if (KIND != K_LOG && (kTile / 32) * OrdSlice<KIND>::BYTES > e->smem_classify) e->smem_classify = (kTile / 32) * OrdSlice<KIND>::BYTES;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kTile, e->smem_classify));
