@@ -224,8 +224,8 @@ static void fill_chunk_ctx(dint_engine* e, Ctx& c) {
   c.flags = e->d_flags[cur];
   c.flags_prev = e->d_flags[cur ^ 1];
   c.prev_n = e->prev_n;
-  c.nc_cur = e->d_nc + 2 * cur;
-  c.nc_ord = e->d_nc + 2 * (cur ^ 1);
+  c.nc_cur = e->d_nc + 4 * cur;          // {listed, overflow, a writer exists, -}
+  c.nc_ord = e->d_nc + 4 * (cur ^ 1);
   c.ord_pending = e->ord_pending ? 1u : 0u;
   c.ord_resp = e->ord_resp;
 }
@@ -437,7 +437,7 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.clist, (size_t)e->max_tiles * kTile))) return rc;
   if ((rc = dalloc(e, &c.ccnt, e->max_tiles))) return rc;
   if ((rc = dalloc(e, &c.cprefix, e->max_tiles + 1))) return rc;
-  if ((rc = dalloc(e, &e->d_nc, 4))) return rc;
+  if ((rc = dalloc(e, &e->d_nc, 8))) return rc;
   {
     uint32_t lg = 0;
     while (((uint64_t)kBucketFill << lg) < ch) lg++;

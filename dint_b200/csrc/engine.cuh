@@ -102,8 +102,9 @@ struct Ctx {
   uint32_t* clist;         // [n_tiles][kTile] indices of listed requests, tile-segmented
   uint32_t* ccnt;          // [n_tiles] listed requests per tile
   uint32_t* cprefix;       // [n_tiles+1] exclusive prefix of ccnt (K3 general path)
-  uint32_t* nc_cur;        // [2] of THIS chunk: [0] listed requests, [1] bucket overflows (K1 resets, K2 counts)
-  const uint32_t* nc_ord;  // [2] of the chunk whose listed requests are replayed by this launch
+  uint32_t* nc_cur;        // of THIS chunk: [0] listed requests, [1] bucket overflows (K1 resets, K2 counts),
+                           //                [2] a writer exists (K1 sets; the NEXT launch's K1 clears it)
+  uint32_t* nc_ord;        // same, of the chunk whose listed requests are replayed by this launch
   uint8_t* ord_resp;       // reply array of that chunk (K2 left the listed requests' bytes there)
   uint32_t ord_pending;    // 1: a previous chunk still has listed requests to replay (done inside K1)
   uint64_t* buckets;       // [2^bucket_log2][kBucketCap] (group << 32 | index), filled by K2

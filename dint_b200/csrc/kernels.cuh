@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   __shared__ uint32_t scratch[kTile / 32];
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
-    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; }
+    // [2] (a writer exists) is OR-ed by any CTA of this launch, so it is cleared one launch early: each K1
+    // clears the slot of the chunk it replays, which is the slot the NEXT chunk will use
+    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; c.nc_ord[2] = 0; }
   }
   __syncthreads();
   // The previous chunk's listed requests are replayed by this launch too (their buckets were filled by its
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   // tile instead (the value is consumed after the NEXT tile's atomics have been issued).
   uint32_t pend_old = 0, pend_test = 0, pend_sh = 0;
   uint32_t* pend_w = nullptr;
+  bool saw_writer = false;          // any request of this CTA's tiles that writes A or L
   for (uint32_t i = 0; i < it.n_my; i++) {
     // the stage that held tile i-1 is free (barrier at the end of iteration i-1): refill it now
     if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
             atomicOr(w, F_R << sh);                      // no return value: a fire-and-forget RED
           } else {
             const uint32_t bits = ((ti.mask & C_RA) ? F_R : 0u) | ((ti.mask & C_WA) ? F_WA : 0u) | ((ti.mask & C_WL) ? F_WL : 0u);
+            saw_writer = true;
             new_old = atomicOr(w, bits << sh);
             new_test = ((ti.mask & C_WA) ? F_WA : 0u) | ((ti.mask & C_WL) ? F_WL : 0u);
             new_w = w;
@@ -431,6 +435,8 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     }
   }
   if (pend_w && ((pend_old >> pend_sh) & pend_test)) atomicOr(pend_w, F_W2 << pend_sh);
+  // a chunk without a single writer cannot hold a conflict: K2 then skips the flag lookups altogether
+  if (__syncthreads_or(saw_writer ? 1 : 0) && threadIdx.x == 0) atomicOr(&c.nc_cur[2], 1u);
   if (do_ord && !ord_first) {
     __syncthreads();                                     // the stages double as the replay's scratch
     ordered_buckets<KIND>(c, smem);
@@ -492,6 +498,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
   const TileIter it = tile_iter(c.n_tiles);
   if (threadIdx.x == 0)
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+  const bool chunk_has_writer = c.nc_cur[2] != 0;      // set by K1; false = nothing in this chunk can conflict
 
   for (uint32_t i = 0; i < it.n_my; i++) {
     uint32_t* scratch = scratch2[i & 1];
@@ -526,7 +533,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
       // issue the state fetch and the flag lookup back to back: one HBM latency, not two
       const bool active = valid && !ti.invalid && ti.mask;
       pf = prefetch_coop<KIND>(c, rec, ki, ti, active);
-      if (active) {
+      if (active && chunk_has_writer) {
         const uint32_t f = (__ldcg(&c.flags[flag_word(c, ki.grp)]) >> flag_shift(ki.grp)) & 15u;
         listed = ((ti.mask & C_RA) && (f & F_WA)) || ((ti.mask & C_WA) && (f & (F_R | F_W2))) ||
                  ((ti.mask & C_WL) && (f & F_W2));
