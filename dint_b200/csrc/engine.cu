@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/dint_b200.h"
@@ -53,6 +54,9 @@ struct dint_engine {
   uint8_t* d_resp[kHostBufs] = {nullptr};
   cudaEvent_t ev_in[kHostBufs]{}, ev_comp[kHostBufs]{}, ev_out[kHostBufs]{};
   uint32_t host_chunk = 0;                   // requests per host-path slice
+  uint32_t host_min_slice = 0;               // smallest slice of the pyramid a host-path call is cut into
+  bool host_ramp_up = true;
+  unsigned long long* h_counters = nullptr;  // pinned mirror of ctx.counters (host path reads it without a blocking copy)
   int coop_grid = 0;
   int grid_classify = 0, grid_apply = 0;     // persistent CTAs (SMs x resident CTAs per SM)
   uint32_t smem_stage = 0;                   // dynamic shared memory of K1/K2: kStages staged tiles
@@ -298,6 +302,46 @@ static void route_unpermute_t(const uint8_t* sorted, const uint32_t* perm, uint3
   k_route_unpermute<MSG><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(sorted, perm, n, out);
 }
 
+// Host-path slice sizes for a call of n requests (see dint_submit): slices double from `mn` up to the plateau
+// `mx`, the body moves in plateau slices (a remainder first), and the end halves back down to `mn`.
+struct HostSlices {
+  uint32_t lvl[32];          // pyramid levels below the plateau, smallest first
+  uint32_t n_lvl = 0, i_up = 0, i_down = 0;
+  uint64_t body = 0, plateau = 0, pending = 0;
+  bool ramp_up;
+  HostSlices(uint64_t n, uint32_t mn, uint32_t mx, bool ramp_up_) : ramp_up(ramp_up_) {
+    if (mn > mx) mn = mx;
+    uint64_t used = 0;
+    for (uint64_t s = mn; s < mx && n_lvl < 32; s <<= 1) {
+      const uint64_t cost = ramp_up ? 2 * s : s;
+      if (used + cost > n) break;
+      lvl[n_lvl++] = (uint32_t)s;
+      used += cost;
+    }
+    body = n - used;
+    plateau = n_lvl ? (uint64_t)lvl[n_lvl - 1] * 2 : mx;
+    if (plateau > mx) plateau = mx;
+    i_down = n_lvl;
+    if (!ramp_up) i_up = n_lvl;
+  }
+  uint32_t next() {          // 0 = done
+    if (i_up < n_lvl) return lvl[i_up++];
+    if (body) {
+      const uint64_t rem = body % plateau;
+      uint64_t c = rem ? rem : plateau;
+      if (pending) { c = pending; pending = 0; }
+      else if (rem && body > rem) {                        // a remainder is shared with one plateau slice: two
+        c = (plateau + rem + 1) / 2;                       // mid-size slices instead of a tiny one and a full one
+        pending = plateau + rem - c;
+      }
+      body -= c;
+      return (uint32_t)c;
+    }
+    if (i_down) return lvl[--i_down];
+    return 0;
+  }
+};
+
 // ======================================================================================================
 extern "C" {
 
@@ -333,6 +377,7 @@ void dint_destroy(dint_engine* e) {
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_route) cudaFree(e->d_route);
+  if (e->h_counters) cudaFreeHost(e->h_counters);
   for (auto& ep : e->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (int i = 0; i < kHostBufs; i++) {
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
@@ -494,6 +539,11 @@ int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
     uint32_t want = hc ? (uint32_t)atoi(hc) : (1u << 18);
     if (want < (uint32_t)kTile) want = kTile;
     e->host_chunk = want < e->chunk ? (want + kTile - 1) / kTile * kTile : e->chunk;
+    const char* ms = getenv("DINT_HOST_MIN_SLICE");
+    e->host_min_slice = ms ? (uint32_t)atoi(ms) : 131072u;
+    const char* ru = getenv("DINT_HOST_RAMP_UP");
+    e->host_ramp_up = ru ? atoi(ru) != 0 : true;
+    if (e->host_min_slice < (uint32_t)kTile) e->host_min_slice = kTile;
   }
   e->msg = kMsgSize[kind];
   e->has_log = kLogEntry[kind] != 0;
@@ -744,6 +794,8 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
       if ((rc = dalloc(e, &e->d_resp[i], (size_t)hchunk * e->msg + 16, false))) return rc;
     }
   }
+  static const bool trace = getenv("DINT_HOST_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
   CU(cudaDeviceSynchronize());     // order after anything submitted on user streams
   const uint8_t* rq = (const uint8_t*)req;
   uint8_t* rs = (uint8_t*)resp;
@@ -761,9 +813,17 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
     CU(cudaEventRecord(e->ev_out[pb], e->s_out));
     return DINT_OK;
   };
-  for (uint64_t off = 0; off < n; off += hchunk, k++) {
+  // Slice schedule.  PCIe moves large copies better than small ones (B200 box, pinned, both directions busy:
+  // 37 GB/s per direction at 2.4 MB, 46 at 9.4 MB, 50 at 38 MB: tools/pcie_probe.cu), but the first slice's
+  // H2D and the last two slices' kernels + D2H overlap with nothing.  So a call is cut as a pyramid: slices
+  // double from host_min_slice up to host_chunk, stay there, and halve back down at the end.  (Measured with
+  // tools/e2e_probe.py: every schedule between 128K..1M slices lands within 5 % -- the copies, not the
+  // kernels or the launches (11 us of CPU per slice), are the bound: 1M requests = 345 us vs 203 us for two
+  // perfectly overlapped 9.4 MB copies.)
+  HostSlices sched(n, e->host_min_slice, hchunk, e->host_ramp_up);
+  uint64_t off = 0;
+  for (uint64_t cn; (cn = sched.next()) != 0; k++) {
     int b = (int)(k % kHostBufs);
-    uint64_t cn = (n - off < hchunk) ? (n - off) : hchunk;
     size_t bytes = (size_t)cn * e->msg;
     if (k >= (uint64_t)kHostBufs) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));   // slice k-kHostBufs no longer read
     CU(cudaMemcpyAsync(e->d_req[b], rq + off * e->msg, bytes, cudaMemcpyHostToDevice, e->s_in));
@@ -777,17 +837,29 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
     prev_bytes = bytes;
     e->stats.h2d_bytes += bytes;
     e->stats.d2h_bytes += bytes;
+    off += cn;
   }
   {
     int rc = flush_ordered(e, e->stream);
     if (rc) return rc;
     if (k >= 1 && (rc = copy_out_prev(k))) return rc;
   }
+  if (!e->h_counters) CU(cudaHostAlloc((void**)&e->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+  CU(cudaMemcpyAsync(e->h_counters, e->ctx.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  const auto t_enq = std::chrono::steady_clock::now();
   CU(cudaStreamSynchronize(e->s_out));
   CU(cudaStreamSynchronize(e->stream));
   int rc = prof_flush(e);
   if (rc) return rc;
-  if ((rc = pull_counters(e))) return rc;
+  if (trace) {
+    const auto t_end = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dint_submit] n=%llu slices=%llu enqueue=%.1f us total=%.1f us\n", (unsigned long long)n, (unsigned long long)k,
+            std::chrono::duration<double, std::micro>(t_enq - t_begin).count(),
+            std::chrono::duration<double, std::micro>(t_end - t_begin).count());
+  }
+  e->stats.errors = e->h_counters[0];
+  e->stats.conflicted = e->h_counters[1];
+  e->stats.max_run = e->h_counters[2];
   return e->stats.errors != err_before ? DINT_EPROTO : DINT_OK;
 }
 
