@@ -11,6 +11,7 @@
 
 #include "../../include/dint_b200.h"
 #include "kernels.cuh"
+#include "route.cuh"
 #include "kv.cuh"
 
 using namespace dint;
@@ -54,10 +55,12 @@ struct dint_engine {
   uint8_t* d_resp[kHostBufs] = {nullptr};
   cudaEvent_t ev_in[kHostBufs]{}, ev_comp[kHostBufs]{}, ev_out[kHostBufs]{};
   uint32_t host_chunk = 0;                   // requests per host-path slice
+  bool plain_launches = false;               // inside the multi-GPU step: no cooperative launches (see GridBar)
   uint32_t host_min_slice = 0;               // smallest slice of the pyramid a host-path call is cut into
   bool host_ramp_up = true;
   unsigned long long* h_counters = nullptr;  // pinned mirror of ctx.counters (host path reads it without a blocking copy)
   int coop_grid = 0;
+  int sms = 0;
   int grid_classify = 0, grid_apply = 0;     // persistent CTAs (SMs x resident CTAs per SM)
   uint32_t smem_stage = 0;                   // dynamic shared memory of K1/K2: kStages staged tiles
   uint64_t total_groups = 0;
@@ -71,6 +74,8 @@ struct dint_engine {
   uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
   uint32_t* d_route = nullptr;               // multi-GPU dispatch scratch (per-tile per-shard counts)
   uint32_t route_tiles = 0;
+  uint32_t* d_route2 = nullptr;              // dispatch scratch: [grid][8] per-CTA counts + the finished-CTA counter
+  int grid_route = 0;                        // co-resident CTAs of k_route_dispatch
   // L2 persistence: the flag sets (+ lock_fasst lock bits) live in one arena that every launch maps
   // with a persisting access-policy window, so the streaming request/reply traffic cannot evict it
   uint8_t* hot_arena = nullptr;
@@ -177,7 +182,13 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
     Ctx f = c;           // this chunk's own counters / replies
     f.nc_ord = c.nc_cur;
     f.ord_resp = c.resp;
-    CU(launch_ex(e, k_ordered<KIND>, e->coop_grid, kThreads, 0, s, true, f));
+    f.coop_launch = e->plain_launches ? 0u : 1u;
+    int g3 = e->coop_grid;
+    if (e->plain_launches && e->sms > 0) {             // leave room for the one-warp flag-polling kernels of the other streams
+      const int per = g3 / e->sms;
+      g3 = (per > 1 ? per - 1 : 1) * e->sms;
+    }
+    CU(launch_ex(e, k_ordered<KIND>, g3, kThreads, 0, s, !e->plain_launches, f));
   }
   CU(cudaGetLastError());
   return DINT_OK;
@@ -218,6 +229,7 @@ static int grids_for(dint_engine* e) {
   if (per_sm < 1) return set_err(DINT_EIO, "k_ordered cannot be resident");
   if (per_sm > 4) per_sm = 4;
   e->coop_grid = per_sm * sms;
+  e->sms = sms;
   return DINT_OK;
 }
 
@@ -293,11 +305,6 @@ static void route_scatter_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, ui
   k_route_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, totals, out, perm);
 }
 template <int MSG>
-static void route_scatter_slabs_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, uint32_t world, uint32_t cap, const uint32_t* tb,
-                                  uint8_t* slabs, uint32_t* perm, uint32_t* overflow, uint32_t tiles, cudaStream_t s) {
-  k_route_scatter_slabs<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, cap, tb, slabs, perm, overflow);
-}
-template <int MSG>
 static void route_unpermute_t(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out, cudaStream_t s) {
   k_route_unpermute<MSG><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(sorted, perm, n, out);
 }
@@ -342,6 +349,36 @@ struct HostSlices {
   }
 };
 
+// ---- fused dispatch / combine (route.cuh) ---------------------------------------------------------------
+template <int KIND>
+static int route_dispatch_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) {
+  using RT = RTile<Wire<KIND>::MSG>;
+  if (!e->d_route2) {
+    e->grid_route = 148 * 8;
+    CU(cudaMalloc(&e->d_route2, ((size_t)e->grid_route * kMaxShards + 16) * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(e->d_route2, 0, ((size_t)e->grid_route * kMaxShards + 16) * sizeof(uint32_t), s));
+  }
+  RouteArgs b = a;
+  b.done = e->d_route2;
+  b.cta_tot = e->d_route2 + 16;
+  int grid = (int)b.n_tiles < e->grid_route ? (int)b.n_tiles : e->grid_route;
+  if (grid < 1) grid = 1;
+  k_route_count<KIND><<<grid, kThreads, 0, s>>>(e->ctx, b);
+  k_route_scatter<KIND><<<grid, kThreads, RT::SMEM, s>>>(b);
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+template <int MSG>
+static int route_combine_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) {
+  using RT = RTile<MSG>;
+  int grid = (int)a.n_tiles;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_route_combine<MSG><<<grid, kThreads, RT::SMEM, s>>>(a);
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+static uint32_t route_tile_records(const dint_engine* e) { return e->msg <= 12 ? kThreads * 4u : (uint32_t)kThreads; }
+
 // ======================================================================================================
 extern "C" {
 
@@ -377,6 +414,7 @@ void dint_destroy(dint_engine* e) {
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_route) cudaFree(e->d_route);
+  if (e->d_route2) cudaFree(e->d_route2);
   if (e->h_counters) cudaFreeHost(e->h_counters);
   for (auto& ep : e->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (int i = 0; i < kHostBufs; i++) {
@@ -498,6 +536,7 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.log_tilebase, e->max_tiles))) return rc;
   if ((rc = dalloc(e, &c.log_total, 2))) return rc;
   if ((rc = dalloc(e, &c.counters, 4))) return rc;
+  if ((rc = dalloc(e, &c.gbar, 4))) return rc;
 
   switch (e->kind) {
     case DINT_LOCK2PL: rc = grids_for<K_LOCK2PL, false>(e); break;
@@ -604,102 +643,68 @@ int dint_route_partition(dint_engine* e, const void* req_dev, const uint8_t* own
   return DINT_OK;
 }
 
-// first pass of a dispatch: per-tile per-shard counts, with the owners either given (client-chosen) or computed here
-static int route_first_pass(dint_engine* e, const uint8_t* rq, uint8_t* owner_dev, bool compute_owner, uint32_t n, uint32_t n_shards,
-                            uint32_t* tilecnt, cudaStream_t s) {
-  const uint32_t tiles = (n + kThreads - 1) / kThreads;
-  if (!compute_owner) { k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, n, n_shards, tilecnt); return DINT_OK; }
-  if (n_shards != e->ctx.n_shards) return set_err(DINT_EINVAL, "owner computation needs n_shards == cfg.n_shards");
-  switch (e->kind) {
-    case DINT_LOCK2PL: k_route_owner_count<K_LOCK2PL><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
-    case DINT_FASST: k_route_owner_count<K_FASST><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
-    case DINT_LOG: k_route_owner_count<K_LOG><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
-    case DINT_STORE: k_route_owner_count<K_STORE><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
-    case DINT_TATP: k_route_owner_count<K_TATP><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
-    default: k_route_owner_count<K_SMALLBANK><<<tiles, kThreads, 0, s>>>(e->ctx, rq, n, owner_dev, tilecnt); break;
-  }
-  return DINT_OK;
-}
+uint32_t dint_route_tile_records(dint_engine* e) { return e ? route_tile_records(e) : 0; }
 
-int dint_route_partition_slabs(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards,
-                               uint32_t cap, void* slabs_dev, uint32_t* perm_dev, uint32_t* overflow_dev, void* cuda_stream) {
-  const bool compute_owner = (n_shards & 0x80000000u) != 0;
-  n_shards &= 0x7fffffffu;
-  if (!e || n_shards == 0 || n_shards > kMaxShards || n > 0xffffffffULL || cap == 0) return set_err(DINT_EINVAL, "bad argument");
-  CU(cudaSetDevice(e->device));
-  cudaStream_t s = (cudaStream_t)cuda_stream;
-  const uint32_t tiles = (uint32_t)((n + kThreads - 1) / kThreads);
-  if (tiles > e->route_tiles) {
-    if (e->d_route) { CU(cudaFree(e->d_route)); e->d_route = nullptr; }
-    e->route_tiles = tiles + tiles / 2 + 64;
-    CU(cudaMalloc(&e->d_route, ((size_t)e->route_tiles * kMaxShards + 3 * kMaxShards) * sizeof(uint32_t)));
-  }
-  uint32_t* totals = e->d_route;
-  uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
-  const size_t slots = (size_t)n_shards * cap;
-  CU(cudaMemsetAsync(slabs_dev, 0xFE, slots * e->msg, s));          // padding records
-  CU(cudaMemsetAsync(perm_dev, 0xFF, slots * sizeof(uint32_t), s));  // 0xffffffff = padding slot
-  if (n == 0) return DINT_OK;
-  e->stats.kernel_launches += 3;
-  {
-    // flag bit 31 of n_shards: "owner_dev is scratch, compute the owners from the keys"
-    int rc = route_first_pass(e, (const uint8_t*)req_dev, (uint8_t*)owner_dev, compute_owner, (uint32_t)n, n_shards, tilecnt, s);
-    if (rc) return rc;
-  }
-  k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
-  const uint8_t* rq = (const uint8_t*)req_dev;
-  uint8_t* out = (uint8_t*)slabs_dev;
-  switch (e->msg) {
-    case 6: route_scatter_slabs_t<6>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
-    case 9: route_scatter_slabs_t<9>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
-    case 23: route_scatter_slabs_t<23>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
-    case 53: route_scatter_slabs_t<53>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
-    default: route_scatter_slabs_t<55>(rq, owner_dev, (uint32_t)n, n_shards, cap, tilecnt, out, perm_dev, overflow_dev, tiles, s); break;
-  }
-  CU(cudaGetLastError());
-  return DINT_OK;
-}
-
-int dint_p2p_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owner_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
-                      uint32_t cap, const dint_peer_ptrs* inbox_ptrs, const dint_peer_ptrs* sig_ptrs, uint32_t epoch,
-                      uint32_t* perm_dev, uint32_t* flags_dev, void* cuda_stream) {
-  const bool compute_owner = (n_shards & 0x80000000u) != 0;
-  n_shards &= 0x7fffffffu;
-  if (!e || !inbox_ptrs || !sig_ptrs || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 || n > 0xffffffffULL)
+int dint_route_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owner_in_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
+                        uint32_t cap, const dint_peer_ptrs* slab_ptrs, const dint_peer_ptrs* sig_ptrs, uint32_t epoch,
+                        uint8_t* owner_dev, uint32_t* tilebase_dev, uint32_t* flags_dev, void* cuda_stream) {
+  if (!e || !slab_ptrs || !flags_dev || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 || n > 0xffffffffULL ||
+      (n && (!req_dev || !owner_dev || !tilebase_dev)))
     return set_err(DINT_EINVAL, "bad argument");
+  if ((uintptr_t)req_dev & 15) return set_err(DINT_EINVAL, "device buffers must be 16-byte aligned");
+  if (!owner_in_dev && n_shards != e->ctx.n_shards) return set_err(DINT_EINVAL, "owner computation needs n_shards == cfg.n_shards");
   CU(cudaSetDevice(e->device));
+  RouteArgs a{};
+  a.req = (const uint8_t*)req_dev;
+  a.owner_in = owner_in_dev;
+  a.owner = owner_dev;
+  a.tilebase = tilebase_dev;
+  a.flags = flags_dev;
+  a.n = (uint32_t)n;
+  a.n_tiles = (uint32_t)((n + route_tile_records(e) - 1) / route_tile_records(e));
+  a.world = n_shards;
+  a.me = rank;
+  a.cap = cap;
+  a.epoch = epoch;
+  for (uint32_t i = 0; i < kMaxShards; i++) { a.slab.p[i] = slab_ptrs->p[i]; a.sig.p[i] = sig_ptrs ? sig_ptrs->p[i] : 0; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  const uint32_t tiles = (uint32_t)((n + kThreads - 1) / kThreads);
-  if (tiles + 1 > e->route_tiles) {
-    if (e->d_route) { CU(cudaFree(e->d_route)); e->d_route = nullptr; }
-    e->route_tiles = tiles + tiles / 2 + 64;
-    CU(cudaMalloc(&e->d_route, ((size_t)e->route_tiles * kMaxShards + 3 * kMaxShards) * sizeof(uint32_t)));
+  e->stats.kernel_launches += 2;
+  switch (e->kind) {
+    case DINT_LOCK2PL: return route_dispatch_t<K_LOCK2PL>(e, a, s);
+    case DINT_FASST: return route_dispatch_t<K_FASST>(e, a, s);
+    case DINT_LOG: return route_dispatch_t<K_LOG>(e, a, s);
+    case DINT_STORE: return route_dispatch_t<K_STORE>(e, a, s);
+    case DINT_TATP: return route_dispatch_t<K_TATP>(e, a, s);
+    default: return route_dispatch_t<K_SMALLBANK>(e, a, s);
   }
-  uint32_t* totals = e->d_route;
-  uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
-  PeerPtrs in{}, sg{};
-  for (uint32_t i = 0; i < kMaxShards; i++) { in.p[i] = inbox_ptrs->p[i]; sg.p[i] = sig_ptrs->p[i]; }
-  e->stats.kernel_launches += 4;
-  if (n) {
-    int rc = route_first_pass(e, (const uint8_t*)req_dev, (uint8_t*)owner_dev, compute_owner, (uint32_t)n, n_shards, tilecnt, s);
-    if (rc) return rc;
-    k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
-  } else {
-    CU(cudaMemsetAsync(totals, 0, kMaxShards * sizeof(uint32_t), s));
-  }
-  const uint64_t slots = (uint64_t)n_shards * cap;
-  const uint32_t grid = (uint32_t)(((n > slots ? n : slots) + kThreads - 1) / kThreads);
-  const uint8_t* rq = (const uint8_t*)req_dev;
+}
+
+int dint_route_combine(dint_engine* e, const dint_peer_ptrs* reply_slab_ptrs, const uint8_t* owner_dev, const uint32_t* tilebase_dev,
+                       uint64_t n, uint32_t n_shards, uint32_t cap, void* out_dev, void* cuda_stream) {
+  if (!e || !reply_slab_ptrs || n_shards == 0 || n_shards > kMaxShards || cap == 0 || n > 0xffffffffULL ||
+      (n && (!owner_dev || !tilebase_dev || !out_dev)))
+    return set_err(DINT_EINVAL, "bad argument");
+  if ((uintptr_t)out_dev & 15) return set_err(DINT_EINVAL, "device buffers must be 16-byte aligned");
+  if (n == 0) return DINT_OK;
+  CU(cudaSetDevice(e->device));
+  RouteArgs a{};
+  a.owner = (uint8_t*)owner_dev;
+  a.tilebase = (uint32_t*)tilebase_dev;
+  a.out = (uint8_t*)out_dev;
+  a.n = (uint32_t)n;
+  a.n_tiles = (uint32_t)((n + route_tile_records(e) - 1) / route_tile_records(e));
+  a.world = n_shards;
+  a.cap = cap;
+  for (uint32_t i = 0; i < kMaxShards; i++) a.slab.p[i] = reply_slab_ptrs->p[i];
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  e->stats.kernel_launches++;
   switch (e->msg) {
-    case 6: k_route_scatter_p2p<6><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
-    case 9: k_route_scatter_p2p<9><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
-    case 23: k_route_scatter_p2p<23><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
-    case 53: k_route_scatter_p2p<53><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
-    default: k_route_scatter_p2p<55><<<grid, kThreads, 0, s>>>(rq, owner_dev, (uint32_t)n, n_shards, rank, cap, tilecnt, totals, in, perm_dev, flags_dev); break;
+    case 6: return route_combine_t<6>(e, a, s);
+    case 9: return route_combine_t<9>(e, a, s);
+    case 23: return route_combine_t<23>(e, a, s);
+    case 53: return route_combine_t<53>(e, a, s);
+    default: return route_combine_t<55>(e, a, s);
   }
-  k_p2p_signal<<<1, 32, 0, s>>>(sg, n_shards, rank, epoch);
-  CU(cudaGetLastError());
-  return DINT_OK;
 }
 
 int dint_p2p_wait(dint_engine* e, const uint32_t* local_sig_dev, uint32_t n_shards, uint32_t epoch, uint32_t* flags_dev, void* cuda_stream) {
@@ -718,27 +723,6 @@ int dint_p2p_signal(dint_engine* e, const dint_peer_ptrs* sig_ptrs, uint32_t n_s
   for (uint32_t i = 0; i < kMaxShards; i++) sg.p[i] = sig_ptrs->p[i];
   e->stats.kernel_launches++;
   k_p2p_signal<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(sg, n_shards, rank, epoch);
-  CU(cudaGetLastError());
-  return DINT_OK;
-}
-
-int dint_p2p_combine(dint_engine* e, const dint_peer_ptrs* outbox_ptrs, const uint32_t* perm_dev, uint32_t n_shards, uint32_t rank,
-                     uint32_t cap, void* out_dev, void* cuda_stream) {
-  if (!e || !outbox_ptrs || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards) return set_err(DINT_EINVAL, "bad argument");
-  CU(cudaSetDevice(e->device));
-  cudaStream_t s = (cudaStream_t)cuda_stream;
-  PeerPtrs ob{};
-  for (uint32_t i = 0; i < kMaxShards; i++) ob.p[i] = outbox_ptrs->p[i];
-  const uint32_t grid = (uint32_t)(((uint64_t)n_shards * cap + kThreads - 1) / kThreads);
-  uint8_t* out = (uint8_t*)out_dev;
-  e->stats.kernel_launches++;
-  switch (e->msg) {
-    case 6: k_route_unpermute_p2p<6><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
-    case 9: k_route_unpermute_p2p<9><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
-    case 23: k_route_unpermute_p2p<23><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
-    case 53: k_route_unpermute_p2p<53><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
-    default: k_route_unpermute_p2p<55><<<grid, kThreads, 0, s>>>(ob, perm_dev, n_shards, rank, cap, out); break;
-  }
   CU(cudaGetLastError());
   return DINT_OK;
 }
@@ -1013,6 +997,143 @@ int64_t dint_kv_count(dint_engine* e, int table) {
   unsigned long long v = 0;
   if (cudaMemcpy(&v, e->ctx.tbl[table].live, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return DINT_EIO;
   return (int64_t)v;
+}
+
+// ---- the whole sharded step over NVLink peer memory, driven from one host call -----------------------------
+// Three streams per rank: `side` partitions batch j+1 into the owners' inboxes while the caller's stream runs
+// the engine on batch j and `ret` pulls the replies of batch j-1 out of the owners' outboxes.  The only
+// cross-GPU synchronisation is three arrays of epoch words per rank (requests written / replies written /
+// replies read), n_sets buffer sets deep.
+struct dint_shard_ctx {
+  dint_engine* e = nullptr;
+  uint32_t W = 0, me = 0, cap = 0, S = 0;
+  uint64_t inbox[4][kMaxShards]{}, outbox[4][kMaxShards]{};
+  PeerPtrs sigreq{}, sigrsp{}, sigdone{};
+  uint32_t *my_req = nullptr, *my_rsp = nullptr, *my_done = nullptr;
+  uint32_t epoch = 0;
+  cudaStream_t side = nullptr, ret = nullptr;
+  cudaEvent_t ev_disp[4]{}, ev_comb[4]{}, ev_fork = nullptr;
+  uint8_t* owner[4]{};
+  uint32_t* tilebase[4]{};
+  uint32_t* flags = nullptr;
+  uint64_t max_n = 0;
+};
+
+int dint_shard_create(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets, const dint_peer_ptrs* inbox_sets,
+                      const dint_peer_ptrs* outbox_sets, const dint_peer_ptrs* sig_blocks, uint64_t max_n, dint_shard_ctx** out) {
+  if (!e || !out || !inbox_sets || !outbox_sets || !sig_blocks || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 ||
+      n_sets < 2 || n_sets > 4 || max_n == 0 || max_n > 0xffffffffULL)
+    return set_err(DINT_EINVAL, "bad argument");
+  CU(cudaSetDevice(e->device));
+  dint_shard_ctx* c = new dint_shard_ctx();
+  e->plain_launches = true;
+  c->e = e; c->W = n_shards; c->me = rank; c->cap = cap; c->S = n_sets; c->max_n = max_n;
+  for (uint32_t s = 0; s < n_sets; s++)
+    for (uint32_t o = 0; o < n_shards; o++) { c->inbox[s][o] = inbox_sets[s].p[o]; c->outbox[s][o] = outbox_sets[s].p[o]; }
+  for (uint32_t o = 0; o < n_shards; o++) {
+    c->sigreq.p[o] = sig_blocks->p[o];
+    c->sigrsp.p[o] = sig_blocks->p[o] + 64;
+    c->sigdone.p[o] = sig_blocks->p[o] + 128;
+  }
+  c->my_req = (uint32_t*)sig_blocks->p[rank];
+  c->my_rsp = (uint32_t*)(sig_blocks->p[rank] + 64);
+  c->my_done = (uint32_t*)(sig_blocks->p[rank] + 128);
+  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->ret, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  const uint32_t tr = route_tile_records(e);
+  const size_t tiles = (size_t)((max_n + tr - 1) / tr);
+  for (uint32_t s = 0; s < n_sets; s++) {
+    CU(cudaEventCreateWithFlags(&c->ev_disp[s], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_comb[s], cudaEventDisableTiming));
+    CU(cudaMalloc(&c->owner[s], max_n + 16));
+    CU(cudaMalloc(&c->tilebase[s], tiles * kMaxShards * sizeof(uint32_t)));
+  }
+  CU(cudaMalloc(&c->flags, 2 * sizeof(uint32_t)));
+  CU(cudaMemset(c->flags, 0, 2 * sizeof(uint32_t)));
+  *out = c;
+  return DINT_OK;
+}
+
+void dint_shard_destroy(dint_shard_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->e->device);
+  cudaDeviceSynchronize();
+  for (uint32_t s = 0; s < c->S; s++) {
+    if (c->ev_disp[s]) cudaEventDestroy(c->ev_disp[s]);
+    if (c->ev_comb[s]) cudaEventDestroy(c->ev_comb[s]);
+    if (c->owner[s]) cudaFree(c->owner[s]);
+    if (c->tilebase[s]) cudaFree(c->tilebase[s]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->flags) cudaFree(c->flags);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ret) cudaStreamDestroy(c->ret);
+  delete c;
+}
+
+int dint_shard_flags(dint_shard_ctx* c, uint32_t out[2]) {
+  if (!c || !out) return DINT_EINVAL;
+  CU(cudaSetDevice(c->e->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, c->flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemset(c->flags, 0, 2 * sizeof(uint32_t)));
+  return DINT_OK;
+}
+
+int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req_dev, const uint8_t* const* dst_dev, uint64_t n,
+                           void* const* out_dev, void* cuda_stream) {
+  if (!c || !req_dev || !out_dev || n == 0 || n > c->max_n) return set_err(DINT_EINVAL, "bad argument");
+  dint_engine* e = c->e;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t main = (cudaStream_t)cuda_stream;
+  const uint32_t W = c->W, S = c->S;
+  const size_t slab = (size_t)c->cap * e->msg;
+  CU(cudaEventRecord(c->ev_fork, main));
+  CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  CU(cudaStreamWaitEvent(c->ret, c->ev_fork, 0));
+  auto dispatch = [&](uint32_t j, uint32_t ep) -> int {    // on `side`
+    const uint32_t s = ep % S;
+    if (ep > S) {
+      k_p2p_wait<<<1, 32, 0, c->side>>>(c->my_rsp, W, ep - S, c->flags + 1);     // every owner has consumed inbox set s
+      CU(cudaStreamWaitEvent(c->side, c->ev_comb[s], 0));                        // and my combine is done with its state
+    }
+    dint_peer_ptrs in{}, sg{};
+    for (uint32_t o = 0; o < W; o++) { in.p[o] = c->inbox[s][o] + (uint64_t)c->me * slab; sg.p[o] = c->sigreq.p[o]; }
+    int rc = dint_route_dispatch(e, req_dev[j], dst_dev ? dst_dev[j] : nullptr, n, W, c->me, c->cap, &in, &sg, ep, c->owner[s],
+                                 c->tilebase[s], c->flags, c->side);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_disp[s], c->side));
+    return DINT_OK;
+  };
+  uint32_t ep0 = c->epoch;
+  int rc = dispatch(0, ep0 + 1);
+  if (rc) return rc;
+  for (uint32_t j = 0; j < k; j++) {
+    const uint32_t ep = ep0 + 1 + j, s = ep % S;
+    if (j + 1 < k && (rc = dispatch(j + 1, ep + 1))) return rc;
+    // caller's stream: the engine sees the batches in order
+    k_p2p_wait<<<1, 32, 0, main>>>(c->my_req, W, ep, c->flags + 1);                    // every source's slab has arrived
+    if (ep > S) k_p2p_wait<<<1, 32, 0, main>>>(c->my_done, W, ep - S, c->flags + 1);   // outbox set s has been read
+    rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)W * c->cap, (uint8_t*)c->outbox[s][c->me], main);
+    if (rc) return rc;
+    k_p2p_signal<<<1, 32, 0, main>>>(c->sigrsp, W, c->me, ep);
+    // ret: the replies travel back while the next batch computes
+    CU(cudaStreamWaitEvent(c->ret, c->ev_disp[s], 0));
+    k_p2p_wait<<<1, 32, 0, c->ret>>>(c->my_rsp, W, ep, c->flags + 1);
+    dint_peer_ptrs ob{};
+    for (uint32_t o = 0; o < W; o++) ob.p[o] = c->outbox[s][o] + (uint64_t)c->me * slab;
+    rc = dint_route_combine(e, &ob, c->owner[s], c->tilebase[s], n, W, c->cap, out_dev[j], c->ret);
+    if (rc) return rc;
+    k_p2p_signal<<<1, 32, 0, c->ret>>>(c->sigdone, W, c->me, ep);
+    CU(cudaEventRecord(c->ev_comb[s], c->ret));
+    e->stats.kernel_launches += 5;
+  }
+  c->epoch = ep0 + k;
+  for (uint32_t s = 0; s < S; s++) CU(cudaStreamWaitEvent(main, c->ev_comb[s], 0));   // join
+  CU(cudaStreamWaitEvent(main, c->ev_disp[(ep0 + k) % S], 0));
+  CU(cudaGetLastError());
+  return DINT_OK;
 }
 
 }  // extern "C"

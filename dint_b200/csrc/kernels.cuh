@@ -97,29 +97,24 @@ DINT_D uint8_t* acquire_tile(const Ctx& c, uint8_t* smem, uint64_t* full, const 
   return tile;
 }
 
+// the shard that owns a request: the slot / bucket / lock_hash ONE server would compute, modulo the shard count
+template <int KIND>
+DINT_D uint32_t route_owner_of(const Ctx& c, const uint8_t* rec) {
+  using W = Wire<KIND>;
+  const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
+  if (ti.invalid || !ti.mask) return c.shard_id;         // no per-key state touched: serve it where it arrived
+  uint32_t gglobal;
+  if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
+  else if constexpr (KIND == K_STORE) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[0].lock_mod);
+  else if constexpr (KIND == K_TATP || KIND == K_SMALLBANK) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[rec[W::TABLE]].lock_mod);
+  else return c.shard_id;
+  return gglobal - (uint32_t)fast_div(gglobal, c.shard_div) * c.n_shards;
+}
 // owner shard of every request (multi-GPU routing; see dint_route_owner)
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uint8_t* req, uint32_t n, uint8_t* owner) {
-  using W = Wire<KIND>;
   const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t* rec = req + (size_t)i * W::MSG;
-  const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
-  uint32_t o = c.shard_id;                          // no per-key state touched: serve it where it arrived
-  if (!ti.invalid && ti.mask) {
-    uint32_t gglobal;                               // the slot / bucket / lock_hash ONE server would compute
-    if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) {
-      gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
-    } else if constexpr (KIND == K_STORE) {
-      gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[0].lock_mod);
-    } else if constexpr (KIND == K_TATP || KIND == K_SMALLBANK) {
-      gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[rec[W::TABLE]].lock_mod);
-    } else {
-      gglobal = c.shard_id;
-    }
-    o = gglobal - (uint32_t)fast_div(gglobal, c.shard_div) * c.n_shards;
-  }
-  owner[i] = (uint8_t)o;
+  if (i < n) owner[i] = (uint8_t)route_owner_of<KIND>(c, req + (size_t)i * Wire<KIND>::MSG);
 }
 
 // ---- multi-GPU dispatch: stable partition of a batch by owner shard -------------------------------------
@@ -191,87 +186,14 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, 
     perm[pos] = i;
   }
 }
-// Fixed-capacity variant for the exchange without a host round trip: shard o's records go to slab o
-// (`cap` records each; the rest of a slab stays padding); a record that does not fit raises *overflow.
-template <int MSG>
-__global__ void __launch_bounds__(kThreads) k_route_scatter_slabs(const uint8_t* req, const uint8_t* owner, uint32_t n,
-                                                                  uint32_t world, uint32_t cap, const uint32_t* tilebase,
-                                                                  uint8_t* slabs, uint32_t* perm, uint32_t* overflow) {
-  __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
-  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-  if (threadIdx.x < (kThreads / 32) * kMaxShards) ((uint32_t*)wcnt)[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t o = i < n ? owner[i] : 0xffu;
-  const uint32_t peers = __match_any_sync(0xffffffffu, o);
-  const uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
-  if (o < world && before == 0) wcnt[warp_id()][o] = __popc(peers);
-  __syncthreads();
-  if (o < world) {
-    uint32_t r = tilebase[(size_t)o * gridDim.x + blockIdx.x] + before;
-    for (uint32_t w = 0; w < warp_id(); w++) r += wcnt[w][o];
-    if (r >= cap) { atomicAdd(overflow, 1u); return; }
-    const uint32_t pos = o * cap + r;
-    copy_record<MSG>(slabs + (size_t)pos * MSG, req + (size_t)i * MSG);
-    perm[pos] = i;
-  }
-}
-// ---- fused dispatch / combine over NVLink peer memory ----------------------------------------------------
+// ---- exchange over NVLink peer memory: epoch flags ---------------------------------------------------------
 // Every rank owns a symmetric buffer {inbox[world][cap], outbox[world][cap], signals} that its peers map
-// (torch symmetric memory / CUDA IPC).  Dispatch: the partition kernel stores each record straight into the
-// OWNER's inbox slab for this source (remote stores over NVLink; no staging copy, no NCCL call); the padding
-// slots of every slab get the padding type byte.  Combine: the inverse-permutation kernel loads each reply
-// straight from the owner's outbox.  Ordering across GPUs: epoch counters written with system-scope
-// release stores after the data (k_p2p_signal) and polled with acquire loads (k_p2p_wait).
+// (torch symmetric memory / CUDA IPC).  The dispatch kernel (route.cuh) stores each record straight into the
+// OWNER's inbox slab for this source, the combine kernel loads each reply straight from the owner's outbox.
+// Ordering across GPUs: epoch counters written with system-scope release stores after the data and polled
+// with acquire loads.
 struct PeerPtrs { uint64_t p[kMaxShards]; };
 
-template <int MSG>
-__global__ void __launch_bounds__(kThreads) k_route_scatter_p2p(const uint8_t* req, const uint8_t* owner, uint32_t n, uint32_t world,
-                                                                uint32_t me, uint32_t cap, const uint32_t* tilebase,
-                                                                const uint32_t* totals, PeerPtrs inbox, uint32_t* perm,
-                                                                uint32_t* overflow) {
-  __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
-  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-  if (threadIdx.x < (kThreads / 32) * kMaxShards) ((uint32_t*)wcnt)[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t n_tiles = (n + kThreads - 1) / kThreads;
-  const uint32_t o = i < n ? owner[i] : 0xffu;
-  const uint32_t peers = __match_any_sync(0xffffffffu, o);
-  const uint32_t before = __popc(peers & ((1u << lane_id()) - 1u));
-  if (o < world && before == 0) wcnt[warp_id()][o] = __popc(peers);
-  __syncthreads();
-  if (o < world) {
-    uint32_t r = tilebase[(size_t)o * n_tiles + blockIdx.x] + before;
-    for (uint32_t w = 0; w < warp_id(); w++) r += wcnt[w][o];
-    if (r >= cap) atomicAdd(overflow, 1u);
-    else {
-      uint8_t* slab = (uint8_t*)inbox.p[o] + (size_t)me * cap * MSG;        // my slab inside the owner's inbox
-      copy_record<MSG>(slab + (size_t)r * MSG, req + (size_t)i * MSG);
-      perm[o * cap + r] = i;
-    }
-  }
-  // padding: slot j of slab o is padding when j >= totals[o]
-  const uint32_t slot = i;
-  if (slot < world * cap) {
-    const uint32_t so = slot / cap, sj = slot - so * cap;
-    if (sj >= totals[so]) {
-      uint8_t* rec = (uint8_t*)inbox.p[so] + ((size_t)me * cap + sj) * MSG;
-#pragma unroll
-      for (int b = 0; b < MSG; b++) rec[b] = kPadType;
-      perm[slot] = 0xffffffffu;
-    }
-  }
-}
-template <int MSG>
-__global__ void __launch_bounds__(kThreads) k_route_unpermute_p2p(PeerPtrs outbox, const uint32_t* perm, uint32_t world, uint32_t me,
-                                                                  uint32_t cap, uint8_t* out) {
-  const uint32_t pos = blockIdx.x * kThreads + threadIdx.x;
-  if (pos >= world * cap) return;
-  const uint32_t idx = perm[pos];
-  if (idx == 0xffffffffu) return;
-  const uint32_t o = pos / cap, r = pos - o * cap;
-  const uint8_t* src = (const uint8_t*)outbox.p[o] + ((size_t)me * cap + r) * MSG;   // my slab inside the owner's outbox
-  copy_record<MSG>(out + (size_t)idx * MSG, src);
-}
 // after the data: tell every peer that epoch `e` of this rank's slab is complete
 __global__ void k_p2p_signal(PeerPtrs sig, uint32_t world, uint32_t me, uint32_t epoch) {
   if (threadIdx.x < world) {
@@ -309,36 +231,6 @@ template <int KIND> struct OrdSlice {
   static constexpr uint32_t BYTES = kBucketCap * (FastReplay<KIND>::ok ? (8 + 8 + 4) : 8);
 };
 template <int KIND> DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch);
-
-// owner + per-tile per-shard counts in one pass (the first pass of the dispatch)
-template <int KIND>
-__global__ void __launch_bounds__(kThreads) k_route_owner_count(const Ctx c, const uint8_t* req, uint32_t n, uint8_t* owner,
-                                                                uint32_t* tilecnt) {
-  using W = Wire<KIND>;
-  __shared__ uint32_t cnt[kMaxShards];
-  if (threadIdx.x < kMaxShards) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-  uint32_t o = 0xffu;
-  if (i < n) {
-    const uint8_t* rec = req + (size_t)i * W::MSG;
-    const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
-    o = c.shard_id;
-    if (!ti.invalid && ti.mask) {
-      uint32_t gglobal;
-      if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
-      else if constexpr (KIND == K_STORE) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[0].lock_mod);
-      else if constexpr (KIND == K_TATP || KIND == K_SMALLBANK) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[rec[W::TABLE]].lock_mod);
-      else gglobal = c.shard_id;
-      o = gglobal - (uint32_t)fast_div(gglobal, c.shard_div) * c.n_shards;
-    }
-    owner[i] = (uint8_t)o;
-  }
-  const uint32_t peers = __match_any_sync(0xffffffffu, o);
-  if (o < c.n_shards && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&cnt[o], (uint32_t)__popc(peers));
-  __syncthreads();
-  if (threadIdx.x < c.n_shards) tilecnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];
-}
 
 // ---------------------------------------------------------------------------------------------------
 // K1 classify (+ clears the flag words of the previous chunk)
@@ -753,12 +645,44 @@ DINT_D uint64_t fx_block_scan(uint64_t x, uint64_t* sh, uint64_t* total) {
   return have ? fx_compose(pre, x) : x;
 }
 
+// Grid-wide barrier of k_ordered.  Stand-alone engines launch it cooperatively (cg grid sync).  Inside the
+// multi-GPU step other streams hold flag-polling kernels that wait for PEERS, and a cooperative launch is not
+// started while another kernel is resident -- it would wait for a kernel that waits for it.  There the
+// launch is a plain one (the grid is sized to be co-resident next to those one-warp kernels) and the barrier is
+// a generation counter in global memory.
+struct GridBar {
+  cg::grid_group g;
+  uint32_t* bar;            // [0] arrivals, [1] generation
+  bool coop;
+  DINT_D void sync() {
+    if (coop) { g.sync(); return; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t gen;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+      __threadfence();
+      if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+        bar[0] = 0;
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+      } else {
+        uint32_t now;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
+        } while (now == gen);
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
   const uint32_t nc = c.nc_ord[0];
   const uint32_t overflow = c.nc_ord[1];
   if (nc == 0 || overflow == 0) return;               // the bucket path (inside the next K1) handles this chunk
-  cg::grid_group grid = cg::this_grid();
+  GridBar grid{cg::this_grid(), c.gbar, c.coop_launch != 0};
   __shared__ uint64_t skeys[2048];                    // radix counters
   __shared__ uint32_t wsum[kThreads / 32];
   __shared__ uint32_t s_carry;

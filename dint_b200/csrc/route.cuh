@@ -1,0 +1,332 @@
+// Multi-GPU dispatch / combine: stable partition of a batch of wire records by owner shard, written straight
+// into fixed-capacity slabs (local memory for an NCCL exchange, or the owners' receive buffers over NVLink),
+// and its inverse.  Two plain launches over the same grid (no cooperative launch: inside the multi-GPU step
+// other streams hold flag-polling kernels, see GridBar in kernels.cuh); the batch comes from HBM once:
+//
+//   k_route_count    every CTA owns a contiguous range of tiles: owner shard of every record (hash of the key,
+//            the slot ONE server would compute, modulo the shard count -- or the client-chosen shard), one byte
+//            per record, and the CTA's per-shard record counts
+//   k_route_scatter  exclusive prefix over the CTAs' counts = first slot of this CTA's records in every slab; the
+//            tiles are read again (L2 hits), partitioned in shared memory into one run per shard, and every run
+//            leaves with 16-byte stores: runs sit in shared memory at the alignment of their destination.
+//            Slots past a slab's total become padding records; the last CTA to finish raises the epoch flags
+//            of the peers (release, system scope) when the slabs live in peer memory.
+//
+// The combine reads, per tile, one contiguous run per shard from the reply slabs and reassembles the tile in
+// request order; its only per-record state is the owner byte and, per tile, the first slot of each run.
+//
+// The reference does this on the CLIENT (key % 3 / lock-id hashing before sendto, e.g.
+// tatp/caladan/client_ebpf_shard.cc: `key % kNumServers`); here any rank may receive any request.
+#pragma once
+#include "kernels.cuh"
+
+namespace dint {
+template <int MSG> struct RTile {
+  static constexpr int PER = MSG <= 12 ? 4 : 1;                  // records per thread
+  static constexpr int RECS = kThreads * PER;                    // records per tile
+  static constexpr int BYTES = RECS * MSG;                       // a multiple of 16
+  static constexpr int RUNS = BYTES + 16 * kMaxShards + 16;      // the partitioned copy: alignment gaps between runs
+  static constexpr int SMEM = BYTES + 16 + RUNS;
+};
+
+struct RouteArgs {
+  const uint8_t* req;        // dispatch: [n * MSG] wire records, 16-byte aligned
+  const uint8_t* owner_in;   // dispatch: client-chosen shard per record, or nullptr = computed from the keys
+  uint8_t* owner;            // [n] owner byte per record (dispatch writes, combine reads); 0xff = undeliverable
+  uint32_t* tilebase;        // [n_tiles][kMaxShards] first slot of each tile's run in each slab
+  uint32_t* cta_tot;         // dispatch scratch [grid][kMaxShards]
+  uint32_t* done;            // dispatch scratch, zero between launches
+  uint32_t* flags;           // [0] += records that did not fit their slab
+  uint8_t* out;              // combine: [n * MSG] replies in request order, 16-byte aligned
+  uint32_t n, n_tiles, world, me, cap, epoch;
+  PeerPtrs slab;             // slab of THIS source at shard o (request slabs for dispatch, reply slabs for combine)
+  PeerPtrs sig;              // dispatch: epoch word array of shard o (word `me` is written); 0 = no signalling
+};
+
+// eight 16-bit counters (one per shard); a tile holds at most 1024 records, so fields never carry
+struct Cnt8 { uint64_t lo, hi; };
+DINT_D Cnt8 operator+(Cnt8 a, Cnt8 b) { return Cnt8{a.lo + b.lo, a.hi + b.hi}; }
+DINT_D Cnt8 operator-(Cnt8 a, Cnt8 b) { return Cnt8{a.lo - b.lo, a.hi - b.hi}; }
+DINT_D uint32_t cnt8_get(Cnt8 a, uint32_t o) { return (uint32_t)(((o < 4 ? a.lo : a.hi) >> (16 * (o & 3))) & 0xffffu); }
+DINT_D void cnt8_inc(Cnt8& a, uint32_t o) {
+  const uint64_t one = 1ull << (16 * (o & 3));
+  if (o < 4) a.lo += one; else a.hi += one;
+}
+// exclusive prefix of `mine` over the CTA's threads, and the CTA total (all threads get both)
+DINT_D void block_scan_cnt8(Cnt8 mine, Cnt8& excl, Cnt8& total, Cnt8* s_w) {
+  Cnt8 x = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Cnt8 y{__shfl_up_sync(0xffffffffu, x.lo, o), __shfl_up_sync(0xffffffffu, x.hi, o)};
+    if ((int)lane_id() >= o) x = x + y;
+  }
+  if (lane_id() == 31) s_w[warp_id()] = x;
+  __syncthreads();
+  Cnt8 woff{0, 0}, tot{0, 0};
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++) {
+    if (w < (int)warp_id()) woff = woff + s_w[w];
+    tot = tot + s_w[w];
+  }
+  excl = woff + x - mine;
+  total = tot;
+  __syncthreads();
+}
+
+// All threads of the CTA: copy nbytes; src and dst have the SAME address modulo 16.
+DINT_D void coop_copy16(uint8_t* dst, const uint8_t* src, uint32_t nbytes) {
+  uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  if (head > nbytes) head = nbytes;
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+  const uint32_t body = (nbytes - head) >> 4;
+  const uint4* s4 = (const uint4*)(src + head);
+  uint4* d4 = (uint4*)(dst + head);
+  for (uint32_t i = threadIdx.x; i < body; i += kThreads) d4[i] = s4[i];
+  const uint32_t done = head + (body << 4);
+  if (threadIdx.x < nbytes - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+// All threads of the CTA: fill nbytes at any alignment with the padding byte.
+DINT_D void coop_fill_pad(uint8_t* dst, uint64_t nbytes) {
+  uint64_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  if (head > nbytes) head = nbytes;
+  if (threadIdx.x < head) dst[threadIdx.x] = kPadType;
+  const uint64_t body = (nbytes - head) >> 4;
+  uint4* d4 = (uint4*)(dst + head);
+  const uint32_t p = 0x01010101u * kPadType;
+  for (uint64_t i = threadIdx.x; i < body; i += kThreads) d4[i] = make_uint4(p, p, p, p);
+  const uint64_t done = head + (body << 4);
+  if (threadIdx.x < nbytes - done) dst[done + threadIdx.x] = kPadType;
+}
+
+// owners of this thread's records of tile t, as bytes (0xff = none) and as a counter vector
+template <int PER>
+DINT_D Cnt8 load_owners(const RouteArgs& a, uint32_t t, uint32_t (&own)[PER]) {
+  const uint32_t i0 = (t * kThreads + threadIdx.x) * PER;
+  Cnt8 mine{0, 0};
+  if (PER == 4 && i0 + 3 < a.n) {
+    const uint32_t w = *(const uint32_t*)(a.owner + i0);
+#pragma unroll
+    for (int j = 0; j < PER; j++) own[j] = (w >> (8 * j)) & 0xffu;
+  } else {
+#pragma unroll
+    for (int j = 0; j < PER; j++) own[j] = i0 + j < a.n ? a.owner[i0 + j] : 0xffu;
+  }
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+    if (own[j] < a.world) cnt8_inc(mine, own[j]);
+  return mine;
+}
+
+// dispatch, launch 1 of 2: owner byte per record, per-CTA per-shard counts (CTA b owns a contiguous range of tiles)
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_route_count(const Ctx c, const RouteArgs a) {
+  using W = Wire<KIND>;
+  using RT = RTile<W::MSG>;
+  constexpr int MSG = W::MSG, PER = RT::PER;
+  __shared__ uint32_t s_cnt[kMaxShards];
+  const uint32_t G = gridDim.x, b = blockIdx.x;
+  const uint32_t t0 = (uint32_t)((uint64_t)a.n_tiles * b / G), t1 = (uint32_t)((uint64_t)a.n_tiles * (b + 1) / G);
+  if (threadIdx.x < kMaxShards) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t i0 = (t * kThreads + threadIdx.x) * PER;
+    uint32_t own[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const uint32_t i = i0 + j;
+      uint32_t o = 0xffu;
+      if (i < a.n) {
+        o = a.owner_in ? a.owner_in[i] : route_owner_of<KIND>(c, a.req + (size_t)i * MSG);
+        if (o >= a.world) o = 0xffu;
+      }
+      own[j] = o;
+    }
+    if (PER == 4 && i0 + 3 < a.n) {
+      *(uint32_t*)(a.owner + i0) = own[0] | (own[1 % PER] << 8) | (own[2 % PER] << 16) | (own[3 % PER] << 24);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (i0 + j < a.n) a.owner[i0 + j] = (uint8_t)own[j];
+    }
+    for (uint32_t o = 0; o < a.world; o++) {
+      uint32_t k = 0;
+#pragma unroll
+      for (int j = 0; j < PER; j++) k += __popc(__ballot_sync(0xffffffffu, own[j] == o));
+      if (lane_id() == 0 && k) atomicAdd(&s_cnt[o], k);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxShards) a.cta_tot[b * kMaxShards + threadIdx.x] = threadIdx.x < a.world ? s_cnt[threadIdx.x] : 0u;
+}
+
+// dispatch, launch 2 of 2 (same grid): partition the tiles into the slabs, pad the slabs, raise the epoch flags
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
+  using W = Wire<KIND>;
+  using RT = RTile<W::MSG>;
+  constexpr int MSG = W::MSG, PER = RT::PER;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* s_in = smem;                                  // the tile as it arrived
+  uint8_t* s_out = smem + RT::BYTES + 16;                // the tile partitioned into runs
+  __shared__ Cnt8 s_w[kThreads / 32];
+  __shared__ uint32_t s_base[kMaxShards], s_total[kMaxShards], s_off[kMaxShards], s_len[kMaxShards];
+  __shared__ uint32_t s_last;
+  const uint32_t G = gridDim.x, b = blockIdx.x;
+  const uint32_t t0 = (uint32_t)((uint64_t)a.n_tiles * b / G), t1 = (uint32_t)((uint64_t)a.n_tiles * (b + 1) / G);
+
+  // ---- first slot of this CTA's records in every slab, and the slab totals (warp o handles shard o) ----
+  {
+    const uint32_t o = warp_id();
+    uint32_t before = 0, all = 0;
+    if (o < a.world)
+      for (uint32_t q = lane_id(); q < G; q += 32) {
+        const uint32_t v = __ldcg(&a.cta_tot[q * kMaxShards + o]);
+        all += v;
+        if (q < b) before += v;
+      }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, d);
+      all += __shfl_xor_sync(0xffffffffu, all, d);
+    }
+    if (lane_id() == 0) { s_base[o] = before; s_total[o] = all; }
+  }
+  __syncthreads();
+  if (b == 0 && threadIdx.x < a.world && s_total[threadIdx.x] > a.cap) atomicAdd(&a.flags[0], s_total[threadIdx.x] - a.cap);
+
+  // ---- padding: slots [total, cap) of every slab, shared out over the CTAs ----
+  for (uint32_t o = 0; o < a.world; o++) {
+    const uint32_t tot = s_total[o] < a.cap ? s_total[o] : a.cap;
+    const uint64_t len = (uint64_t)(a.cap - tot) * MSG;
+    const uint64_t lo = len * b / G, hi = len * (b + 1) / G;
+    if (hi > lo) coop_fill_pad((uint8_t*)a.slab.p[o] + (uint64_t)tot * MSG + lo, hi - lo);
+  }
+
+  // ---- phase 2: partition every tile in shared memory, one contiguous run per shard leaves ----
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t first = t * RT::RECS;
+    const uint32_t valid = (a.n - first < (uint32_t)RT::RECS ? a.n - first : (uint32_t)RT::RECS) * MSG;
+    {
+      const uint8_t* src = a.req + (size_t)t * RT::BYTES;
+      const uint32_t body = valid >> 4;
+      for (uint32_t i = threadIdx.x; i < body; i += kThreads) ((uint4*)s_in)[i] = __ldcg((const uint4*)src + i);
+      if (threadIdx.x < valid - (body << 4)) s_in[(body << 4) + threadIdx.x] = src[(body << 4) + threadIdx.x];
+    }
+    uint32_t own[PER];
+    const Cnt8 mine = load_owners<PER>(a, t, own);
+    Cnt8 excl, total;
+    block_scan_cnt8(mine, excl, total, s_w);              // (its barriers also publish s_in)
+    if (threadIdx.x == 0) {
+      uint32_t off = 0;
+      for (uint32_t o = 0; o < a.world; o++) {
+        const uint32_t cnt = cnt8_get(total, o), base = s_base[o];
+        const uint32_t room = base < a.cap ? a.cap - base : 0u;
+        const uint32_t take = cnt < room ? cnt : room;
+        const uint32_t daddr = (uint32_t)((a.slab.p[o] + (uint64_t)base * MSG) & 15u);
+        off += (daddr - off) & 15u;                      // the run starts at its destination's alignment
+        s_off[o] = off;
+        s_len[o] = take * MSG;
+        off += cnt * MSG;
+        a.tilebase[(size_t)t * kMaxShards + o] = base;
+      }
+    }
+    __syncthreads();
+    {
+      Cnt8 seen = excl;
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const uint32_t o = own[j];
+        if (o < a.world) {
+          const uint32_t r = cnt8_get(seen, o);
+          cnt8_inc(seen, o);
+          if (r * MSG < s_len[o]) copy_record<MSG>(s_out + s_off[o] + r * MSG, s_in + (threadIdx.x * PER + j) * MSG);
+        }
+      }
+    }
+    __syncthreads();
+    for (uint32_t o = 0; o < a.world; o++)
+      if (s_len[o]) coop_copy16((uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_out + s_off[o], s_len[o]);
+    __syncthreads();
+    if (threadIdx.x < a.world) s_base[threadIdx.x] += cnt8_get(total, threadIdx.x);
+    __syncthreads();
+  }
+
+  // ---- the last CTA to finish tells the peers that this source's slabs of epoch `epoch` are complete ----
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(a.done, 1u);
+    s_last = prev == G - 1;
+    if (s_last) *a.done = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < a.world && a.sig.p[threadIdx.x]) {
+    __threadfence_system();
+    uint32_t* flag = (uint32_t*)a.sig.p[threadIdx.x] + a.me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.epoch) : "memory");
+  }
+}
+
+// combine: the replies of tile t are one contiguous run per shard in the reply slabs; put them back in order
+template <int MSG>
+__global__ void __launch_bounds__(kThreads) k_route_combine(const RouteArgs a) {
+  using RT = RTile<MSG>;
+  constexpr int PER = RT::PER;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* s_out = smem;                                 // the tile in request order
+  uint8_t* s_in = smem + RT::BYTES + 16;                 // the runs as they sit in the slabs
+  __shared__ Cnt8 s_w[kThreads / 32];
+  __shared__ uint32_t s_off[kMaxShards], s_len[kMaxShards], s_base[kMaxShards];
+  for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    uint32_t own[PER];
+    const Cnt8 mine = load_owners<PER>(a, t, own);
+    Cnt8 excl, total;
+    block_scan_cnt8(mine, excl, total, s_w);
+    if (threadIdx.x == 0) {
+      uint32_t off = 0;
+      for (uint32_t o = 0; o < a.world; o++) {
+        const uint32_t cnt = cnt8_get(total, o), base = a.tilebase[(size_t)t * kMaxShards + o];
+        const uint32_t room = base < a.cap ? a.cap - base : 0u;
+        const uint32_t take = cnt < room ? cnt : room;
+        const uint32_t saddr = (uint32_t)((a.slab.p[o] + (uint64_t)base * MSG) & 15u);
+        off += (saddr - off) & 15u;
+        s_off[o] = off;
+        s_len[o] = take * MSG;
+        s_base[o] = base;
+        off += cnt * MSG;
+      }
+    }
+    __syncthreads();
+    for (uint32_t o = 0; o < a.world; o++)
+      if (s_len[o]) coop_copy16(s_in + s_off[o], (const uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_len[o]);
+    __syncthreads();
+    {
+      Cnt8 seen = excl;
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const uint32_t o = own[j];
+        uint8_t* dst = s_out + (threadIdx.x * PER + j) * MSG;
+        bool have = false;
+        if (o < a.world) {
+          const uint32_t r = cnt8_get(seen, o);
+          cnt8_inc(seen, o);
+          if (r * MSG < s_len[o]) { copy_record<MSG>(dst, s_in + s_off[o] + r * MSG); have = true; }
+        }
+        if (!have)                                       // undeliverable or dropped by a full slab: error reply
+          for (int q = 0; q < MSG; q++) dst[q] = 0xff;
+      }
+    }
+    __syncthreads();
+    {
+      const uint32_t first = t * RT::RECS;
+      const uint32_t valid = (a.n - first < (uint32_t)RT::RECS ? a.n - first : (uint32_t)RT::RECS) * MSG;
+      uint8_t* dst = a.out + (size_t)t * RT::BYTES;
+      const uint32_t body = valid >> 4;
+      for (uint32_t i = threadIdx.x; i < body; i += kThreads) ((uint4*)dst)[i] = ((const uint4*)s_out)[i];
+      if (threadIdx.x < valid - (body << 4)) dst[(body << 4) + threadIdx.x] = s_out[(body << 4) + threadIdx.x];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dint

@@ -49,7 +49,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_partition_slabs", "dint_route_unpermute", "dint_p2p_dispatch", "dint_p2p_wait", "dint_p2p_signal", "dint_p2p_combine", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_flags", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod",
@@ -78,12 +78,16 @@ def lib():
     L.dint_submit_device.restype = i32; L.dint_submit_device.argtypes = [vp, vp, u64, vp, vp]
     L.dint_route_owner.restype = i32; L.dint_route_owner.argtypes = [vp, vp, u64, vp, vp]
     L.dint_route_partition.restype = i32; L.dint_route_partition.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp]
-    L.dint_route_partition_slabs.restype = i32; L.dint_route_partition_slabs.argtypes = [vp, vp, vp, u64, u32, u32, vp, vp, vp, vp]
     pp = C.POINTER(DintPeerPtrs)
-    L.dint_p2p_dispatch.restype = i32; L.dint_p2p_dispatch.argtypes = [vp, vp, vp, u64, u32, u32, u32, pp, pp, u32, vp, vp, vp]
+    L.dint_route_tile_records.restype = u32; L.dint_route_tile_records.argtypes = [vp]
+    L.dint_route_dispatch.restype = i32; L.dint_route_dispatch.argtypes = [vp, vp, vp, u64, u32, u32, u32, pp, pp, u32, vp, vp, vp, vp]
+    L.dint_route_combine.restype = i32; L.dint_route_combine.argtypes = [vp, pp, vp, vp, u64, u32, u32, vp, vp]
     L.dint_p2p_wait.restype = i32; L.dint_p2p_wait.argtypes = [vp, vp, u32, u32, vp, vp]
     L.dint_p2p_signal.restype = i32; L.dint_p2p_signal.argtypes = [vp, pp, u32, u32, u32, vp]
-    L.dint_p2p_combine.restype = i32; L.dint_p2p_combine.argtypes = [vp, pp, vp, u32, u32, u32, vp, vp]
+    L.dint_shard_create.restype = i32; L.dint_shard_create.argtypes = [vp, u32, u32, u32, u32, pp, pp, pp, u64, C.POINTER(vp)]
+    L.dint_shard_destroy.restype = None; L.dint_shard_destroy.argtypes = [vp]
+    L.dint_shard_submit_many.restype = i32; L.dint_shard_submit_many.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), u64, C.POINTER(vp), vp]
+    L.dint_shard_flags.restype = i32; L.dint_shard_flags.argtypes = [vp, C.POINTER(u32)]
     L.dint_route_unpermute.restype = i32; L.dint_route_unpermute.argtypes = [vp, vp, vp, u64, vp, vp]
     L.dint_sync.restype = i32; L.dint_sync.argtypes = [vp]
     L.dint_kv_get.restype = i32; L.dint_kv_get.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]
@@ -256,21 +260,43 @@ class Engine:
             raise DintError(rc, "dint_route_partition")
         return out, perm, counts
 
-    def route_partition_slabs(self, req, owner, n_shards, cap, overflow):
-        """Fixed-capacity dispatch: returns (slabs uint8 [n_shards*cap*msg], perm int32 [n_shards*cap]); `overflow`
-        (int32 CUDA tensor of 1) is incremented on the device for every record that did not fit."""
+    def route_state(self, n, device):
+        """Buffers the dispatch fills for the combine: (owner uint8 [n], tilebase int32 [tiles * 8])."""
         import torch
-        n = owner.numel()
-        ns = n_shards & 0x7fffffff                        # bit 31 = DINT_ROUTE_COMPUTE_OWNER
-        slabs = torch.empty(ns * cap * self.msg, dtype=torch.uint8, device=req.device)
-        perm = torch.empty(ns * cap, dtype=torch.int32, device=req.device)
-        s = torch.cuda.current_stream(req.device).cuda_stream
-        rc = lib().dint_route_partition_slabs(self.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, n_shards, cap,
-                                              C.c_void_p(slabs.data_ptr()), C.c_void_p(perm.data_ptr()),
-                                              C.c_void_p(overflow.data_ptr()), C.c_void_p(s) if s else None)
+        tr = lib().dint_route_tile_records(self.h)
+        tiles = (n + tr - 1) // tr
+        return (torch.empty(max(n, 1), dtype=torch.uint8, device=device),
+                torch.empty(max(tiles, 1) * 8, dtype=torch.int32, device=device))
+
+    def route_dispatch(self, req, n, n_shards, rank, cap, slab_ptrs, flags, owner_in=None, sig_ptrs=None, epoch=0, state=None,
+                       stream=None):
+        """Fused stable partition of n records into per-shard slabs (see dint_route_dispatch).  slab_ptrs /
+        sig_ptrs: DintPeerPtrs; flags: int32 CUDA tensor (>= 2).  Returns the (owner, tilebase) state."""
+        import torch
+        if state is None:
+            state = self.route_state(n, req.device)
+        s = stream if stream is not None else torch.cuda.current_stream(req.device).cuda_stream
+        rc = lib().dint_route_dispatch(self.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner_in.data_ptr()) if owner_in is not None else None,
+                                       n, n_shards, rank, cap, C.byref(slab_ptrs), C.byref(sig_ptrs) if sig_ptrs is not None else None,
+                                       epoch, C.c_void_p(state[0].data_ptr()), C.c_void_p(state[1].data_ptr()),
+                                       C.c_void_p(flags.data_ptr()), C.c_void_p(s) if s else None)
         if rc != 0:
-            raise DintError(rc, "dint_route_partition_slabs")
-        return slabs, perm
+            raise DintError(rc, "dint_route_dispatch")
+        return state
+
+    def route_combine(self, reply_ptrs, state, n, n_shards, cap, out, stream=None):
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(out.device).cuda_stream
+        rc = lib().dint_route_combine(self.h, C.byref(reply_ptrs), C.c_void_p(state[0].data_ptr()), C.c_void_p(state[1].data_ptr()),
+                                      n, n_shards, cap, C.c_void_p(out.data_ptr()), C.c_void_p(s) if s else None)
+        if rc != 0:
+            raise DintError(rc, "dint_route_combine")
+        return out
+
+    @staticmethod
+    def slab_ptrs(base_ptr, n_shards, stride_bytes):
+        """DintPeerPtrs for slabs laid out back to back in one local buffer."""
+        return DintPeerPtrs.of([base_ptr + o * stride_bytes for o in range(n_shards)])
 
     def route_unpermute(self, sorted_resp, perm, out=None):
         import torch

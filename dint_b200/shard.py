@@ -90,7 +90,7 @@ class ShardedEngine:
             self.cfg.accts_sizing = cfg_over.get("accts_sizing", 24000000)
         self.use_slabs, self.strict = use_slabs, strict
         self.slab_slack = slab_slack if slab_slack is not None else (1.5 if by_dst else 1.02)
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device) if self.engine is not None else None
+        self.overflow = torch.zeros(2, dtype=torch.int32, device=self.device) if self.engine is not None else None
         self.use_p2p = False
         if use_p2p and self.engine is not None:
             self._init_p2p(p2p_max_n)
@@ -101,70 +101,65 @@ class ShardedEngine:
         cap = int(mean * self.slab_slack) + int(8 * (mean ** 0.5)) + 64
         return (cap + 15) // 16 * 16
 
-    def _init_p2p(self, max_n):
-        """Symmetric buffer per rank: inbox [world][cap] | outbox [world][cap] | signal words, mapped by all peers
-        (torch symmetric memory = CUDA IPC + peer access over NVLink)."""
+    def _init_p2p(self, max_n, n_sets=3):
+        """Symmetric buffer per rank: n_sets x {inbox [world][cap] | outbox [world][cap]} | signal block, mapped by
+        all peers (torch symmetric memory = CUDA IPC + peer access over NVLink); the step itself is driven by the
+        library (dint_shard_submit_many)."""
         import torch.distributed._symmetric_memory as symm_mem
         W = self.world
         self.p2p_max_n = max_n
-        region = (W * self._cap(max_n) * self.msg + 255) // 256 * 256
-        self.p2p_region = region
-        self.sym = symm_mem.empty(2 * region + 4096, dtype=torch.uint8, device=self.device)
+        cap = self._cap(max_n)
+        region = (W * cap * self.msg + 255) // 256 * 256
+        self.sym = symm_mem.empty(n_sets * 2 * region + 4096, dtype=torch.uint8, device=self.device)
         grp = self.group if self.group is not None else dist.group.WORLD
         self.sym_hdl = symm_mem.rendezvous(self.sym, group=grp.group_name)
         self.sym.zero_()
         torch.cuda.synchronize(self.device)
         self.sym_hdl.barrier()
-        ptrs = list(self.sym_hdl.buffer_ptrs)
-        self.p_inbox = DintPeerPtrs.of(ptrs)
-        self.p_outbox = DintPeerPtrs.of([p + region for p in ptrs])
-        self.p_sigreq = DintPeerPtrs.of([p + 2 * region for p in ptrs])
-        self.p_sigrsp = DintPeerPtrs.of([p + 2 * region + 256 for p in ptrs])
-        self.my_sigreq = self.sym.data_ptr() + 2 * region
-        self.my_sigrsp = self.sym.data_ptr() + 2 * region + 256
-        self.p2p_flags = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self.epoch = 0
+        ptrs = [int(p) for p in self.sym_hdl.buffer_ptrs]
+        inbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * 2 * region for p in ptrs]) for s in range(n_sets)])
+        outbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * 2 * region + region for p in ptrs]) for s in range(n_sets)])
+        sig = DintPeerPtrs.of([p + n_sets * 2 * region for p in ptrs])
+        ctx = C.c_void_p()
+        rc = lib().dint_shard_create(self.engine.h, W, self.rank, cap, n_sets, inbox, outbox, C.byref(sig), max_n, C.byref(ctx))
+        if rc != 0:
+            raise DintError(rc, "dint_shard_create")
+        self.p2p_ctx = ctx
         self.use_p2p = True
 
-    def _submit_gpu_p2p(self, req, n, dst):
-        """Dispatch = remote stores into the owners' inboxes, combine = remote loads from their outboxes; epoch
-        flags order the phases across GPUs.  No NCCL call, no host round trip.  Every rank must pass the same n."""
-        eng, W, L = self.engine, self.world, lib()
-        cap = self._cap(n)
-        self.epoch += 1
-        e = self.epoch
+    def _p2p_many(self, reqs, dsts=None):
+        """k equally sized batches through dint_shard_submit_many (same k and n on every rank)."""
+        k = len(reqs)
+        n = reqs[0].numel() // self.msg
+        assert all(r.numel() == n * self.msg and r.is_contiguous() for r in reqs) and 0 < n <= self.p2p_max_n
+        outs = [torch.empty(n * self.msg, dtype=torch.uint8, device=self.device) for _ in range(k)]
+        a_req = (C.c_void_p * k)(*[r.data_ptr() for r in reqs])
+        a_out = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
+        a_dst = None if dsts is None or dsts[0] is None else (C.c_void_p * k)(*[d.data_ptr() for d in dsts])
         s = torch.cuda.current_stream(self.device).cuda_stream
-        sp = C.c_void_p(s) if s else None
-        owner = dst if dst is not None else torch.empty(n, dtype=torch.uint8, device=self.device)
-        wflag = W if dst is not None else (W | 0x80000000)
-        perm = torch.empty(W * cap, dtype=torch.int32, device=self.device)
-        fl = C.c_void_p(self.p2p_flags.data_ptr())
-        rc = L.dint_p2p_dispatch(eng.h, C.c_void_p(req.data_ptr()), C.c_void_p(owner.data_ptr()), n, wflag, self.rank, cap,
-                                 C.byref(self.p_inbox), C.byref(self.p_sigreq), e, C.c_void_p(perm.data_ptr()), fl, sp)
-        if rc == 0:
-            rc = L.dint_p2p_wait(eng.h, C.c_void_p(self.my_sigreq), W, e, fl, sp)
+        rc = lib().dint_shard_submit_many(self.p2p_ctx, k, a_req, a_dst, n, a_out, C.c_void_p(s) if s else None)
         if rc != 0:
-            raise DintError(rc, "dint_p2p_dispatch/wait")
-        nb = W * cap * self.msg
-        eng.submit_tensor(self.sym[:nb], self.sym[self.p2p_region:self.p2p_region + nb])
-        rc = L.dint_p2p_signal(eng.h, C.byref(self.p_sigrsp), W, self.rank, e, sp)
-        if rc == 0:
-            rc = L.dint_p2p_wait(eng.h, C.c_void_p(self.my_sigrsp), W, e, fl, sp)
-        out = torch.empty(n * self.msg, dtype=torch.uint8, device=self.device)
-        if rc == 0:
-            rc = L.dint_p2p_combine(eng.h, C.byref(self.p_outbox), C.c_void_p(perm.data_ptr()), W, self.rank, cap,
-                                    C.c_void_p(out.data_ptr()), sp)
-        if rc != 0:
-            raise DintError(rc, "dint_p2p_signal/wait/combine")
-        return out
+            raise DintError(rc, "dint_shard_submit_many")
+        return outs
+
+    def _submit_gpu_p2p(self, req, n, dst):
+        """Dispatch = ONE kernel that partitions the batch and stores every run straight into the owners' inboxes
+        (then raises their epoch flags); combine = ONE kernel that loads the replies from their outboxes.  No
+        NCCL call, no host round trip.  Every rank must pass the same n."""
+        return self._p2p_many([req], [dst])[0]
 
     def check_p2p(self):
         """(overflowed records, timed-out waits) since the last check; both must be 0 for the results to stand."""
-        v = self.p2p_flags.tolist()
-        self.p2p_flags.zero_()
-        return v[0], v[1]
+        v = (C.c_uint32 * 2)()
+        rc = lib().dint_shard_flags(self.p2p_ctx, v)
+        if rc != 0:
+            raise DintError(rc, "dint_shard_flags")
+        return int(v[0]), int(v[1])
 
     def close(self):
+        if self.use_p2p:
+            lib().dint_shard_destroy(self.p2p_ctx)
+            self.use_p2p = False
         if self.engine is not None:
             self.engine.close()
             self.engine = None
@@ -198,21 +193,22 @@ class ShardedEngine:
         out.index_copy_(0, order, back)
         return out.view(-1)
 
+    def _dispatch_local(self, req, n, dst):
+        """Partition into a local send buffer of `world` slabs; returns (slabs, state, cap)."""
+        eng, W = self.engine, self.world
+        cap = self._cap(n)
+        slabs = torch.empty(W * cap * self.msg, dtype=torch.uint8, device=req.device)
+        ptrs = Engine.slab_ptrs(slabs.data_ptr(), W, cap * self.msg)
+        state = eng.route_dispatch(req, n, W, self.rank, cap, ptrs, self.overflow, owner_in=dst)
+        return slabs, state, cap
+
     def _submit_gpu_slabs(self, req, n, dst):
         """Fixed-capacity exchange: every rank sends every peer one slab of `cap` records (real ones first, the
         rest padding), so the all-to-all needs no split sizes from the device -- no host round trip inside the
         step.  The local engine runs ONE batch of world * cap records in source-rank order; padding records are
         answered unchanged.  A slab overflow (counted on the device) means the result must be discarded."""
-        eng = self.engine
-        W = self.world
-        mean = (n + W - 1) // W
-        cap = int(mean * self.slab_slack) + int(8 * (mean ** 0.5)) + 64
-        cap = (cap + 15) // 16 * 16
-        if dst is not None:
-            slabs, perm = eng.route_partition_slabs(req, dst, W, cap, self.overflow)
-        else:                                              # owners computed inside the first dispatch pass
-            scratch = torch.empty(n, dtype=torch.uint8, device=req.device)
-            slabs, perm = eng.route_partition_slabs(req, scratch, W | 0x80000000, cap, self.overflow)
+        eng, W = self.engine, self.world
+        slabs, state, cap = self._dispatch_local(req, n, dst)
         recv = torch.empty_like(slabs)
         dist.all_to_all_single(recv, slabs, group=self.group)
         out_local = torch.empty_like(recv)
@@ -220,7 +216,7 @@ class ShardedEngine:
         back = torch.empty_like(slabs)
         dist.all_to_all_single(back, out_local, group=self.group)
         out = torch.empty(n * self.msg, dtype=torch.uint8, device=req.device)
-        return eng.route_unpermute(back, perm, out)
+        return eng.route_combine(Engine.slab_ptrs(back.data_ptr(), W, cap * self.msg), state, n, W, cap, out)
 
     def submit_many(self, reqs):
         """A sequence of collective batches (each rank passes equally many, equally sized tensors), software
@@ -228,6 +224,8 @@ class ShardedEngine:
         local engine and its replies travel back on the main stream.  The engine still sees the batches in
         order, so the result equals calling submit_tensor() on each batch in turn."""
         eng, W = self.engine, self.world
+        if self.use_p2p and reqs[0].numel() // self.msg <= self.p2p_max_n:
+            return self._p2p_many(reqs)
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_side"):
             self._side = torch.cuda.Stream(self.device)
@@ -239,14 +237,13 @@ class ShardedEngine:
             n = req.numel() // self.msg
             cap = self._cap(n)
             with torch.cuda.stream(side):
-                scratch = torch.empty(n, dtype=torch.uint8, device=req.device)
-                slabs, perm = eng.route_partition_slabs(req, scratch, W | 0x80000000, cap, self.overflow)
+                slabs, state, _ = self._dispatch_local(req, n, None)
                 recv = torch.empty_like(slabs)
                 dist.all_to_all_single(recv, slabs, group=self.group)
                 ev = torch.cuda.Event()
                 ev.record(side)
-            keep.extend([scratch, slabs, perm, recv])
-            return recv, perm, ev, n
+            keep.extend([slabs, state, recv])
+            return recv, (state, cap), ev, n
 
         if not hasattr(self, "_ret"):
             self._ret = torch.cuda.Stream(self.device)
@@ -268,7 +265,8 @@ class ShardedEngine:
                 back = torch.empty_like(recv)
                 dist.all_to_all_single(back, out_local, group=self.group)
                 out = torch.empty(n * self.msg, dtype=torch.uint8, device=self.device)
-                outs.append(eng.route_unpermute(back, perm, out))
+                state, cap = perm
+                outs.append(eng.route_combine(Engine.slab_ptrs(back.data_ptr(), W, cap * self.msg), state, n, W, cap, out))
             keep.extend([out_local, back])
         main.wait_stream(ret)
         main.wait_stream(side)
@@ -277,7 +275,7 @@ class ShardedEngine:
 
     def check_overflow(self):
         """True if any fixed-capacity exchange since the last check dropped a record (results invalid)."""
-        v = int(self.overflow.item())
+        v = int(self.overflow[0].item())
         self.overflow.zero_()
         return v != 0
 

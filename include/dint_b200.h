@@ -141,36 +141,57 @@ int dint_route_owner(dint_engine *e, const void *req_dev, uint64_t n, uint8_t *o
  * All pointers are device pointers; asynchronous on cuda_stream. */
 int dint_route_partition(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
                          void *sorted_dev, uint32_t *perm_dev, uint32_t *counts_dev, void *cuda_stream);
-/* Fixed-capacity dispatch (no host round trip for the split sizes): records of shard o go to slab o of `cap`
- * records inside slabs_dev (n_shards * cap records, pre-filled with padding by this call: every byte 0xFE --
- * a padding record is answered unchanged and touches nothing); perm_dev (n_shards * cap entries) maps slab
- * positions to original indices (0xffffffff = padding); *overflow_dev is incremented for every record that
- * did not fit (the caller must then repeat the batch through dint_route_partition).
- * For dint_route_partition_slabs and dint_p2p_dispatch: OR-ing DINT_ROUTE_COMPUTE_OWNER into n_shards makes the call
- * compute the owners itself (as dint_route_owner would) into owner_dev, which is then a scratch buffer of n bytes. */
-#define DINT_ROUTE_COMPUTE_OWNER 0x80000000u
-int dint_route_partition_slabs(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards,
-                               uint32_t cap, void *slabs_dev, uint32_t *perm_dev, uint32_t *overflow_dev, void *cuda_stream);
-/* Fused dispatch / combine over NVLink peer memory (one process per GPU; the buffers are each rank's
- * symmetric-memory regions mapped into this process).  inbox_ptrs[o] / outbox_ptrs[o] / sig_ptrs[o]: device
- * pointers to rank o's inbox [n_shards][cap] records, outbox (same shape) and signal words [n_shards] u32.
- *   dint_p2p_dispatch: partitions n records by owner and STORES them into the owners' inboxes (slab `rank`),
- *     pads the slabs, then release-signals epoch to every peer's sig[rank].
- *   dint_p2p_wait:    blocks the stream until local_sig[0..n_shards) have all reached epoch (acquire).
- *   dint_p2p_signal:  release-signals epoch to every peer's sig[rank] (replies ready in my outbox).
- *   dint_p2p_combine: LOADS this rank's replies from the owners' outboxes into out_dev at their original
- *     indices (perm_dev from dint_p2p_dispatch).
- * *flags_dev (2 x u32): [0] += records that did not fit a slab, [1] = 1 if a wait timed out. */
+/* Fixed-capacity dispatch / combine (no host round trip for the split sizes), local or over NVLink peer memory.
+ * Every source rank sends every shard o one SLAB of `cap` records: its records for o first, in request order,
+ * then padding records (every byte 0xFE: a padding record is answered unchanged and touches nothing).
+ *   dint_route_dispatch: ONE cooperative kernel.  owner_in_dev = client-chosen shard per record (tatp / smallbank
+ *     placement) or NULL = computed as dint_route_owner would (needs n_shards == cfg.n_shards).  slab_ptrs->p[o] =
+ *     device address of THIS source's slab for shard o: inside a local send buffer (then exchange the slabs with
+ *     an all-to-all) or inside rank o's receive buffer mapped over NVLink (then no collective is needed: with
+ *     sig_ptrs != NULL the kernel's last CTA release-stores `epoch` to word `rank` of sig_ptrs->p[o] for every o).
+ *     Outputs for the combine: owner_dev[n] (one byte per record, 0xFF = undeliverable) and tilebase_dev
+ *     [ceil(n / dint_route_tile_records())][8].  flags_dev[0] += records that did not fit their slab.
+ *   dint_route_combine: reply_slab_ptrs->p[o] = where shard o's replies to THIS source's slab are (local receive
+ *     buffer or rank o's reply buffer over NVLink); out_dev[i] = reply to request i (0xFF bytes if undelivered).
+ * The reference does this routing in its clients (e.g. `key % kNumServers` before sendto,
+ * tatp/caladan/client_ebpf_shard.cc); with this call any rank may receive any request. */
 typedef struct dint_peer_ptrs { uint64_t p[8]; } dint_peer_ptrs;
-int dint_p2p_dispatch(dint_engine *e, const void *req_dev, const uint8_t *owner_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
-                      uint32_t cap, const dint_peer_ptrs *inbox_ptrs, const dint_peer_ptrs *sig_ptrs, uint32_t epoch,
-                      uint32_t *perm_dev, uint32_t *flags_dev, void *cuda_stream);
+uint32_t dint_route_tile_records(dint_engine *e);
+int dint_route_dispatch(dint_engine *e, const void *req_dev, const uint8_t *owner_in_dev, uint64_t n, uint32_t n_shards,
+                        uint32_t rank, uint32_t cap, const dint_peer_ptrs *slab_ptrs, const dint_peer_ptrs *sig_ptrs,
+                        uint32_t epoch, uint8_t *owner_dev, uint32_t *tilebase_dev, uint32_t *flags_dev, void *cuda_stream);
+int dint_route_combine(dint_engine *e, const dint_peer_ptrs *reply_slab_ptrs, const uint8_t *owner_dev,
+                       const uint32_t *tilebase_dev, uint64_t n, uint32_t n_shards, uint32_t cap, void *out_dev,
+                       void *cuda_stream);
+/* Epoch flags for the exchange over peer memory (one process per GPU; the buffers are each rank's
+ * symmetric-memory regions mapped into this process; sig_ptrs->p[o] = rank o's signal words [n_shards] u32):
+ *   dint_p2p_wait:    blocks the stream until local_sig[0..n_shards) have all reached epoch (acquire).
+ *   dint_p2p_signal:  release-signals epoch to every peer's sig[rank] (e.g. replies ready in my reply buffer).
+ * flags_dev[1] = 1 if a wait timed out. */
 int dint_p2p_wait(dint_engine *e, const uint32_t *local_sig_dev, uint32_t n_shards, uint32_t epoch, uint32_t *flags_dev,
                   void *cuda_stream);
 int dint_p2p_signal(dint_engine *e, const dint_peer_ptrs *sig_ptrs, uint32_t n_shards, uint32_t rank, uint32_t epoch,
                     void *cuda_stream);
-int dint_p2p_combine(dint_engine *e, const dint_peer_ptrs *outbox_ptrs, const uint32_t *perm_dev, uint32_t n_shards, uint32_t rank,
-                     uint32_t cap, void *out_dev, void *cuda_stream);
+/* The whole sharded step over NVLink peer memory, driven from ONE host call per sequence of batches (what
+ * dint_b200/shard.py uses at N > 1).  Every rank owns n_sets (2..4) buffer sets {inbox, outbox}, each
+ * n_shards * cap records, plus one 256-byte signal block (three arrays of 8 epoch words: requests written /
+ * replies written / replies read), all in memory its peers map (CUDA IPC / torch symmetric memory), zeroed once.
+ *   inbox_sets[s].p[o], outbox_sets[s].p[o]: device address of rank o's set s; sig_blocks->p[o]: rank o's block.
+ * dint_shard_submit_many: k batches of n (<= max_n) records each, the same k and n on every rank; batch j+1 is
+ * partitioned into the owners' inboxes (dint_route_dispatch) while batch j runs through the local engine on
+ * cuda_stream and the replies of batch j-1 are pulled from the owners' outboxes (dint_route_combine); out_dev[j]
+ * is complete when cuda_stream reaches the end of the call.  The engine sees the batches in order, so the
+ * result equals k sequential collective steps.  dst_dev: NULL, or per batch the client-chosen shard of every
+ * record.  dint_shard_flags (synchronises): [0] records that overflowed a slab, [1] timed-out waits, since the
+ * last call; both must be 0 for the replies to stand. */
+typedef struct dint_shard_ctx dint_shard_ctx;
+int dint_shard_create(dint_engine *e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets,
+                      const dint_peer_ptrs *inbox_sets, const dint_peer_ptrs *outbox_sets, const dint_peer_ptrs *sig_blocks,
+                      uint64_t max_n, dint_shard_ctx **out);
+void dint_shard_destroy(dint_shard_ctx *c);
+int dint_shard_submit_many(dint_shard_ctx *c, uint32_t k, const void *const *req_dev, const uint8_t *const *dst_dev, uint64_t n,
+                           void *const *out_dev, void *cuda_stream);
+int dint_shard_flags(dint_shard_ctx *c, uint32_t out[2]);
 int dint_route_unpermute(dint_engine *e, const void *sorted_dev, const uint32_t *perm_dev, uint64_t n, void *out_dev,
                          void *cuda_stream);
 int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */

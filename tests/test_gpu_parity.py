@@ -246,6 +246,92 @@ def test_engine_reproduces_reference_golden(name):
 
 
 # ---------------------------------------------------------------- multi-GPU dispatch kernels (1 GPU) -----
+def _route_case(kind, n, seed=3):
+    cfg = {}
+    if kind == wire.FASST:
+        req = T.fasst_random(n, 10**6, seed=seed)
+    elif kind == wire.LOCK2PL:
+        req = T.lock2pl_random(n, 10**5, seed=seed)
+    elif kind == wire.LOG:
+        req = T.log_random(n, seed=seed)
+    elif kind == wire.STORE:
+        req = T.store_random(n, 500, seed=seed)
+        cfg = dict(subs_populate=500)
+    elif kind == wire.SMALLBANK:
+        req = T.smallbank_random(n, 300, seed=seed)
+        cfg = dict(accts_populate=300)
+    else:
+        req = T.tatp_random(n, 20, seed=seed)
+        cfg = dict(subs_populate=20)
+    return np.ascontiguousarray(req).view(np.uint8).reshape(-1), cfg
+
+
+@pytest.mark.parametrize("kind,world,n,by_dst", [
+    (wire.FASST, 2, 70001, False), (wire.FASST, 8, (1 << 20) + 13, False), (wire.FASST, 1, 5000, False),
+    (wire.LOCK2PL, 3, 4097, False), (wire.LOG, 2, 1000, False), (wire.STORE, 4, 70001, False),
+    (wire.TATP, 3, 30011, True), (wire.TATP, 5, 30011, False), (wire.SMALLBANK, 6, 12345, True), (wire.FASST, 4, 1, False),
+])
+def test_route_dispatch_combine(kind, world, n, by_dst):
+    """k_route_dispatch / k_route_combine against numpy: slab o = the records owned by shard o in request order,
+    then padding; the combine of the slabs themselves is the identity; a client-chosen shard >= world is
+    undeliverable (0xFF reply)."""
+    import torch
+    from dint_b200.shard import owners_cpu
+    req, cfg = _route_case(kind, n)
+    msg = wire.MSG_SIZE[kind]
+    rank = world - 1
+    rng = np.random.default_rng(5)
+    with Engine(kind, n_shards=1 if by_dst else world, shard_id=0 if by_dst else rank, **cfg) as eng:
+        d = torch.from_numpy(req).cuda()
+        if by_dst:
+            want_owner = rng.integers(0, world, n).astype(np.uint8)
+            want_owner[rng.integers(0, n, 7)] = 200                      # shards that do not exist
+            owner_in = torch.from_numpy(want_owner).cuda()
+        else:
+            want_owner = owners_cpu(kind, eng.cfg, world, rank, req)
+            owner_in = None
+        counts = np.bincount(want_owner[want_owner < world], minlength=world)[:world]
+        cap = (int(counts.max()) + 16 + 15) // 16 * 16
+        slabs = torch.zeros(world * cap * msg, dtype=torch.uint8, device="cuda")
+        flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+        ptrs = Engine.slab_ptrs(slabs.data_ptr(), world, cap * msg)
+        state = eng.route_dispatch(d, n, world, rank, cap, ptrs, flags, owner_in=owner_in)
+        got = slabs.cpu().numpy().reshape(world, cap, msg)
+        rec = req.reshape(n, msg)
+        own = state[0].cpu().numpy()[:n]
+        assert np.array_equal(own, np.where(want_owner < world, want_owner, 255))
+        for o in range(world):
+            assert np.array_equal(got[o, :counts[o]], rec[want_owner == o]), o
+            assert (got[o, counts[o]:] == 0xFE).all(), o
+        assert flags.cpu().tolist() == [0, 0]
+        out = torch.empty(n * msg, dtype=torch.uint8, device="cuda")
+        eng.route_combine(ptrs, state, n, world, cap, out)
+        back = out.cpu().numpy().reshape(n, msg)
+        ok = want_owner < world
+        assert np.array_equal(back[ok], rec[ok])
+        assert (back[~ok] == 0xFF).all()
+
+
+def test_route_dispatch_overflow_is_counted():
+    import torch
+    n, world = 50000, 2
+    req, cfg = _route_case(wire.FASST, n)
+    with Engine(wire.FASST, n_shards=world, shard_id=0) as eng:
+        d = torch.from_numpy(req).cuda()
+        cap = 16000                                                      # < n / 2
+        slabs = torch.zeros(world * cap * 9, dtype=torch.uint8, device="cuda")
+        flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+        ptrs = Engine.slab_ptrs(slabs.data_ptr(), world, cap * 9)
+        state = eng.route_dispatch(d, n, world, 0, cap, ptrs, flags)
+        own = state[0].cpu().numpy()[:n]
+        counts = np.bincount(own, minlength=world)[:world]
+        assert flags.cpu().tolist()[0] == int(np.maximum(counts - cap, 0).sum()) > 0
+        rec = req.reshape(n, 9)
+        got = slabs.cpu().numpy().reshape(world, cap, 9)
+        for o in range(world):
+            assert np.array_equal(got[o], rec[own == o][:cap])
+
+
 @pytest.mark.parametrize("kind,world", [(wire.FASST, 2), (wire.FASST, 8), (wire.STORE, 3), (wire.TATP, 5)])
 def test_route_owner_partition_unpermute(kind, world):
     """k_route_owner / k_route_count+scan+scatter / k_route_unpermute against numpy: owner = the slot one

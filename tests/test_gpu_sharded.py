@@ -50,7 +50,20 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
         want2 = seq.process(np.concatenate([mk(r + 50) for r in range(world)]))
         msg = wire.MSG_SIZE[kind]
         lo, hi = rank * n_per_rank * msg, (rank + 1) * n_per_rank * msg
-        ret[rank] = bool(np.array_equal(got1, want1[lo:hi]) and np.array_equal(got2, want2[lo:hi]))
+        ok = bool(np.array_equal(got1, want1[lo:hi]) and np.array_equal(got2, want2[lo:hi]))
+        # a pipelined sequence of batches (dispatch of k+1 | engine of k | combine of k-1) = the same batches in turn
+        K = 7
+        dev = [torch.from_numpy(np.ascontiguousarray(mk(rank + 100 + 10 * i)).view(np.uint8).reshape(-1)).cuda() for i in range(K)]
+        outs = se.submit_many(dev)
+        torch.cuda.synchronize()
+        for i in range(K):
+            want = seq.process(np.concatenate([mk(r + 100 + 10 * i) for r in range(world)]))
+            ok = ok and bool(np.array_equal(outs[i].cpu().numpy(), want[lo:hi]))
+        if mode == 'p2p':
+            ok = ok and se.check_p2p() == (0, 0)
+        else:
+            ok = ok and not se.check_overflow()
+        ret[rank] = ok
         se.close()
     finally:
         dist.destroy_process_group()

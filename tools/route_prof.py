@@ -25,15 +25,16 @@ def ev():
 acc = {}
 for it in range(25):
     t = [ev()]
-    owner = eng.route_owner(req); t.append(ev())
-    slabs, perm = eng.route_partition_slabs(req, owner, W, cap, se.overflow); t.append(ev())
+    t.append(ev())
+    slabs, state, cap = se._dispatch_local(req, n, None); t.append(ev())
     recv = torch.empty_like(slabs); dist.all_to_all_single(recv, slabs); t.append(ev())
     out_local = torch.empty_like(recv); eng.submit_tensor(recv, out_local); t.append(ev())
     back = torch.empty_like(slabs); dist.all_to_all_single(back, out_local); t.append(ev())
-    out = torch.empty(n * 9, dtype=torch.uint8, device="cuda"); eng.route_unpermute(back, perm, out); t.append(ev())
+    out = torch.empty(n * 9, dtype=torch.uint8, device="cuda")
+    eng.route_combine(eng.slab_ptrs(back.data_ptr(), W, cap * 9), state, n, W, cap, out); t.append(ev())
     torch.cuda.synchronize()
     if it >= 5:
-        for name, a, b in zip(["owner", "partition", "a2a_out", "engine", "a2a_back", "unpermute"], t[:-1], t[1:]):
+        for name, a, b in zip(["-", "dispatch", "a2a_out", "engine", "a2a_back", "combine"], t[:-1], t[1:]):
             acc[name] = acc.get(name, 0.0) + a.elapsed_time(b)
         acc["total"] = acc.get("total", 0.0) + t[0].elapsed_time(t[-1])
 # whole calls back to back (no per-phase events, no sync in between)
