@@ -399,7 +399,8 @@ def main():
                    "requests_per_step": STEP_REQS * world, "chunk": args.chunk,
                    "cache": "every step replays a different 37.7 MB trace segment (inputs larger than reuse distance; "
                             "lock/version tables 148.5 MB > 126 MB L2)",
-                   "parallelism": f"key-space sharded x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"key-space sharded x{world}, exchange={res.get('exchange', 'slabs')} "
+                                   "(dispatch/combine kernels over NVLink peer memory)") if world > 1 else "single GPU"},
         "requests_per_s": reqs / (ms * 1e-3),
         "replies_bit_exact_vs_closed_loop_recording": bool(res["parity_last_step"]),
         "abort_stats": {k: res["wl_stats"][k] for k in ("committed", "validation_aborts", "lock_rejects")},
@@ -415,7 +416,8 @@ def main():
         line["e2e"] = {"value": committed / e2e_s, "unit": "txn/s", "h2d_bytes_per_step": STEP_REQS * 9 * world,
                        "d2h_bytes_per_step": STEP_REQS * 9 * world, "requests_per_s": reqs / e2e_s,
                        "replies_bit_exact": bool(res.get("e2e_parity", False)),
-                       "path": "dint_submit(): pinned host wire structs -> H2D -> kernels -> D2H, per step"}
+                       "path": ("dint_submit(): pinned host wire structs -> H2D -> kernels -> D2H, per step" if world == 1 else
+                                "pinned host wire structs -> H2D -> dint_shard_submit_many (dispatch, engine, combine) -> D2H, per step")}
     if "cpu_baseline" in res:
         line["cpu_baseline"] = res["cpu_baseline"]
     if not args.no_extra and world == 1:

@@ -34,7 +34,8 @@ struct RouteArgs {
   const uint8_t* owner_in;   // dispatch: client-chosen shard per record, or nullptr = computed from the keys
   uint8_t* owner;            // [n] owner byte per record (dispatch writes, combine reads); 0xff = undeliverable
   uint32_t* tilebase;        // [n_tiles][kMaxShards] first slot of each tile's run in each slab
-  uint32_t* cta_tot;         // dispatch scratch [grid][kMaxShards]
+  uint32_t* cta_tot;         // dispatch scratch [grid][kMaxShards]: per-CTA per-shard counts
+  uint32_t* grp_tot;         // dispatch scratch [grid / 32 + 1][kMaxShards]: the same per 32 CTAs; zero between launches
   uint32_t* done;            // dispatch scratch, zero between launches
   uint32_t* flags;           // [0] += records that did not fit their slab
   uint8_t* out;              // combine: [n * MSG] replies in request order, 16-byte aligned
@@ -84,6 +85,19 @@ DINT_D void coop_copy16(uint8_t* dst, const uint8_t* src, uint32_t nbytes) {
   for (uint32_t i = threadIdx.x; i < body; i += kThreads) d4[i] = s4[i];
   const uint32_t done = head + (body << 4);
   if (threadIdx.x < nbytes - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+// The same by ONE warp.
+DINT_D void warp_copy16(uint8_t* dst, const uint8_t* src, uint32_t nbytes) {
+  const uint32_t lane = lane_id();
+  uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  if (head > nbytes) head = nbytes;
+  if (lane < head) dst[lane] = src[lane];
+  const uint32_t body = (nbytes - head) >> 4;
+  const uint4* s4 = (const uint4*)(src + head);
+  uint4* d4 = (uint4*)(dst + head);
+  for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
+  const uint32_t done = head + (body << 4);
+  if (lane < nbytes - done) dst[done + lane] = src[done + lane];
 }
 // All threads of the CTA: fill nbytes at any alignment with the padding byte.
 DINT_D void coop_fill_pad(uint8_t* dst, uint64_t nbytes) {
@@ -157,6 +171,8 @@ __global__ void __launch_bounds__(kThreads) k_route_count(const Ctx c, const Rou
   }
   __syncthreads();
   if (threadIdx.x < kMaxShards) a.cta_tot[b * kMaxShards + threadIdx.x] = threadIdx.x < a.world ? s_cnt[threadIdx.x] : 0u;
+  // group totals (32 consecutive CTAs) keep the scatter kernel's prefix short: G/32 + 32 loads instead of G
+  if (threadIdx.x < a.world && s_cnt[threadIdx.x]) atomicAdd(&a.grp_tot[(b / 32) * kMaxShards + threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // dispatch, launch 2 of 2 (same grid): partition the tiles into the slabs, pad the slabs, raise the epoch flags
@@ -176,14 +192,17 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
 
   // ---- first slot of this CTA's records in every slab, and the slab totals (warp o handles shard o) ----
   {
-    const uint32_t o = warp_id();
+    const uint32_t o = warp_id(), ng = (G + 31) / 32, myg = b / 32;
     uint32_t before = 0, all = 0;
-    if (o < a.world)
-      for (uint32_t q = lane_id(); q < G; q += 32) {
-        const uint32_t v = __ldcg(&a.cta_tot[q * kMaxShards + o]);
+    if (o < a.world) {
+      for (uint32_t g = lane_id(); g < ng; g += 32) {
+        const uint32_t v = __ldcg(&a.grp_tot[g * kMaxShards + o]);
         all += v;
-        if (q < b) before += v;
+        if (g < myg) before += v;
       }
+      const uint32_t q = myg * 32 + lane_id();
+      if (q < b) before += __ldcg(&a.cta_tot[q * kMaxShards + o]);
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
       before += __shfl_xor_sync(0xffffffffu, before, d);
@@ -244,8 +263,13 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
       }
     }
     __syncthreads();
-    for (uint32_t o = 0; o < a.world; o++)
-      if (s_len[o]) coop_copy16((uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_out + s_off[o], s_len[o]);
+    if (a.world <= 2) {
+      for (uint32_t o = 0; o < a.world; o++)
+        if (s_len[o]) coop_copy16((uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_out + s_off[o], s_len[o]);
+    } else {                                             // one warp per run: the runs leave side by side
+      for (uint32_t o = warp_id(); o < a.world; o += kThreads / 32)
+        if (s_len[o]) warp_copy16((uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_out + s_off[o], s_len[o]);
+    }
     __syncthreads();
     if (threadIdx.x < a.world) s_base[threadIdx.x] += cnt8_get(total, threadIdx.x);
     __syncthreads();
@@ -260,6 +284,8 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
     if (s_last) *a.done = 0;
   }
   __syncthreads();
+  if (s_last)
+    for (uint32_t i = threadIdx.x; i < ((G + 31) / 32) * kMaxShards; i += kThreads) a.grp_tot[i] = 0;   // for the next launch
   if (s_last && threadIdx.x < a.world && a.sig.p[threadIdx.x]) {
     __threadfence_system();
     uint32_t* flag = (uint32_t*)a.sig.p[threadIdx.x] + a.me;
@@ -281,24 +307,29 @@ __global__ void __launch_bounds__(kThreads) k_route_combine(const RouteArgs a) {
     uint32_t own[PER];
     const Cnt8 mine = load_owners<PER>(a, t, own);
     Cnt8 excl, total;
+    if (threadIdx.x < kMaxShards) s_base[threadIdx.x] = a.tilebase[(size_t)t * kMaxShards + threadIdx.x];   // one latency, not eight
     block_scan_cnt8(mine, excl, total, s_w);
     if (threadIdx.x == 0) {
       uint32_t off = 0;
       for (uint32_t o = 0; o < a.world; o++) {
-        const uint32_t cnt = cnt8_get(total, o), base = a.tilebase[(size_t)t * kMaxShards + o];
+        const uint32_t cnt = cnt8_get(total, o), base = s_base[o];
         const uint32_t room = base < a.cap ? a.cap - base : 0u;
         const uint32_t take = cnt < room ? cnt : room;
         const uint32_t saddr = (uint32_t)((a.slab.p[o] + (uint64_t)base * MSG) & 15u);
         off += (saddr - off) & 15u;
         s_off[o] = off;
         s_len[o] = take * MSG;
-        s_base[o] = base;
         off += cnt * MSG;
       }
     }
     __syncthreads();
-    for (uint32_t o = 0; o < a.world; o++)
-      if (s_len[o]) coop_copy16(s_in + s_off[o], (const uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_len[o]);
+    if (a.world <= 2) {
+      for (uint32_t o = 0; o < a.world; o++)
+        if (s_len[o]) coop_copy16(s_in + s_off[o], (const uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_len[o]);
+    } else {
+      for (uint32_t o = warp_id(); o < a.world; o += kThreads / 32)
+        if (s_len[o]) warp_copy16(s_in + s_off[o], (const uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_len[o]);
+    }
     __syncthreads();
     {
       Cnt8 seen = excl;

@@ -17,6 +17,7 @@ so each shard sees its requests in global order.  The result equals ONE sequenti
 the concatenation of all ranks' slices.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -337,7 +338,11 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
     n_steps = steps + warmup
     msg = 9
     big = args.chunk + args.chunk // 2                   # one round + slab padding fits one engine chunk
-    se = ShardedEngine(wire.FASST, chunk=big, use_slabs=True, strict=False)
+    # exchange: "p2p" = dispatch/combine kernels storing to / loading from peer memory over NVLink, driven by
+    # dint_shard_submit_many; "slabs" = the same kernels on local buffers + NCCL all-to-all
+    mode = os.environ.get("DINT_SHARD_MODE", "p2p")
+    mk = lambda: ShardedEngine(wire.FASST, chunk=big, use_slabs=True, strict=False, use_p2p=(mode == "p2p"), p2p_max_n=B.CLIENTS)
+    se = mk()
     wl = Workload(wire.FASST, n_clients=B.CLIENTS, seed=20230 + rank, **fam)
     reqs = np.empty((n_steps, B.STEP_REQS * msg), dtype=np.uint8)
     resps = np.empty_like(reqs)
@@ -354,7 +359,7 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
     wl_stats = wl.stats()
     se.close()
     # timed replay from fresh shards
-    se = ShardedEngine(wire.FASST, chunk=big, use_slabs=True, strict=False)
+    se = mk()
     d_req = torch.from_numpy(reqs).to(dev)
     last = None
     rb = B.CLIENTS * msg                                 # one collective call per client round, as recorded
@@ -383,6 +388,8 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
     clocks = sampler.stop()
     se.engine.profile(False)
     ok = bool((last.cpu().numpy() == resps[n_steps - 1]).all()) and not se.check_overflow()
+    if se.use_p2p:
+        ok = ok and se.check_p2p() == (0, 0)
     out = dict(ms=ms, kernel_times=se.engine.kernel_times(), stats=se.engine.stats(), clocks=clocks, parity_last_step=ok,
                committed=sum(committed[warmup:]), requests=steps * B.STEP_REQS, wl_stats=wl_stats)
     types = np.concatenate([resps[s].reshape(-1, msg)[:, 0] for s in range(warmup, n_steps)])
@@ -391,7 +398,7 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
     # end to end: pinned host -> device -> collective step -> host
     t_e2e = 0.0
     se.close()
-    se = ShardedEngine(wire.FASST, chunk=big, use_slabs=True, strict=False)
+    se = mk()
     pin = torch.empty(B.STEP_REQS * msg, dtype=torch.uint8).pin_memory()
     pout = torch.empty_like(pin).pin_memory()
     for s in range(n_steps):
@@ -400,11 +407,11 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         d = pin.to(dev, non_blocking=True)
-        o = torch.cat([se.submit_tensor(d[r * rb:(r + 1) * rb]) for r in range(B.ROUNDS_PER_STEP)])
+        o = torch.cat(se.submit_many([d[r * rb:(r + 1) * rb] for r in range(B.ROUNDS_PER_STEP)]))
         pout.copy_(o, non_blocking=True)
         torch.cuda.synchronize(dev)
         if s >= warmup:
             t_e2e += time.perf_counter() - t0
-    out.update(e2e_s=t_e2e, e2e_parity=bool((pout.numpy() == resps[n_steps - 1]).all()))
+    out.update(exchange=mode, e2e_s=t_e2e, e2e_parity=bool((pout.numpy() == resps[n_steps - 1]).all()))
     se.close()
     return out

@@ -16,7 +16,8 @@ n = 1 << 20
 K = 8
 reqs = [torch.from_numpy(T.fasst_random(n, 24_000_000, seed=100 * rank + i, weights=(0.6, 0.15, 0.05, 0.2))).cuda().view(torch.uint8).reshape(-1) for i in range(K)]
 res = {}
-for mode in ("p2p", "slabs"):
+modes = os.environ.get("SANITY_MODES", "p2p,slabs").split(",")
+for mode in modes:
     se = ShardedEngine(wire.FASST, chunk=n + n // 2, use_slabs=True, use_p2p=(mode == "p2p"), p2p_max_n=n, strict=False)
     outs = se.submit_many(reqs)
     torch.cuda.synchronize(); dist.barrier()
@@ -40,7 +41,8 @@ for mode in ("p2p", "slabs"):
     if rank == 0:
         print(f"{mode}: {us:.1f} us per 1M-request batch per rank ({n / us / 1e3:.2f} G req/s per GPU), host enqueue {t_cpu * 1e6 / (5 * K):.1f} us/batch, flags {flags}", flush=True)
     se.close()
-same = all(torch.equal(a, b) for a, b in zip(res["p2p"], res["slabs"]))
-if rank == 0:
-    print("p2p == slabs replies:", same)
+if len(modes) == 2:
+    same = all(torch.equal(a, b) for a, b in zip(res["p2p"], res["slabs"]))
+    if rank == 0:
+        print("p2p == slabs replies:", same)
 dist.destroy_process_group()
