@@ -348,6 +348,10 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (dint_b200 has no CPU fallback)")
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -434,7 +438,9 @@ def main():
             line["extra"]["smallbank"] = run_txn(args, torch, rank, "smallbank")
         except Exception as ex:  # side measurements must never cost the headline line
             line.setdefault("extra", {})["error"] = repr(ex)
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
