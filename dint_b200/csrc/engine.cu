@@ -302,11 +302,11 @@ static int pull_counters(dint_engine* e) {
 template <int MSG>
 static void route_scatter_t(const uint8_t* rq, const uint8_t* ow, uint32_t n, uint32_t world, const uint32_t* tb,
                             const uint32_t* totals, uint8_t* out, uint32_t* perm, uint32_t tiles, cudaStream_t s) {
-  k_route_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, totals, out, perm);
+  k_exact_scatter<MSG><<<tiles, kThreads, 0, s>>>(rq, ow, n, world, tb, totals, out, perm);
 }
 template <int MSG>
 static void route_unpermute_t(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out, cudaStream_t s) {
-  k_route_unpermute<MSG><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(sorted, perm, n, out);
+  k_exact_unpermute<MSG><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(sorted, perm, n, out);
 }
 
 // Host-path slice sizes for a call of n requests (see dint_submit): slices double from `mn` up to the plateau
@@ -389,6 +389,13 @@ uint32_t dint_log_entry_size(int kind) { return (kind >= 0 && kind < DINT_NUM_KI
 const char* dint_last_error(void) { return g_last_error.c_str(); }
 uint64_t dint_test_fasthash64(uint64_t x, int len) { return len == 4 ? fasthash64_u32((uint32_t)x) : fasthash64_u64(x); }
 uint32_t dint_test_fastmod(uint64_t n, uint32_t d) { FastMod f = make_fastmod(d); return fast_mod(n, f); }
+uint32_t dint_test_host_slices(uint64_t n, uint32_t min_slice, uint32_t max_slice, int ramp_up, uint32_t* out, uint32_t cap) {
+  HostSlices sched(n, min_slice, max_slice, ramp_up != 0);
+  uint32_t k = 0;
+  for (uint32_t cn; (cn = sched.next()) != 0; k++)
+    if (k < cap) out[k] = cn;
+  return k;
+}
 
 void dint_default_cfg(int kind, dint_cfg* cfg) {
   memset(cfg, 0, sizeof *cfg);
@@ -629,8 +636,8 @@ int dint_route_partition(dint_engine* e, const void* req_dev, const uint8_t* own
   uint32_t* tilecnt = e->d_route + 3 * kMaxShards;
   if (n == 0) { CU(cudaMemsetAsync(counts_dev, 0, n_shards * sizeof(uint32_t), s)); return DINT_OK; }
   e->stats.kernel_launches += 3;
-  k_route_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
-  k_route_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
+  k_exact_count<<<tiles, kThreads, 0, s>>>(owner_dev, (uint32_t)n, n_shards, tilecnt);
+  k_exact_scan<<<n_shards, kThreads, 0, s>>>(tilecnt, tiles, totals);
   const uint8_t* rq = (const uint8_t*)req_dev;
   uint8_t* out = (uint8_t*)sorted_dev;
   switch (e->msg) {

@@ -118,12 +118,12 @@ __global__ void __launch_bounds__(kThreads) k_route_owner(const Ctx c, const uin
 }
 
 // ---- multi-GPU dispatch: stable partition of a batch by owner shard -------------------------------------
-// (1) k_route_count: per 256-record tile, how many records go to each shard;  (2) k_route_scan (one CTA):
+// (1) k_route_count: per 256-record tile, how many records go to each shard;  (2) k_exact_scan (one CTA):
 // exclusive offsets -- shard-major, then tile order -- and the per-shard totals;  (3) k_route_scatter: every
 // record is copied to its slot (stable inside a shard: tile order, then thread order) and the inverse
 // permutation is recorded.  Afterwards the wire records sit grouped by destination, ready for the exchange.
 constexpr int kMaxShards = 8;
-__global__ void __launch_bounds__(kThreads) k_route_count(const uint8_t* owner, uint32_t n, uint32_t world, uint32_t* tilecnt) {
+__global__ void __launch_bounds__(kThreads) k_exact_count(const uint8_t* owner, uint32_t n, uint32_t world, uint32_t* tilecnt) {
   __shared__ uint32_t cnt[kMaxShards];
   if (threadIdx.x < kMaxShards) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) k_route_count(const uint8_t* owner, 
   __syncthreads();
   if (threadIdx.x < world) tilecnt[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];   // shard-major
 }
-__global__ void __launch_bounds__(kThreads) k_route_scan(uint32_t* tilecnt, uint32_t n_tiles, uint32_t* totals) {
+__global__ void __launch_bounds__(kThreads) k_exact_scan(uint32_t* tilecnt, uint32_t n_tiles, uint32_t* totals) {
   // one CTA per shard: exclusive scan of that shard's row of per-tile counts, row total -> totals[shard]
   __shared__ uint32_t wsum[kThreads / 32];
   __shared__ uint32_t carry;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) k_route_scan(uint32_t* tilecnt, uint
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 template <int MSG>
-__global__ void __launch_bounds__(kThreads) k_route_scatter(const uint8_t* req, const uint8_t* owner, uint32_t n, uint32_t world,
+__global__ void __launch_bounds__(kThreads) k_exact_scatter(const uint8_t* req, const uint8_t* owner, uint32_t n, uint32_t world,
                                                             const uint32_t* tilebase, const uint32_t* totals, uint8_t* out,
                                                             uint32_t* perm) {
   __shared__ uint32_t wcnt[kThreads / 32][kMaxShards];
@@ -218,7 +218,7 @@ __global__ void k_p2p_wait(const uint32_t* my_sig, uint32_t world, uint32_t epoc
 
 // combine: replies arrive in partition order; put each back at its original index
 template <int MSG>
-__global__ void __launch_bounds__(kThreads) k_route_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {
+__global__ void __launch_bounds__(kThreads) k_exact_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {
   const uint32_t pos = blockIdx.x * kThreads + threadIdx.x;
   if (pos >= n) return;
   const uint32_t idx = perm[pos];

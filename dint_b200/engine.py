@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_flags", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
-    "dint_test_fasthash64", "dint_test_fastmod",
+    "dint_test_fasthash64", "dint_test_fastmod", "dint_test_host_slices",
 ]
 
 

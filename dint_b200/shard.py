@@ -341,6 +341,17 @@ def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
     # exchange: "p2p" = dispatch/combine kernels storing to / loading from peer memory over NVLink, driven by
     # dint_shard_submit_many; "slabs" = the same kernels on local buffers + NCCL all-to-all
     mode = os.environ.get("DINT_SHARD_MODE", "p2p")
+    if mode == "p2p":
+        # all ranks must take the same path: agree on whether peer-mapped (symmetric) memory is available here
+        try:
+            import torch.distributed._symmetric_memory as _sm          # noqa: F401
+            ok_here = 1
+        except Exception:
+            ok_here = 0
+        t = torch.tensor([ok_here], device=dev, dtype=torch.int32)
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            mode = "slabs"
     mk = lambda: ShardedEngine(wire.FASST, chunk=big, use_slabs=True, strict=False, use_p2p=(mode == "p2p"), p2p_max_n=B.CLIENTS)
     se = mk()
     wl = Workload(wire.FASST, n_clients=B.CLIENTS, seed=20230 + rank, **fam)

@@ -224,6 +224,9 @@ void dint_host_free(void *p);
 /* hooks for unit tests of the host/device-shared arithmetic (no GPU needed) */
 uint64_t dint_test_fasthash64(uint64_t x, int len);      /* len 4 or 8, seed 0xdeadbeef */
 uint32_t dint_test_fastmod(uint64_t n, uint32_t d);
+/* test hook: the slice sizes dint_submit cuts a call of n requests into (host logic, no GPU needed);
+ * returns the number of slices, writes the first `cap` of them */
+uint32_t dint_test_host_slices(uint64_t n, uint32_t min_slice, uint32_t max_slice, int ramp_up, uint32_t *out, uint32_t cap);
 
 #ifdef __cplusplus
 }

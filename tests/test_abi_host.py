@@ -45,6 +45,33 @@ def test_fasthash_and_fastmod_are_exact():
             assert L.dint_test_fastmod(n, d) == n % d, (n, d)
 
 
+def test_host_slice_schedule_covers_every_call_exactly():
+    """dint_submit's slice schedule (pure host logic): the slices sum to n, none exceeds a device buffer,
+    small slices sit only at the two ends (a pyramid), and tiny calls are not split."""
+    import ctypes as C
+    L = E.lib()
+    L.dint_test_host_slices.restype = C.c_uint32
+    L.dint_test_host_slices.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.c_uint32]
+    buf = (C.c_uint32 * 4096)()
+    rng = np.random.default_rng(7)
+    cases = [(1, 131072, 262144), (1000, 131072, 262144), (131072, 131072, 262144), (262144, 131072, 262144),
+             (1 << 20, 131072, 262144), ((1 << 20) + 5, 131072, 262144), (4 << 20, 65536, 1 << 20), (10**8, 65536, 262144)]
+    cases += [(int(rng.integers(1, 3 * 10**7)), int(rng.choice([128, 4096, 65536, 1 << 20])), int(rng.choice([128, 65536, 262144, 1 << 20])))
+              for _ in range(300)]
+    for n, mn, mx in cases:
+        for ramp_up in (0, 1):
+            k = L.dint_test_host_slices(n, mn, mx, ramp_up, buf, 4096)
+            assert k <= 4096 or n > 4096 * mx
+            sl = list(buf[:min(k, 4096)])
+            if k <= 4096:
+                assert sum(sl) == n, (n, mn, mx, ramp_up)
+            assert all(0 < c <= mx for c in sl), (n, mn, mx, ramp_up, sl[:8])
+            if n < min(mn, mx):
+                assert sl == [n]
+            if mn < mx and n >= 2 * mn and k <= 4096:
+                assert sl[-1] == mn, (n, mn, mx, sl)                    # the call ends on its smallest slice
+
+
 def test_default_cfg_is_the_reference_constants():
     c = E.default_cfg(wire.TATP)
     assert (c.lock_slots, c.log_ring, c.subs_sizing, c.accts_sizing, c.n_shards) == (36000000, 1000000, 7000000, 24000000, 1)
