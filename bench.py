@@ -216,10 +216,26 @@ def cpu_baseline(kind, sample_req, txn_per_req, threads, target_s, check_against
     rate1 = st["req_per_s"]
     repeat = max(1, int(target_s * rate1 * max(1, threads) * 0.7 / n))
     _, st = O.run_ref(kind, sample_req, threads=threads, repeat=repeat, want_out=False, spread=threads > 1)
-    return {"value": st["req_per_s"] * txn_per_req, "unit": "txn/s", "cores": threads, "kind": "reference",
-            "sample": f"first step of the trace ({n} requests) x {repeat} passes through oracle/_ref "
-                      f"`server {threads}` under the replay shim ({st['seconds']:.1f} s)",
-            "req_per_s": st["req_per_s"], "gpu_replies_equal_reference": parity}
+    res = {"value": st["req_per_s"] * txn_per_req, "unit": "txn/s", "cores": threads, "kind": "reference",
+           "sample": f"first step of the trace ({n} requests) x {repeat} passes through oracle/_ref "
+                     f"`server {threads}` under the replay shim ({st['seconds']:.1f} s)",
+           "req_per_s": st["req_per_s"], "gpu_replies_equal_reference": parity}
+    res["udp_as_shipped"] = udp_as_shipped(O, kind, sample_req, txn_per_req)
+    return res
+
+
+def udp_as_shipped(O, kind, sample_req, txn_per_req, seconds=4.0):
+    """the unmodified reference server with REAL sockets on loopback (`server 8`, the reference's
+    thread count, exp/run_lock_fasst.sh), two syscalls per request as deployed; informational, never the value."""
+    try:
+        cores = os.cpu_count() or 8
+        ct = max(8, min(32, cores // 4))
+        r = O.run_ref_udp(kind, sample_req, server_threads=8, client_threads=ct, window=32, seconds=seconds)
+        return {"req_per_s": r["req_per_s"], "txn_per_s": r["req_per_s"] * txn_per_req, "server_threads": 8,
+                "client_threads": ct, "lost_datagrams": r["lost"], "seconds": r["seconds"],
+                "note": "oracle/_ref server, bind address rewritten to 127.0.0.1, replies counted not compared"}
+    except Exception as ex:
+        return {"unavailable": repr(ex)[:200]}
 
 
 def run_store_get(args, torch, rank, steps, warmup):
@@ -491,6 +507,8 @@ def main_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "txn/s", "cores": cores if kind == "reference" else 1, "kind": kind,
                              "sample": f"{n}-request closed-loop trace x {max(1, cores // 2)} passes per step"},
             "e2e": {"value": val, "unit": "txn/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if kind == "reference":
+        line["cpu_baseline"]["udp_as_shipped"] = udp_as_shipped(O, wire.FASST, sample, txn_per_req)
     print(json.dumps(line))
 
 

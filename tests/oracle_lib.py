@@ -167,3 +167,43 @@ def run_ref(kind, req: np.ndarray, threads=1, repeat=1, want_out=True, spread=Fa
         stats = json.load(open(sp))
         out = np.fromfile(op, dtype=np.uint8).reshape(req.shape) if want_out else None
     return out, stats
+
+
+def run_ref_udp(kind, req: np.ndarray, server_threads=8, client_threads=8, window=32, seconds=5.0, port=None):
+    """SURVEY 8(d) baseline B1, "the reference UDP server as shipped": the UNMODIFIED server binary with REAL
+    sockets on loopback (only its bind address is rewritten, oracle/udp_shim.c), driven by the multi-socket
+    replayer oracle/udp_blast.c.  Replies are counted, not compared.  Returns the replayer's JSON dict."""
+    import signal
+    import socket
+    import time
+    req = np.ascontiguousarray(req, dtype=np.uint8)
+    if port is None:
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s_:
+            s_.bind(("127.0.0.1", 0))
+            port = s_.getsockname()[1]
+    with tempfile.TemporaryDirectory() as td:
+        tp = os.path.join(td, "trace.bin")
+        req.tofile(tp)
+        env = dict(os.environ, LD_PRELOAD=os.path.join(REF_DIR, "udp_shim.so"), DINT_UDP_PORT=str(port))
+        argv = [os.path.join(REF_DIR, REF_BIN[kind])]
+        if kind in (TATP, SMALLBANK):
+            argv.append("2")
+        argv.append(str(server_threads))
+        srv = subprocess.Popen(argv, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, start_new_session=True)
+        try:
+            time.sleep(1.0 if kind in (LOCK2PL, FASST, LOG) else 40.0)        # table population of the KV servers
+            if srv.poll() is not None:
+                raise RuntimeError(f"reference UDP server exited {srv.returncode} before serving")
+            r = subprocess.run([os.path.join(REF_DIR, "udp_blast"), tp, str(MSG_SIZE[kind]), str(port), str(client_threads),
+                                str(window), str(seconds)], capture_output=True, timeout=seconds + 60)
+            if r.returncode != 0:
+                raise RuntimeError(f"udp_blast exited {r.returncode}: {r.stderr[-300:]!r}")
+            out = json.loads(r.stdout.decode().strip().splitlines()[-1])
+        finally:
+            try:
+                os.killpg(srv.pid, signal.SIGKILL)       # exactly the process group we started
+            except ProcessLookupError:
+                pass
+            srv.wait()
+    out.update(server_threads=server_threads, port=port)
+    return out

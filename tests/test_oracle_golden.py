@@ -1,6 +1,7 @@
 """CPU tests: the oracle restatement (oracle/dint_oracle.c) against (a) the fasthash64 known-answer
 table of SURVEY.md section 8(c), (b) the golden fixtures produced by the unmodified reference servers,
 (c) when oracle/_ref is present (this container), a live replay through the reference binaries."""
+import os
 import struct
 
 import numpy as np
@@ -146,3 +147,16 @@ def test_txn_drivers_run_valid_protocols_against_oracle_shards():
         st = runs[0][1]
         assert st["committed"] > 0.2 * st["txns"]
         assert all(v[0] > 0 for v in st["by_type"].values())
+
+
+@pytest.mark.skipif(not (O.ref_available() and os.path.exists(os.path.join(O.REF_DIR, "udp_blast"))),
+                    reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_server_answers_over_loopback_udp():
+    """The "as shipped" CPU baseline harness (oracle/udp_shim.c + udp_blast.c): the unmodified lock_fasst server
+    with real sockets answers every datagram it is sent."""
+    req = T.fasst_random(20000, 10**6, seed=2)
+    try:
+        r = O.run_ref_udp(O.FASST, req, server_threads=2, client_threads=2, window=8, seconds=1.0)
+    except (OSError, RuntimeError) as ex:      # no loopback sockets in this sandbox
+        pytest.skip(repr(ex))
+    assert r["replies"] > 1000 and r["lost"] <= r["replies"] // 100
