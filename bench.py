@@ -238,6 +238,57 @@ def udp_as_shipped(O, kind, sample_req, txn_per_req, seconds=4.0):
         return {"unavailable": repr(ex)[:200]}
 
 
+def run_closed_loop_extra(args, torch, rank, kind_name, rounds=16, warm=24):
+    """lock_2pl / log_server side measurement: the reference's closed-loop clients (workloads.cc) recorded against
+    the GPU engine through the host path, then replayed device-resident and timed; replies must be bit-exact."""
+    from dint_b200 import Engine, wire
+    from dint_b200.workloads import Workload, REF
+    kind = {"lock_2pl": wire.LOCK2PL, "log_server": wire.LOG}[kind_name]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    fam = REF if kind == wire.LOCK2PL else {}
+    wl = Workload(kind, n_clients=CLIENTS, seed=20230 + rank, **fam)
+    if kind == wire.LOG:
+        warm = 3                                          # no protocol state to warm up
+    reqs, resps, committed = [], [], []
+    with Engine(kind, device=dev.index, chunk=args.chunk) as eng:
+        for _ in range(warm + rounds):
+            before = wl.stats()["committed"]
+            q = wl.next()
+            a = eng.submit(q)
+            wl.feed(a)
+            reqs.append(q.copy()); resps.append(a.copy())
+            committed.append(wl.stats()["committed"] - before)   # transactions whose last reply arrived this round
+    st = wl.stats()
+    with Engine(kind, device=dev.index, chunk=args.chunk) as eng:
+        d_req = [torch.from_numpy(r).to(dev) for r in reqs]
+        d_out = torch.empty_like(d_req[0])
+        for r in range(warm):
+            eng.submit_tensor(d_req[r], d_out)
+        torch.cuda.synchronize(dev)
+        eng.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(warm, warm + rounds):
+            eng.submit_tensor(d_req[r], d_out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        ok = bool((d_out.cpu().numpy() == resps[-1]).all())
+        est = eng.stats()
+    n_req = rounds * CLIENTS
+    res = {"workload": ("lock_2pl REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(exclusive)=0.2, closed-loop 2PL clients "
+                        "(acquire in id order, release in reverse, retry after a reject)" if kind == wire.LOCK2PL else
+                        "log_server: key uniform [0, 7,009,999], ver [0,127], 40 random bytes per append") +
+                       f"; {CLIENTS} logical clients, {rounds} rounds timed (device-resident replay of the recorded closed loop)",
+           "requests_per_s": n_req / (ms * 1e-3), "replies_bit_exact": ok, "gpu_launches": est["kernel_launches"],
+           "conflicted_fraction": est["conflicted"] / max(1, est["requests"])}
+    if kind == wire.LOCK2PL:
+        res["txn_per_s"] = sum(committed[warm:]) / (ms * 1e-3)
+        res["requests_per_txn"] = n_req / max(1, sum(committed[warm:]))
+        res["lock_rejects"] = st["lock_rejects"]
+    return res
+
+
 def run_store_get(args, torch, rank, steps, warmup):
     """The store lookup path: 100 % kRead, NURand keys over the reference's 24 M-key population."""
     from dint_b200 import Engine, wire
@@ -454,6 +505,11 @@ def main():
             line["extra"]["smallbank"] = run_txn(args, torch, rank, "smallbank")
         except Exception as ex:  # side measurements must never cost the headline line
             line.setdefault("extra", {})["error"] = repr(ex)
+        for kn in ("lock_2pl", "log_server"):
+            try:
+                line["extra"][kn] = run_closed_loop_extra(args, torch, rank, kn)
+            except Exception as ex:
+                line.setdefault("extra", {})[kn] = {"error": repr(ex)}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
