@@ -118,6 +118,10 @@ def test_workload_drivers_are_deterministic_and_valid():
     (wire.FASST, lambda: T.fasst_random(20000, 64, seed=11)),
     (wire.LOCK2PL, lambda: T.lock2pl_random(20000, 64, seed=12)),
     (wire.LOG, lambda: T.log_random(5000, seed=13)),
+    (wire.FASST, lambda: T.fasst_random(1, 1, seed=14)),                      # a single datagram
+    (wire.FASST, lambda: T.fasst_random(6000, 1, seed=15)),                   # every request on ONE lock slot
+    (wire.LOCK2PL, lambda: T.lock2pl_random(6000, 1, seed=16, p_release=0.7)),  # releases without a hold: u32 wrap
+    (wire.LOCK2PL, lambda: T.lock2pl_random(3000, 2**32 - 1, seed=17)),       # ids over the whole u32 range
 ])
 def test_oracle_matches_live_reference_binary(kind, make):
     req = make()
