@@ -2,6 +2,7 @@
 
   dint_b200/lib/libdint_b200.so   CUDA kernels + C ABI (include/dint_b200.h), nvcc, sm_100a only
   dint_b200/lib/libdint_wl.so     workload clients (CPU C++: the reference's closed-loop clients restated)
+  dint_b200/lib/dint_udp_server   the reference's UDP server front-end over the C ABI (recvmmsg / sendmmsg)
 """
 import os
 import shutil
@@ -12,6 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdint_b200.so")
 WL_LIB = os.path.join(LIBDIR, "libdint_wl.so")
+UDP_SERVER = os.path.join(LIBDIR, "dint_udp_server")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -51,4 +53,8 @@ def build(force=False, verbose=False):
     wl_src = [os.path.join(CSRC, "workloads.cc"), os.path.join(CSRC, "txn_workloads.cc")]
     if os.path.exists(wl_src[0]) and (force or _newer(WL_LIB, wl_src + _sources((".h", ".cuh")))):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", WL_LIB] + wl_src, check=True)
+    srv_src = os.path.join(CSRC, "udp_server.cc")
+    if os.path.exists(srv_src) and (force or _newer(UDP_SERVER, [srv_src, LIB] + _sources((".h",)))):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-o", UDP_SERVER, srv_src, "-L" + LIBDIR, "-ldint_b200",
+                        "-Wl,-rpath,$ORIGIN", "-lpthread"], check=True)
     return LIB

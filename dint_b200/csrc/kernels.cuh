@@ -103,7 +103,7 @@ DINT_D uint32_t route_owner_of(const Ctx& c, const uint8_t* rec) {
   using W = Wire<KIND>;
   const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
   if (ti.invalid || !ti.mask) return c.shard_id;         // no per-key state touched: serve it where it arrived
-  uint32_t gglobal;
+  uint32_t gglobal = 0;
   if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
   else if constexpr (KIND == K_STORE) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[0].lock_mod);
   else if constexpr (KIND == K_TATP || KIND == K_SMALLBANK) gglobal = fast_mod(fasthash64_u64(ld_u64_unaligned(rec + W::KEY)), c.tbl[rec[W::TABLE]].lock_mod);

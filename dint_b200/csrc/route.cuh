@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
   using W = Wire<KIND>;
   using RT = RTile<W::MSG>;
   constexpr int MSG = W::MSG, PER = RT::PER;
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_in = smem;                                  // the tile as it arrived
   uint8_t* s_out = smem + RT::BYTES + 16;                // the tile partitioned into runs
   __shared__ Cnt8 s_w[kThreads / 32];
@@ -298,7 +298,7 @@ template <int MSG>
 __global__ void __launch_bounds__(kThreads) k_route_combine(const RouteArgs a) {
   using RT = RTile<MSG>;
   constexpr int PER = RT::PER;
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_out = smem;                                 // the tile in request order
   uint8_t* s_in = smem + RT::BYTES + 16;                 // the runs as they sit in the slabs
   __shared__ Cnt8 s_w[kThreads / 32];

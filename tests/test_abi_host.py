@@ -83,3 +83,15 @@ def test_no_cpu_fallback():
     with pytest.raises(E.DintError) as ei:
         E.Engine(wire.FASST)
     assert ei.value.code == -19        # DINT_ENODEV
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="only meaningful without a GPU")
+def test_udp_front_end_builds_and_fails_loudly_without_a_gpu():
+    """dint_udp_server (the reference's UDP server shape over the C ABI) has no CPU path either."""
+    import subprocess
+    from dint_b200 import _build
+    E.lib()
+    assert os.path.exists(_build.UDP_SERVER)
+    r = subprocess.run([_build.UDP_SERVER, "lock_fasst", "--port", "29731"], capture_output=True, timeout=60)
+    assert r.returncode == 1 and b"dint_create failed" in r.stderr
+    assert subprocess.run([_build.UDP_SERVER, "no_such_server"], capture_output=True, timeout=60).returncode == 2

@@ -2,6 +2,7 @@
 
 Bar: bit-exact response streams (integer/byte work) and bit-exact final server state.
 """
+import os
 import numpy as np
 import pytest
 
@@ -361,3 +362,38 @@ def test_route_owner_partition_unpermute(kind, world):
         assert np.array_equal(srt.cpu().numpy().reshape(-1, msg), req.reshape(-1, msg)[order])
         back = eng.route_unpermute(srt, perm)
         assert np.array_equal(back.cpu().numpy(), req)
+
+
+# ---------------------------------------------------------------- the UDP front-end (opt-in until measured) ---
+@pytest.mark.skipif(os.environ.get("DINT_UDP_TEST") != "1", reason="opt-in: set DINT_UDP_TEST=1 (needs loopback sockets)")
+def test_udp_front_end_serves_the_wire_protocol_bit_exact():
+    """dint_udp_server behind a real socket: one client socket, windows of 64 datagrams (loopback keeps their
+    order), replies must equal ONE sequential reference server's."""
+    import socket
+    import subprocess
+    import time
+    from dint_b200 import _build
+    req = T.fasst_random(20000, 3000, seed=21)
+    want = O.Oracle(wire.FASST).process(req).reshape(-1, 9)
+    with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s0:
+        s0.bind(("127.0.0.1", 0))
+        port = s0.getsockname()[1]
+    srv = subprocess.Popen([_build.UDP_SERVER, "lock_fasst", "--port", str(port), "--bind", "127.0.0.1"], stderr=subprocess.PIPE)
+    try:
+        time.sleep(8.0)                                   # CUDA context + tables
+        assert srv.poll() is None, srv.stderr.read()
+        c = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        c.settimeout(5.0)
+        c.connect(("127.0.0.1", port))
+        rec = np.ascontiguousarray(req).view(np.uint8).reshape(-1, 9)
+        got = np.empty_like(rec)
+        for lo in range(0, len(rec), 64):
+            hi = min(lo + 64, len(rec))
+            for i in range(lo, hi):
+                c.send(rec[i].tobytes())
+            for i in range(lo, hi):
+                got[i] = np.frombuffer(c.recv(64), dtype=np.uint8)
+        assert np.array_equal(got, want)
+    finally:
+        srv.terminate()
+        srv.wait(timeout=20)
