@@ -1,0 +1,56 @@
+"""-m gpu: size-independent properties (tests/properties.py, pinned on the oracle by tests/test_properties_cpu.py) on
+the CUDA engine at BASELINE.json's FULL sizes -- 36,000,000 lock slots, 24,000,000 lock ids, the 24,000,000-key
+store -- with millions of requests per batch, through the C ABI.  An oracle replay of this volume is the bench's
+job (`gpu_replies_equal_reference`); here the domain's own invariants are the checker."""
+import os
+
+import numpy as np
+import pytest
+
+import properties as P
+import trace_gen as T
+from dint_b200 import Engine, wire
+
+pytestmark = pytest.mark.gpu
+
+N = 1 << 21          # requests per batch: two engine chunks, so chunk boundaries are crossed
+# the most contended variants (millions of requests on a few thousand slots / a few hundred keys in ONE call) were
+# written after the last GPU session of round 1: opt-in until they have run once
+STRESS = os.environ.get("DINT_FULL_PROPERTIES") == "1"
+
+
+class EngineServer:
+    def __init__(self, eng):
+        self.eng = eng
+        self.lock_slots = int(eng.cfg.lock_slots)
+
+    def submit(self, req):
+        return self.eng.submit(req)
+
+
+def test_fasst_full_size_roundtrip_and_checksum():
+    with Engine(wire.FASST) as eng:                      # reference constants: 36 M slots (utils.h:16)
+        srv = EngineServer(eng)
+        assert P.fasst_acquire_abort_roundtrip(srv, N, 24_000_000, seed=1) > N // 2
+        assert P.fasst_commit_checksum(srv, N, 24_000_000, seed=2) > N // 2
+        # and under heavy contention (the HOT shape: 4800 ids), where almost everything goes through the ordered path
+        assert P.fasst_acquire_abort_roundtrip(srv, N, 4800, seed=3) <= 4800
+        assert P.fasst_commit_checksum(srv, N, 4800, seed=4) <= 3 * 4800
+
+
+def test_lock2pl_full_size_counters_balance():
+    with Engine(wire.LOCK2PL) as eng:
+        srv = EngineServer(eng)
+        assert P.lock2pl_counters_balance(srv, N, 24_000_000, seed=5) > N // 2
+        if STRESS:
+            assert P.lock2pl_counters_balance(srv, N, 4800, seed=6) > 0
+
+
+def test_store_full_population_read_your_writes():
+    with Engine(wire.STORE, populate=True) as eng:       # 2,000,000 subscribers -> 24,000,000 keys, as the reference
+        srv = EngineServer(eng)
+        keys = wire.as_records(wire.STORE, T.store_random(N, 2_000_000, seed=7, p_set=0.0, p_miss=0.0))["key"].copy()
+        assert P.store_read_your_writes(srv, keys, seed=8) == N
+        if STRESS:
+            hot = wire.as_records(wire.STORE, T.store_random(N, 50, seed=9, p_set=0.0, p_miss=0.0))["key"].copy()
+            assert P.store_read_your_writes(srv, hot, seed=10) == N  # 600 keys x 3500 writes each: the replay path
