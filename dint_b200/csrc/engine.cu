@@ -1016,7 +1016,9 @@ int64_t dint_kv_count(dint_engine* e, int table) {
 struct dint_shard_ctx {
   dint_engine* e = nullptr;
   uint32_t W = 0, me = 0, cap = 0, S = 0;
-  uint64_t inbox[4][kMaxShards]{}, outbox[4][kMaxShards]{};
+  uint64_t inbox[4][kMaxShards]{}, outbox[4][kMaxShards]{}, retbox[4][kMaxShards]{};
+  bool push = false;                       // DINT_SHARD_PUSH=1 and return buffers given: owners push the replies
+  cudaEvent_t ev_eng[4]{};
   PeerPtrs sigreq{}, sigrsp{}, sigdone{};
   uint32_t *my_req = nullptr, *my_rsp = nullptr, *my_done = nullptr;
   uint32_t epoch = 0;
@@ -1034,7 +1036,8 @@ struct dint_shard_ctx {
 };
 
 int dint_shard_create(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets, const dint_peer_ptrs* inbox_sets,
-                      const dint_peer_ptrs* outbox_sets, const dint_peer_ptrs* sig_blocks, uint64_t max_n, dint_shard_ctx** out) {
+                      const dint_peer_ptrs* outbox_sets, const dint_peer_ptrs* retbox_sets, const dint_peer_ptrs* sig_blocks, uint64_t max_n,
+                      dint_shard_ctx** out) {
   if (!e || !out || !inbox_sets || !outbox_sets || !sig_blocks || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 ||
       n_sets < 2 || n_sets > 4 || max_n == 0 || max_n > 0xffffffffULL)
     return set_err(DINT_EINVAL, "bad argument");
@@ -1043,7 +1046,11 @@ int dint_shard_create(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
   e->plain_launches = true;
   c->e = e; c->W = n_shards; c->me = rank; c->cap = cap; c->S = n_sets; c->max_n = max_n;
   for (uint32_t s = 0; s < n_sets; s++)
-    for (uint32_t o = 0; o < n_shards; o++) { c->inbox[s][o] = inbox_sets[s].p[o]; c->outbox[s][o] = outbox_sets[s].p[o]; }
+    for (uint32_t o = 0; o < n_shards; o++) {
+      c->inbox[s][o] = inbox_sets[s].p[o];
+      c->outbox[s][o] = outbox_sets[s].p[o];
+      c->retbox[s][o] = retbox_sets ? retbox_sets[s].p[o] : 0;
+    }
   for (uint32_t o = 0; o < n_shards; o++) {
     c->sigreq.p[o] = sig_blocks->p[o];
     c->sigrsp.p[o] = sig_blocks->p[o] + 64;
@@ -1060,12 +1067,14 @@ int dint_shard_create(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
   for (uint32_t s = 0; s < n_sets; s++) {
     CU(cudaEventCreateWithFlags(&c->ev_disp[s], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_comb[s], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_eng[s], cudaEventDisableTiming));
     CU(cudaMalloc(&c->owner[s], max_n + 16));
     CU(cudaMalloc(&c->tilebase[s], tiles * kMaxShards * sizeof(uint32_t)));
   }
   CU(cudaMalloc(&c->flags, 2 * sizeof(uint32_t)));
   CU(cudaMemset(c->flags, 0, 2 * sizeof(uint32_t)));
   c->trace = getenv("DINT_SHARD_TRACE") != nullptr;
+  { const char* ps = getenv("DINT_SHARD_PUSH"); c->push = retbox_sets && ps && atoi(ps) == 1 && ((size_t)cap * e->msg) % 16 == 0; }
   { const char* ts = getenv("DINT_SHARD_STREAMS"); c->three_streams = !ts || atoi(ts) == 3; }
   *out = c;
   return DINT_OK;
@@ -1086,6 +1095,7 @@ void dint_shard_destroy(dint_shard_ctx* c) {
   for (uint32_t s = 0; s < c->S; s++) {
     if (c->ev_disp[s]) cudaEventDestroy(c->ev_disp[s]);
     if (c->ev_comb[s]) cudaEventDestroy(c->ev_comb[s]);
+    if (c->ev_eng[s]) cudaEventDestroy(c->ev_eng[s]);
     if (c->owner[s]) cudaFree(c->owner[s]);
     if (c->tilebase[s]) cudaFree(c->tilebase[s]);
   }
@@ -1152,10 +1162,22 @@ int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req
     const uint32_t s = ep % S;
     if (!one_stream) CU(cudaStreamWaitEvent(ret, c->ev_disp[s], 0));
     mark(j, 6, ret);
+    if (c->push) {                                         // my replies to the other sources go out first, then the flag
+      if (!one_stream) CU(cudaStreamWaitEvent(ret, c->ev_eng[s], 0));
+      if (W > 1) {
+        PeerPtrs rb{};
+        for (uint32_t o = 0; o < W; o++) rb.p[o] = c->retbox[s][o];
+        const uint32_t slab16 = (uint32_t)(slab / 16);
+        k_push_slabs<<<148 * 2, kThreads, 0, ret>>>((const uint8_t*)c->outbox[s][c->me], rb, W, c->me, slab16);
+      }
+      k_p2p_signal<<<1, 32, 0, ret>>>(c->sigrsp, W, c->me, ep);
+    }
     k_p2p_wait<<<1, 32, 0, ret>>>(c->my_rsp, W, ep, c->flags + 1);
     mark(j, 7, ret);
     dint_peer_ptrs ob{};
-    for (uint32_t o = 0; o < W; o++) ob.p[o] = c->outbox[s][o] + (uint64_t)c->me * slab;
+    for (uint32_t o = 0; o < W; o++)
+      ob.p[o] = c->push ? (o == c->me ? c->outbox[s][c->me] + (uint64_t)c->me * slab : c->retbox[s][c->me] + (uint64_t)o * slab)
+                        : c->outbox[s][o] + (uint64_t)c->me * slab;
     int rc = dint_route_combine(e, &ob, c->owner[s], c->tilebase[s], n, W, c->cap, out_dev[j], ret);
     if (rc) return rc;
     k_p2p_signal<<<1, 32, 0, ret>>>(c->sigdone, W, c->me, ep);
@@ -1176,7 +1198,8 @@ int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req
     mark(j, 4, main);
     rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)W * c->cap, (uint8_t*)c->outbox[s][c->me], main);
     if (rc) return rc;
-    k_p2p_signal<<<1, 32, 0, main>>>(c->sigrsp, W, c->me, ep);
+    if (!c->push) k_p2p_signal<<<1, 32, 0, main>>>(c->sigrsp, W, c->me, ep);
+    else if (!one_stream) CU(cudaEventRecord(c->ev_eng[s], main));
     mark(j, 5, main);
     if (j >= lag && (rc = combine(j - lag, ep - lag))) return rc;
     e->stats.kernel_launches += 5;

@@ -216,6 +216,20 @@ __global__ void k_p2p_wait(const uint32_t* my_sig, uint32_t world, uint32_t epoc
   __threadfence_system();
 }
 
+// push variant of the combine's transport: the owner copies the reply slab of every source into that source's
+// return buffer with posted remote stores (a remote load stalls the issuing warp for an NVLink round trip, a
+// remote store does not); slab bytes are a multiple of 16, all bases 16-byte aligned
+__global__ void __launch_bounds__(kThreads) k_push_slabs(const uint8_t* outbox, PeerPtrs retbox, uint32_t world, uint32_t me, uint32_t slab16) {
+  const uint64_t total = (uint64_t)(world - 1) * slab16;                 // uint4 elements to move
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (uint64_t)gridDim.x * kThreads) {
+    uint32_t o = (uint32_t)(i / slab16);
+    const uint32_t j = (uint32_t)(i - (uint64_t)o * slab16);
+    if (o >= me) o++;                                                    // every source but myself
+    const uint4 v = __ldcg((const uint4*)(outbox + (size_t)o * slab16 * 16) + j);
+    ((uint4*)retbox.p[o])[(size_t)me * slab16 + j] = v;                  // my slab inside source o's return buffer
+  }
+}
+
 // combine: replies arrive in partition order; put each back at its original index
 template <int MSG>
 __global__ void __launch_bounds__(kThreads) k_exact_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {

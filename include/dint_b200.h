@@ -177,6 +177,8 @@ int dint_p2p_signal(dint_engine *e, const dint_peer_ptrs *sig_ptrs, uint32_t n_s
  * n_shards * cap records, plus one 256-byte signal block (three arrays of 8 epoch words: requests written /
  * replies written / replies read), all in memory its peers map (CUDA IPC / torch symmetric memory), zeroed once.
  *   inbox_sets[s].p[o], outbox_sets[s].p[o]: device address of rank o's set s; sig_blocks->p[o]: rank o's block.
+ *   retbox_sets (optional, same shape): return buffers; with DINT_SHARD_PUSH=1 the owners STORE the replies into the
+ *   sources' return buffers (posted writes) instead of the sources loading them from the owners' outboxes.
  * dint_shard_submit_many: k batches of n (<= max_n) records each, the same k and n on every rank; batch j+1 is
  * partitioned into the owners' inboxes (dint_route_dispatch) while batch j runs through the local engine on
  * cuda_stream and the replies of batch j-1 are pulled from the owners' outboxes (dint_route_combine); out_dev[j]
@@ -186,8 +188,8 @@ int dint_p2p_signal(dint_engine *e, const dint_peer_ptrs *sig_ptrs, uint32_t n_s
  * last call; both must be 0 for the replies to stand. */
 typedef struct dint_shard_ctx dint_shard_ctx;
 int dint_shard_create(dint_engine *e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets,
-                      const dint_peer_ptrs *inbox_sets, const dint_peer_ptrs *outbox_sets, const dint_peer_ptrs *sig_blocks,
-                      uint64_t max_n, dint_shard_ctx **out);
+                      const dint_peer_ptrs *inbox_sets, const dint_peer_ptrs *outbox_sets, const dint_peer_ptrs *retbox_sets,
+                      const dint_peer_ptrs *sig_blocks, uint64_t max_n, dint_shard_ctx **out);
 void dint_shard_destroy(dint_shard_ctx *c);
 int dint_shard_submit_many(dint_shard_ctx *c, uint32_t k, const void *const *req_dev, const uint8_t *const *dst_dev, uint64_t n,
                            void *const *out_dev, void *cuda_stream);

@@ -40,7 +40,9 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
             mk, cfg = (lambda r: T.lock2pl_random(n_per_rank, 500, seed=5 + r)), {}
         else:
             mk, cfg = (lambda r: T.store_random(n_per_rank, 400, seed=5 + r)), dict(subs_populate=400)
-        se = ShardedEngine(kind, chunk=1 << 13, use_slabs=(mode == 'slabs'), use_p2p=(mode == 'p2p'), p2p_max_n=n_per_rank, **cfg)
+        if mode == 'p2p_push':
+            os.environ["DINT_SHARD_PUSH"] = "1"           # owners store the replies into the sources' return buffers
+        se = ShardedEngine(kind, chunk=1 << 13, use_slabs=(mode == 'slabs'), use_p2p=mode.startswith('p2p'), p2p_max_n=n_per_rank, **cfg)
         if kind == wire.STORE:
             se.populate()
         got1 = se.submit(mk(rank))
@@ -59,7 +61,7 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
         for i in range(K):
             want = seq.process(np.concatenate([mk(r + 100 + 10 * i) for r in range(world)]))
             ok = ok and bool(np.array_equal(outs[i].cpu().numpy(), want[lo:hi]))
-        if mode == 'p2p':
+        if mode.startswith('p2p'):
             ok = ok and se.check_p2p() == (0, 0)
         else:
             ok = ok and not se.check_overflow()
@@ -70,7 +72,11 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["exact", "slabs", "p2p"])
+# p2p_push was written after the last GPU session of round 1: opt-in until it has run once
+MODES = ["exact", "slabs", "p2p"] + (["p2p_push"] if os.environ.get("DINT_FULL_PROPERTIES") == "1" else [])
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("kind", [0, 1, 3])
 def test_sharded_nccl_world2(kind, mode):
     """exact = variable-count NCCL all-to-all; slabs = fixed-capacity NCCL exchange with padding records;
