@@ -71,11 +71,11 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 # p2p_push was written after the last GPU session of round 1: opt-in until it has run once
 MODES = ["exact", "slabs", "p2p"] + (["p2p_push"] if os.environ.get("DINT_FULL_PROPERTIES") == "1" else [])
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("kind", [0, 1, 3])
 def test_sharded_nccl_world2(kind, mode):
