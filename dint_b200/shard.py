@@ -111,17 +111,19 @@ class ShardedEngine:
         self.p2p_max_n = max_n
         cap = self._cap(max_n)
         region = (W * cap * self.msg + 255) // 256 * 256
-        self.sym = symm_mem.empty(n_sets * 3 * region + 4096, dtype=torch.uint8, device=self.device)
+        push = os.environ.get("DINT_SHARD_PUSH") == "1"          # experimental: owners store the replies into return buffers
+        k = 3 if push else 2                                     # regions per set: inbox | outbox [| return buffer]
+        self.sym = symm_mem.empty(n_sets * k * region + 4096, dtype=torch.uint8, device=self.device)
         grp = self.group if self.group is not None else dist.group.WORLD
         self.sym_hdl = symm_mem.rendezvous(self.sym, group=grp.group_name)
         self.sym.zero_()
         torch.cuda.synchronize(self.device)
         self.sym_hdl.barrier()
         ptrs = [int(p) for p in self.sym_hdl.buffer_ptrs]
-        inbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * 3 * region for p in ptrs]) for s in range(n_sets)])
-        outbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * 3 * region + region for p in ptrs]) for s in range(n_sets)])
-        retbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * 3 * region + 2 * region for p in ptrs]) for s in range(n_sets)])
-        sig = DintPeerPtrs.of([p + n_sets * 3 * region for p in ptrs])
+        inbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region for p in ptrs]) for s in range(n_sets)])
+        outbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region + region for p in ptrs]) for s in range(n_sets)])
+        retbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region + 2 * region for p in ptrs]) for s in range(n_sets)]) if push else None
+        sig = DintPeerPtrs.of([p + n_sets * k * region for p in ptrs])
         ctx = C.c_void_p()
         rc = lib().dint_shard_create(self.engine.h, W, self.rank, cap, n_sets, inbox, outbox, retbox, C.byref(sig), max_n, C.byref(ctx))
         if rc != 0:
