@@ -229,31 +229,6 @@ DINT_D void tma_store_commit_and_wait() {
 }
 DINT_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Stage `bytes` (any size) from global `src` (16-byte aligned) into shared `dst` (16-byte aligned):
-// the 16-byte-multiple body goes through one TMA bulk copy issued by thread 0, the <16-byte tail of
-// the very last tile through plain byte loads.  Call from all threads; returns after the data is
-// visible to the whole CTA.
-DINT_D void stage_in(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* bar, uint32_t phase) {
-  uint32_t body = bytes & ~15u;
-  if (threadIdx.x == 0 && body) {
-    mbar_expect_tx(bar, body);
-    tma_load_1d(dst, src, body, bar);
-  }
-  for (uint32_t b = body + threadIdx.x; b < bytes; b += blockDim.x) dst[b] = src[b];
-  if (body) mbar_wait(bar, phase);
-  __syncthreads();
-}
-// Write a staged tile back.  All threads call it after their last shared-memory write.
-DINT_D void stage_out(uint8_t* gdst, const uint8_t* ssrc, uint32_t bytes) {
-  fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the async proxy
-  __syncthreads();
-  uint32_t body = bytes & ~15u;
-  if (threadIdx.x == 0 && body) {
-    tma_store_1d(gdst, ssrc, body);
-    tma_store_commit_and_wait();
-  }
-  for (uint32_t b = body + threadIdx.x; b < bytes; b += blockDim.x) gdst[b] = ssrc[b];
-}
 #endif  // __CUDACC__
 
 }  // namespace dint
