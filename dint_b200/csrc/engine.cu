@@ -55,6 +55,7 @@ struct dint_engine {
   uint8_t* d_resp[kHostBufs] = {nullptr};
   cudaEvent_t ev_in[kHostBufs]{}, ev_comp[kHostBufs]{}, ev_out[kHostBufs]{};
   uint32_t host_chunk = 0;                   // requests per host-path slice
+  bool pdl = false;                          // DINT_PDL=1: programmatic dependent launches for K1 / K2 (experimental)
   bool plain_launches = false;               // inside the multi-GPU step: no cooperative launches (see GridBar)
   uint32_t host_min_slice = 0;               // smallest slice of the pyramid a host-path call is cut into
   bool host_ramp_up = true;
@@ -146,9 +147,14 @@ static cudaError_t launch_ex(dint_engine* e, void (*kern)(Args...), int grid, in
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[3];
   int na = 0;
   if (coop) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
+  else if (e->pdl) {                                    // DINT_PDL=1: the launch may overlap its predecessor's tail
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
   if (e->use_window) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = e->window; na++; }
   cfg.attrs = at;
   cfg.numAttrs = na;
@@ -587,6 +593,7 @@ int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
     uint32_t want = hc ? (uint32_t)atoi(hc) : (1u << 18);
     if (want < (uint32_t)kTile) want = kTile;
     e->host_chunk = want < e->chunk ? (want + kTile - 1) / kTile * kTile : e->chunk;
+    { const char* pd = getenv("DINT_PDL"); e->pdl = pd && atoi(pd) == 1; }
     const char* ms = getenv("DINT_HOST_MIN_SLICE");
     e->host_min_slice = ms ? (uint32_t)atoi(ms) : 131072u;
     const char* ru = getenv("DINT_HOST_RAMP_UP");

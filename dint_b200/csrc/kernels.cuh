@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[kStages];
   __shared__ uint32_t scratch[kTile / 32];
+  griddep_wait();                                        // everything below depends on the previous launch of the stream
+  griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     // [2] (a writer exists) is OR-ed by any CTA of this launch, so it is cleared one launch early: each K1
@@ -402,8 +404,10 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
   __syncthreads();
   const TileIter it = tile_iter(c.n_tiles);
-  if (threadIdx.x == 0)
-    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+  if (threadIdx.x == 0)                                  // the request tiles do not depend on K1: their loads may start
+    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);   // before K1 has drained
+  griddep_wait();                                        // flags, group ids, counters: K1's output
+  griddep_launch();
   const bool chunk_has_writer = c.nc_cur[2] != 0;      // set by K1; false = nothing in this chunk can conflict
 
   for (uint32_t i = 0; i < it.n_my; i++) {
@@ -693,6 +697,7 @@ struct GridBar {
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
+  griddep_wait();
   const uint32_t nc = c.nc_ord[0];
   const uint32_t overflow = c.nc_ord[1];
   if (nc == 0 || overflow == 0) return;               // the bucket path (inside the next K1) handles this chunk
