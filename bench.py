@@ -289,6 +289,62 @@ def run_closed_loop_extra(args, torch, rank, kind_name, rounds=16, warm=24):
     return res
 
 
+def run_udp_front_end(seconds=4.0):
+    """dint_udp_server (the reference's UDP server shape over the C ABI, dint_b200/csrc/udp_server.cc) with the GPU
+    engine behind it, driven over loopback by the same multi-socket replayer that times the unmodified reference
+    server for cpu_baseline.udp_as_shipped.  Runs in child processes with deadlines."""
+    import signal
+    import socket
+    import tempfile
+    from dint_b200 import _build, wire
+    blast = os.path.join(ROOT, "oracle", "_ref", "udp_blast")
+    if not (os.path.exists(_build.UDP_SERVER) and os.path.exists(blast)):
+        return {"unavailable": "dint_udp_server or oracle/_ref/udp_blast not built"}
+    n = 1 << 20
+    rng = np.random.default_rng(20230)
+    rec = np.zeros(n, dtype=wire.MSG_DTYPE[wire.FASST])
+    rec["type"] = rng.choice(4, size=n, p=(0.6, 0.15, 0.05, 0.2))          # read / acquire / abort / commit mix of the REF trace
+    rec["lid"] = rng.integers(0, 24_000_000, size=n)
+    with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s0:
+        s0.bind(("127.0.0.1", 0))
+        port = s0.getsockname()[1]
+    with tempfile.TemporaryDirectory() as td:
+        tp = os.path.join(td, "trace.bin")
+        wire.as_bytes(rec).tofile(tp)
+        srv = subprocess.Popen([_build.UDP_SERVER, "lock_fasst", "--bind", "127.0.0.1", "--port", str(port), "--sockets", "8"],
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, start_new_session=True)
+        try:
+            t0 = time.time()
+            os.set_blocking(srv.stderr.fileno(), False)
+            banner = b""
+            while b"sockets, batches" not in banner:                         # printed once the engine exists and the sockets are bound
+                if srv.poll() is not None or time.time() - t0 > 90:
+                    return {"unavailable": "server did not come up: " + banner.decode(errors="replace")[-200:]}
+                time.sleep(0.2)
+                try:
+                    banner += srv.stderr.read() or b""
+                except (BlockingIOError, TypeError):
+                    pass
+            cores = os.cpu_count() or 8
+            ct = max(8, min(32, cores // 4))
+            r = subprocess.run([blast, tp, "9", str(port), str(ct), "64", str(seconds)], capture_output=True, timeout=seconds + 60)
+            out = json.loads(r.stdout.decode().strip().splitlines()[-1])
+        finally:
+            try:
+                os.killpg(srv.pid, signal.SIGTERM)          # exactly the process group we started
+            except ProcessLookupError:
+                pass
+            try:
+                srv.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                os.killpg(srv.pid, signal.SIGKILL)
+                srv.wait()
+    return {"req_per_s": out["req_per_s"], "lost_datagrams": out["lost"], "server_sockets": 8, "client_threads": out["client_threads"],
+            "window": out["window"], "seconds": out["seconds"],
+            "note": "loopback UDP, one datagram per request, recvmmsg/sendmmsg front-end + dint_submit; same replayer as "
+                    "cpu_baseline.udp_as_shipped; replies counted, not compared (parity of this path: tests)"}
+
+
 def run_store_get(args, torch, rank, steps, warmup):
     """The store lookup path: 100 % kRead, NURand keys over the reference's 24 M-key population."""
     from dint_b200 import Engine, wire
@@ -519,6 +575,11 @@ def main():
                 line["extra"][kn] = json.loads(rows[-1]) if rows else {"error": f"exit {r.returncode}: {r.stderr.decode()[-300:]}"}
             except Exception as ex:
                 line.setdefault("extra", {})[kn] = {"error": repr(ex)[:300]}
+        try:
+            torch.cuda.empty_cache()
+            line["extra"]["udp_front_end"] = run_udp_front_end()
+        except Exception as ex:
+            line.setdefault("extra", {})["udp_front_end"] = {"error": repr(ex)[:300]}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
