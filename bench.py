@@ -528,6 +528,10 @@ def main():
         "config": {"workload": "lock_fasst REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(write)=0.2, closed-loop "
                                "FaSST clients (read/acquire/validate/commit), 36,000,000-slot table; "
                                f"{CLIENTS} logical clients per GPU, {ROUNDS_PER_STEP} rounds = {STEP_REQS} requests per step per GPU",
+                   "baseline_config": "BASELINE.json configs[1] (lock_fasst OCC validate/commit, 1 B200).  Its '4800 keys, "
+                                      "Zipf-0.8, 24M-op' wording is, in the reference, 4800 trace FILES, read fraction 0.8 and 24 M "
+                                      "uniform lock ids (BASELINE.md section 1 note, lock_fasst/caladan/trace_init.sh:9-27): the headline "
+                                      "runs that reference shape; the literal reading (4800 ids, Zipf 0.8) is extra.lock_fasst_HOT",
                    "requests_per_step": STEP_REQS * world, "chunk": args.chunk,
                    "cache": "every step replays a different 37.7 MB trace segment (inputs larger than reuse distance; "
                             "lock/version tables 148.5 MB > 126 MB L2)",
