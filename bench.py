@@ -380,6 +380,31 @@ def run_store_get(args, torch, rank, steps, warmup):
             "kernel_ms": {k: v[1] for k, v in kt.items()}}
 
 
+class DeferredCpuBaseline(threading.Thread):
+    """The unmodified reference shard server (oracle/_ref, replay shim, one handler thread) over a recorded request
+    stream, in the background: its table population takes most of a minute of host time, the GPU work goes on."""
+
+    def __init__(self, kind, req, txn_per_req, what):
+        super().__init__(daemon=True)
+        self.kind, self.req, self.txn_per_req, self.what = kind, req, txn_per_req, what
+        self.result = {"unavailable": "did not finish"}
+
+    def run(self):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            if not O.ref_available(self.kind):
+                self.result = {"unavailable": "oracle/_ref not built"}
+                return
+            t0 = time.time()
+            _, st = O.run_ref(self.kind, self.req, threads=1, repeat=1, want_out=False, timeout=400)
+            self.result = {"value": st["req_per_s"] * self.txn_per_req, "unit": "txn/s", "cores": 1, "kind": "reference",
+                           "req_per_s": st["req_per_s"], "sample": f"{self.what}: {st['requests']} requests in {st['seconds']:.2f} s "
+                           f"through oracle/_ref server_shard under the replay shim (population + replay {time.time() - t0:.0f} s wall)"}
+        except Exception as ex:
+            self.result = {"unavailable": repr(ex)[:200]}
+
+
 def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, clients=1 << 20):
     """Full transaction mixes driven by the reference's closed-loop client state machines
     (dint_b200/csrc/txn_workloads.cc) against THREE shard servers (primary key % 3 + 2 backups + log on all
@@ -415,6 +440,12 @@ def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, client
     st = wl.stats()
     for e in engs:
         e.close()
+    deferred = None
+    if rank == 0:                                          # shard 0's request stream from the start of the recording
+        sample = np.concatenate([np.ascontiguousarray(parts[0]).reshape(-1) for parts, _ in rec[: rounds_warm + 4]])
+        deferred = DeferredCpuBaseline(kind, sample, st["committed"] / max(1, st["requests"]),
+                                       f"shard 0's first {rounds_warm + 4} rounds of the recorded closed loop")
+        deferred.start()
     # device-resident replay from freshly populated shards
     engs = make()
     d = [[torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in parts] for parts, _ in rec]
@@ -449,7 +480,7 @@ def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, client
             "txn_per_s": tc / (ms * 1e-3), "requests_per_s": tr / (ms * 1e-3), "requests_per_txn": st["requests"] / max(1, st["txns"]),
             "commit_rate_by_type": {k: round(v[1] / max(1, v[0]), 4) for k, v in st["by_type"].items()},
             "replies_bit_exact": ok, "gpu_launches": launches, "conflicted_fraction": conflicted / max(1, tr),
-            "populate_s_per_3_shards": round(t_pop, 1)}
+            "populate_s_per_3_shards": round(t_pop, 1), "_deferred_cpu": deferred}
 
 
 def main():
@@ -584,6 +615,12 @@ def main():
             line["extra"]["udp_front_end"] = run_udp_front_end()
         except Exception as ex:
             line.setdefault("extra", {})["udp_front_end"] = {"error": repr(ex)[:300]}
+    for v in line.get("extra", {}).values():               # background CPU baselines: collect (bounded wait)
+        if isinstance(v, dict) and "_deferred_cpu" in v:
+            d = v.pop("_deferred_cpu")
+            if d is not None:
+                d.join(timeout=420)
+                v["cpu_baseline"] = d.result
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
