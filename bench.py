@@ -397,7 +397,7 @@ class DeferredCpuBaseline(threading.Thread):
                 self.result = {"unavailable": "oracle/_ref not built"}
                 return
             t0 = time.time()
-            _, st = O.run_ref(self.kind, self.req, threads=1, repeat=1, want_out=False, timeout=400)
+            _, st = O.run_ref(self.kind, self.req, threads=1, repeat=1, want_out=False, timeout=240)
             self.result = {"value": st["req_per_s"] * self.txn_per_req, "unit": "txn/s", "cores": 1, "kind": "reference",
                            "req_per_s": st["req_per_s"], "sample": f"{self.what}: {st['requests']} requests in {st['seconds']:.2f} s "
                            f"through oracle/_ref server_shard under the replay shim (population + replay {time.time() - t0:.0f} s wall)"}
@@ -619,7 +619,7 @@ def main():
         if isinstance(v, dict) and "_deferred_cpu" in v:
             d = v.pop("_deferred_cpu")
             if d is not None:
-                d.join(timeout=420)
+                d.join(timeout=120)
                 v["cpu_baseline"] = d.result
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
