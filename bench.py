@@ -352,8 +352,13 @@ def run_store_get(args, torch, rank, steps, warmup):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     n = 1 << 22
     wl = Workload(wire.STORE, n_clients=n, seed=1 + rank)
+    first = wl.next().copy()
+    deferred = None
+    if rank == 0:                                          # BASELINE.json configs[0]: the reference store server on the host CPU
+        deferred = DeferredCpuBaseline(wire.STORE, first, 1.0, "the first step of the GET trace")
+        deferred.start()
     with Engine(wire.STORE, device=dev.index, chunk=args.chunk, populate=True) as eng:
-        bufs = [torch.from_numpy(wl.next().copy()).to(dev) for _ in range(steps + warmup)]   # open-loop: no feedback needed
+        bufs = [torch.from_numpy(first).to(dev)] + [torch.from_numpy(wl.next().copy()).to(dev) for _ in range(steps + warmup - 1)]   # open-loop
         d_out = torch.empty_like(bufs[0])
         for s in range(warmup):
             eng.submit_tensor(bufs[s], d_out)
@@ -377,7 +382,7 @@ def run_store_get(args, torch, rank, steps, warmup):
             "get_per_s": n * steps / (ms * 1e-3), "hit_fraction_last_step": hits / n,
             "roofline": {"kernel": "k_apply<store>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "peak_source": how, "avg_launch_us": t / l * 1e3},
-            "kernel_ms": {k: v[1] for k, v in kt.items()}}
+            "kernel_ms": {k: v[1] for k, v in kt.items()}, "_deferred_cpu": deferred}
 
 
 class DeferredCpuBaseline(threading.Thread):
@@ -400,7 +405,7 @@ class DeferredCpuBaseline(threading.Thread):
             _, st = O.run_ref(self.kind, self.req, threads=1, repeat=1, want_out=False, timeout=240)
             self.result = {"value": st["req_per_s"] * self.txn_per_req, "unit": "txn/s", "cores": 1, "kind": "reference",
                            "req_per_s": st["req_per_s"], "sample": f"{self.what}: {st['requests']} requests in {st['seconds']:.2f} s "
-                           f"through oracle/_ref server_shard under the replay shim (population + replay {time.time() - t0:.0f} s wall)"}
+                           f"through the oracle/_ref server under the replay shim (population + replay {time.time() - t0:.0f} s wall)"}
         except Exception as ex:
             self.result = {"unavailable": repr(ex)[:200]}
 
