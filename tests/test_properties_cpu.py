@@ -44,3 +44,22 @@ def test_store_properties_on_the_oracle():
     srv = OracleServer(wire.STORE, subs_populate=500)
     keys = wire.as_records(wire.STORE, T.store_random(8000, 500, seed=4, p_set=0.0, p_miss=0.0))["key"].copy()
     assert P.store_read_your_writes(srv, keys, seed=5) == 8000
+
+
+def test_the_gpu_suites_exact_calls_hold_on_the_oracle_at_full_size():
+    """tests/test_gpu_properties.py, call for call (2^21 requests, 36 M slots, 24 M ids, the 24 M-key store), on the oracle:
+    whatever fails there on the GPU is then a parity bug of the engine, not a bug of the property."""
+    N = 1 << 21
+    srv = OracleServer(wire.FASST)
+    assert P.fasst_acquire_abort_roundtrip(srv, N, 24_000_000, seed=1) > N // 2
+    assert P.fasst_commit_checksum(srv, N, 24_000_000, seed=2) > N // 2
+    assert P.fasst_acquire_abort_roundtrip(srv, N, 4800, seed=3) <= 4800
+    assert P.fasst_commit_checksum(srv, N, 4800, seed=4) <= 3 * 4800
+    srv = OracleServer(wire.LOCK2PL)
+    assert P.lock2pl_counters_balance(srv, N, 24_000_000, seed=5) > N // 2
+    assert P.lock2pl_counters_balance(srv, N, 4800, seed=6) > 0
+    srv = OracleServer(wire.STORE, subs_populate=2_000_000)
+    keys = wire.as_records(wire.STORE, T.store_random(N, 2_000_000, seed=7, p_set=0.0, p_miss=0.0))["key"].copy()
+    assert P.store_read_your_writes(srv, keys, seed=8) == N
+    hot = wire.as_records(wire.STORE, T.store_random(N, 50, seed=9, p_set=0.0, p_miss=0.0))["key"].copy()
+    assert P.store_read_your_writes(srv, hot, seed=10) == N
