@@ -472,7 +472,12 @@ static int create_impl(dint_engine* e) {
       break;
     case DINT_FASST:
       groups = local_groups(cf.lock_slots);
+#ifdef DINT_VER16
+      if ((rc = dalloc(e, &c.ver16, groups))) return rc;
+      if ((rc = dalloc(e, &c.ver_hi, groups))) return rc;
+#else
       if ((rc = dalloc(e, &c.ver, groups))) return rc;     // lock bits: in the hot arena, below
+#endif
       break;
     case DINT_LOG:
       groups = 0;
@@ -887,7 +892,17 @@ int dint_lock_state(dint_engine* e, int table, uint32_t slot, uint32_t out[2]) {
     uint32_t w;
     CU(cudaMemcpy(&w, c.lockbits + (g >> 5), 4, cudaMemcpyDeviceToHost));
     out[0] = (w >> (g & 31)) & 1u;
+#ifdef DINT_VER16
+    if (e->kind == DINT_FASST) {
+      uint16_t lo = 0;
+      uint32_t hi = 0;
+      CU(cudaMemcpy(&lo, c.ver16 + g, 2, cudaMemcpyDeviceToHost));
+      if (lo & 0x8000u) CU(cudaMemcpy(&hi, c.ver_hi + g, 4, cudaMemcpyDeviceToHost));
+      out[1] = (lo & 0x7fffu) | (hi << 15);
+    }
+#else
     if (e->kind == DINT_FASST) CU(cudaMemcpy(&out[1], c.ver + g, 4, cudaMemcpyDeviceToHost));
+#endif
   }
   return DINT_OK;
 }

@@ -134,6 +134,10 @@ struct Ctx {
   unsigned long long* log_total;     // [2]: [0] appends before this chunk ... running total, [1] this chunk's total
   // bookkeeping
   unsigned long long* counters;   // [0] errors [1] conflicted [2] max_run
+#ifdef DINT_VER16
+  uint16_t* ver16;                // lock_fasst, experimental layout: low 15 bits of the version + flag 0x8000 "see ver_hi"
+  uint32_t* ver_hi;               //   high 17 bits, cold: read / written only for slots past 32767 commits
+#endif
   uint32_t* gbar;                 // k_ordered's grid barrier when it is not launched cooperatively
   uint32_t coop_launch;           // 1: k_ordered was launched cooperatively
 };
@@ -288,9 +292,31 @@ template <> DINT_D KeyInfo key_info<K_FASST>(const Ctx& c, const uint8_t* rec) {
   if (!to_local_group(c, fast_mod(k.h, c.slot_mod), k.grp)) k.grp = kNoGroup;   // :82
   return k;
 }
+// The version of a lock_fasst slot.  Default layout: `ver` u32 per slot (144 MB at 36 M slots: every READ is an HBM
+// sector for 4 bytes).  -DDINT_VER16 (experimental, not yet measured): a 16-bit hot array (72 MB, can stay in L2)
+// holding the low 15 bits and a flag; the high 17 bits live in a cold u32 array that only slots with more than
+// 32767 commits ever touch.  Exact for the whole u32 range (wrap included); 16-bit stores leave the neighbouring
+// slot alone, and a solo or replayed request owns its slot's version exclusively.
+DINT_D uint32_t ver_load(const Ctx& c, uint32_t g) {
+#ifdef DINT_VER16
+  const uint32_t lo = __ldcg(&c.ver16[g]);
+  return (lo & 0x8000u) ? ((lo & 0x7fffu) | (__ldcg(&c.ver_hi[g]) << 15)) : lo;
+#else
+  return __ldcg(&c.ver[g]);
+#endif
+}
+DINT_D void ver_store(const Ctx& c, uint32_t g, uint32_t v) {
+#ifdef DINT_VER16
+  const uint32_t hi = v >> 15;
+  if (hi) c.ver_hi[g] = hi;                              // (a stale ver_hi under a cleared flag is never read)
+  c.ver16[g] = (uint16_t)((v & 0x7fffu) | (hi ? 0x8000u : 0u));
+#else
+  c.ver[g] = v;
+#endif
+}
 template <> struct Pre<K_FASST> { uint32_t ver; };
 template <> DINT_D Pre<K_FASST> prefetch<K_FASST>(const Ctx& c, const uint8_t*, const KeyInfo& ki, const TypeInfo& ti) {
-  return Pre<K_FASST>{(ti.mask & (C_RA | C_WA)) ? __ldcg(&c.ver[ki.grp]) : 0u};
+  return Pre<K_FASST>{(ti.mask & (C_RA | C_WA)) ? ver_load(c, ki.grp) : 0u};
 }
 template <> DINT_D Pre<K_FASST> prefetch_coop<K_FASST>(const Ctx& c, const uint8_t* rec, const KeyInfo& ki, const TypeInfo& ti, bool active) {
   return active ? prefetch<K_FASST>(c, rec, ki, ti) : Pre<K_FASST>{0u};
@@ -310,7 +336,7 @@ DINT_D void apply_one<K_FASST>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, co
     bm_clear_bit(c.lockbits, g);
     rec[W::TYPE] = 7;
   } else {                                 // kCommit :109-114      ver++, CAS(1 -> 0)
-    c.ver[g] = pf.ver + 1;
+    ver_store(c, g, pf.ver + 1);
     bm_clear_bit(c.lockbits, g);
     rec[W::TYPE] = 8;
   }
@@ -322,10 +348,10 @@ template <> struct FastReplay<K_FASST> {
   struct State { uint32_t ver, lock, g; bool dirty_ver; };
   static DINT_D uint32_t load_op(const uint8_t* rec) { return rec[W::TYPE]; }
   static DINT_D State load_state(const Ctx& c, uint32_t g) {
-    return State{__ldcg(&c.ver[g]), (__ldcg(&c.lockbits[g >> 5]) >> (g & 31)) & 1u, g, false};
+    return State{ver_load(c, g), (__ldcg(&c.lockbits[g >> 5]) >> (g & 31)) & 1u, g, false};
   }
   static DINT_D void store_state(const Ctx& c, uint32_t g, const State& st) {
-    if (st.dirty_ver) c.ver[g] = st.ver;
+    if (st.dirty_ver) ver_store(c, g, st.ver);
     if (st.lock) bm_set(c.lockbits, g); else bm_clear_bit(c.lockbits, g);   // neighbours share the word: atomics
   }
   static DINT_D uint64_t step(State& st, uint32_t t) {               // lock_fasst/udp/server.cc:86-114
