@@ -149,3 +149,16 @@ def store_read_your_writes(server, keys, seed):
     assert np.array_equal(g1["val"], vals[last[inv]])
     assert np.array_equal((g1["ver"].astype(np.int64) - g0["ver"].astype(np.int64)) % (1 << 32), cnt[inv])
     return n
+
+
+def fasst_version_counts_commits(server, k, lid=12345):
+    """lock_fasst/udp/server.cc:92-114: [ACQUIRE, COMMIT] x k on ONE id inside ONE batch.  Sequential semantics grant
+    every acquire (the previous commit released the lock) and the version advances by exactly k -- across the 15-bit
+    boundary of the experimental 16-bit version layout when k > 32767."""
+    before = wire.as_records(wire.FASST, server.submit(fasst_records([Fasst.kRead], np.array([lid], dtype=np.uint32))))["ver"][0]
+    types = np.tile(np.array([Fasst.kAcquireLock, Fasst.kCommit], dtype=np.uint8), k)
+    r = wire.as_records(wire.FASST, server.submit(fasst_records(types, np.full(2 * k, lid, dtype=np.uint32))))
+    assert (r["type"][0::2] == Fasst.kGrantLock).all() and (r["type"][1::2] == Fasst.kCommitAck).all()
+    after = wire.as_records(wire.FASST, server.submit(fasst_records([Fasst.kRead], np.array([lid], dtype=np.uint32))))["ver"][0]
+    assert (int(after) - int(before)) % (1 << 32) == k
+    return int(after)

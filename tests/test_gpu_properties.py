@@ -36,6 +36,8 @@ def test_fasst_full_size_roundtrip_and_checksum():
         # and under heavy contention (the HOT shape: 4800 ids), where almost everything goes through the ordered path
         assert P.fasst_acquire_abort_roundtrip(srv, N, 4800, seed=3) <= 4800
         assert P.fasst_commit_checksum(srv, N, 4800, seed=4) <= 3 * 4800
+        if STRESS:                                       # 80,000 requests on one slot in one call; crosses 2^15 commits
+            assert P.fasst_version_counts_commits(srv, 40000) >= 40000
 
 
 def test_lock2pl_full_size_counters_balance():

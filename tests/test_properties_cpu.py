@@ -32,6 +32,7 @@ def test_fasst_properties_on_the_oracle(lock_slots, n_keys):
     srv = OracleServer(wire.FASST, lock_slots=lock_slots)
     assert P.fasst_acquire_abort_roundtrip(srv, 20000, n_keys, seed=1) > 0
     assert P.fasst_commit_checksum(srv, 20000, n_keys, seed=2) > 0
+    assert P.fasst_version_counts_commits(srv, 40000) >= 40000
 
 
 @pytest.mark.parametrize("lock_slots,n_keys", [(36000000, 24000000), (1009, 5000)])
