@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         nvcc = find_nvcc()
         if nvcc is None:
             raise RuntimeError("nvcc not found: cannot build libdint_b200.so (there is no CPU fallback)")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        # DINT_NVCC_DEFINES="-DDINT_TILE_TICKETS -DDINT_VER16": experimental variants; default: none
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DINT_NVCC_DEFINES", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
               ["-o", LIB, os.path.join(CSRC, "engine.cu")]
         subprocess.run(cmd, check=True)
     wl_src = [os.path.join(CSRC, "workloads.cc"), os.path.join(CSRC, "txn_workloads.cc")]

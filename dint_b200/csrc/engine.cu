@@ -557,6 +557,9 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.log_total, 2))) return rc;
   if ((rc = dalloc(e, &c.counters, 4))) return rc;
   if ((rc = dalloc(e, &c.gbar, 4))) return rc;
+#ifdef DINT_TILE_TICKETS
+  if ((rc = dalloc(e, &c.tickets, 4))) return rc;
+#endif
 
   switch (e->kind) {
     case DINT_LOCK2PL: rc = grids_for<K_LOCK2PL, false>(e); break;

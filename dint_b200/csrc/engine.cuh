@@ -138,6 +138,9 @@ struct Ctx {
   uint16_t* ver16;                // lock_fasst, experimental layout: low 15 bits of the version + flag 0x8000 "see ver_hi"
   uint32_t* ver_hi;               //   high 17 bits, cold: read / written only for slots past 32767 commits
 #endif
+#ifdef DINT_TILE_TICKETS
+  uint32_t* tickets;              // [0] k_classify's, [1] k_apply's tile ticket counter
+#endif
   uint32_t* gbar;                 // k_ordered's grid barrier when it is not launched cooperatively
   uint32_t coop_launch;           // 1: k_ordered was launched cooperatively
 };

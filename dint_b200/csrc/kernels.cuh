@@ -59,18 +59,52 @@ template <int MSG> struct Stage {
 
 // Persistent-CTA tile pipeline: CTA b owns tiles b, b + gridDim.x, ...; thread 0 keeps kStages - 1
 // TMA bulk loads in flight ahead of the tile being processed.
+//
+// -DDINT_TILE_TICKETS (experimental, not yet measured): tiles are handed out by a global ticket counter instead.
+// A statically striped persistent grid loses a whole wave when some of its CTAs cannot be resident next to another
+// stream's kernel (the multi-GPU step: engine 114 us instead of 62 next to a dispatch); with tickets the CTAs that
+// are resident simply take more tiles.  Thread 0 draws the ticket when it issues the load and publishes the tile
+// id in a shared-memory ring; the CTA barriers of the tile loop make it visible one iteration before it is used.
+#ifdef DINT_TILE_TICKETS
+constexpr uint32_t kNoTile = 0xffffffffu;
+struct TileIter {
+  uint32_t n_tiles, ns;
+  uint32_t* ctr;        // global ticket counter of this kernel (reset by the OTHER kernel of the K1 / K2 pair)
+  uint32_t* ring;       // shared memory, [ns]: tile id held by each pipeline stage, kNoTile = no more tiles
+  DINT_D uint32_t tile(uint32_t i) const { return ring[i % ns]; }
+  DINT_D bool has(uint32_t i) const { return ring[i % ns] != kNoTile; }
+  DINT_D bool may_issue(uint32_t) const { return true; }
+};
+DINT_D TileIter tile_iter(uint32_t n_tiles, uint32_t ns, uint32_t* ctr, uint32_t* ring) {
+  return TileIter{n_tiles, ns, ctr, ring};
+}
+#else
 struct TileIter {
   uint32_t n_my;        // tiles owned by this CTA
   DINT_D uint32_t tile(uint32_t i) const { return blockIdx.x + i * gridDim.x; }
+  DINT_D bool has(uint32_t i) const { return i < n_my; }
+  DINT_D bool may_issue(uint32_t i) const { return i < n_my; }
 };
 DINT_D TileIter tile_iter(uint32_t n_tiles) {
   TileIter it;
   it.n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   return it;
 }
+#endif
 template <int MSG>
 DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, const TileIter& it, uint32_t i) {
+#ifdef DINT_TILE_TICKETS
+  uint32_t t = kNoTile;
+  if (it.n_tiles) {                                      // (a flush launch has no tiles and must not touch the counter)
+    t = atomicAdd(it.ctr, 1u);
+    if (t >= it.n_tiles) t = kNoTile;
+  }
+  it.ring[i % it.ns] = t;
+  if (t == kNoTile) return;
+  const uint32_t first = t * kTile;
+#else
   const uint32_t t = it.tile(i), first = t * kTile;
+#endif
   const uint32_t cnt = min((uint32_t)kTile, c.n - first);
   const uint32_t body = (cnt * MSG) & ~15u;
   const uint32_t buf = i % Stage<MSG>::N;
@@ -274,9 +308,18 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     ordered_buckets<KIND>(c, smem);
     __syncthreads();
   }
+#ifdef DINT_TILE_TICKETS
+  __shared__ uint32_t s_ring[kStages];
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.tickets[1] = 0;          // K2 is not running: its counter is reset here
+  const TileIter it = tile_iter(c.n_tiles, NS, &c.tickets[0], s_ring);
+  if (threadIdx.x == 0)
+    for (uint32_t i = 0; i < NS; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+  __syncthreads();
+#else
   const TileIter it = tile_iter(c.n_tiles);
   if (threadIdx.x == 0)
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+#endif
 
   // retire the previous chunk's flags: every word it touched is zeroed (all of that set's nibbles
   // were written by that chunk, so whole-word stores are exact).  Loads are batched four deep so that
@@ -299,9 +342,9 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   uint32_t pend_old = 0, pend_test = 0, pend_sh = 0;
   uint32_t* pend_w = nullptr;
   bool saw_writer = false;          // any request of this CTA's tiles that writes A or L
-  for (uint32_t i = 0; i < it.n_my; i++) {
+  for (uint32_t i = 0; it.has(i); i++) {
     // the stage that held tile i-1 is free (barrier at the end of iteration i-1): refill it now
-    if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
+    if (threadIdx.x == 0 && i && it.may_issue(i + NS - 1)) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
     uint32_t first, cnt;
     const uint8_t* tile = acquire_tile<W::MSG>(c, smem, full, it, i, first, cnt);
     const bool valid = threadIdx.x < cnt;
@@ -403,21 +446,32 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
   if (threadIdx.x == 0)
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
   __syncthreads();
+#ifdef DINT_TILE_TICKETS
+  __shared__ uint32_t s_ring[kStages];
+  griddep_wait();                                        // (the ticket counter itself is K1's to reset: wait first)
+  griddep_launch();
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.tickets[0] = 0;          // K1 is not running: its counter is reset here
+  const TileIter it = tile_iter(c.n_tiles, NS, &c.tickets[1], s_ring);
+  if (threadIdx.x == 0)
+    for (uint32_t i = 0; i < NS; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+  __syncthreads();
+#else
   const TileIter it = tile_iter(c.n_tiles);
   if (threadIdx.x == 0)                                  // the request tiles do not depend on K1: their loads may start
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);   // before K1 has drained
   griddep_wait();                                        // flags, group ids, counters: K1's output
   griddep_launch();
+#endif
   const bool chunk_has_writer = c.nc_cur[2] != 0;      // set by K1; false = nothing in this chunk can conflict
 
-  for (uint32_t i = 0; i < it.n_my; i++) {
+  for (uint32_t i = 0; it.has(i); i++) {
     uint32_t* scratch = scratch2[i & 1];
     uint32_t g_k1 = kNoGroup;
     if (kGrpFromK1) {
       const uint32_t idx = it.tile(i) * kTile + threadIdx.x;
       if (idx < c.n) g_k1 = __ldcg(&c.grp[idx]);
     }
-    if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) {
+    if (threadIdx.x == 0 && i && it.may_issue(i + NS - 1)) {
       // the stage that held tile i-1 is refilled as soon as its bulk store has finished READING it
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
