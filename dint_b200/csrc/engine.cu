@@ -808,6 +808,42 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
   const uint8_t* rq = (const uint8_t*)req;
   uint8_t* rs = (uint8_t*)resp;
   unsigned long long err_before = e->stats.errors;
+  // DINT_HOST_ZEROCOPY=1 (experimental, not yet measured): no D2H stage -- the kernels store the replies straight
+  // into `resp` when it is pinned, device-mapped host memory (dint_host_alloc): the tiles leave K2 as bulk stores
+  // over PCIe while the next slice's H2D runs the other way, the replay patches its few records in place.
+  static const bool zero_copy = getenv("DINT_HOST_ZEROCOPY") != nullptr && atoi(getenv("DINT_HOST_ZEROCOPY")) == 1;
+  if (zero_copy && n && ((uintptr_t)resp & 15) == 0 && resp != req) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, resp) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      uint8_t* rs_dev = (uint8_t*)at.devicePointer;
+      uint64_t k = 0;
+      for (uint64_t off = 0; off < n; off += hchunk, k++) {       // slices of hchunk (a multiple of 128 records): every
+        const int b = (int)(k % kHostBufs);                        // slice of resp starts 16-byte aligned
+        const uint64_t cn = (n - off < hchunk) ? (n - off) : hchunk;
+        const size_t bytes = (size_t)cn * e->msg;
+        if (k >= (uint64_t)kHostBufs) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));      // slice k-kHostBufs replayed
+        CU(cudaMemcpyAsync(e->d_req[b], rq + off * e->msg, bytes, cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaEventRecord(e->ev_in[b], e->s_in));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+        int rc = submit_chunk(e, e->d_req[b], (uint32_t)cn, rs_dev + off * e->msg, e->stream);
+        if (rc) return rc;
+        if (k >= 1) CU(cudaEventRecord(e->ev_comp[(int)((k - 1) % kHostBufs)], e->stream));     // slice k-1 is final now
+        e->stats.h2d_bytes += bytes;
+        e->stats.d2h_bytes += bytes;
+      }
+      int rc = flush_ordered(e, e->stream);
+      if (rc) return rc;
+      if (!e->h_counters) CU(cudaHostAlloc((void**)&e->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+      CU(cudaMemcpyAsync(e->h_counters, e->ctx.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      if ((rc = prof_flush(e))) return rc;
+      e->stats.errors = e->h_counters[0];
+      e->stats.conflicted = e->h_counters[1];
+      e->stats.max_run = e->h_counters[2];
+      return e->stats.errors != err_before ? DINT_EPROTO : DINT_OK;
+    }
+    cudaGetLastError();                                    // not device-mapped host memory: the copying path below
+  }
   // three-stage pipeline: H2D (s_in) | kernels (stream) | D2H (s_out).  Slice k's replies are final only
   // after the launch that replays its listed requests -- K1 of slice k+1, or the flush after the last
   // slice -- so D2H(k) is ordered behind that.
