@@ -11,7 +11,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libdint_b200.so")
+# DINT_LIB_TAG=<tag> (development only, tools/variants.sh): load / build libdint_b200_<tag>.so, compiled with DINT_NVCC_DEFINES
+_TAG = os.environ.get("DINT_LIB_TAG", "")
+LIB = os.path.join(LIBDIR, f"libdint_b200_{_TAG}.so" if _TAG else "libdint_b200.so")
 WL_LIB = os.path.join(LIBDIR, "libdint_wl.so")
 UDP_SERVER = os.path.join(LIBDIR, "dint_udp_server")
 
@@ -47,7 +49,7 @@ def build(force=False, verbose=False):
         nvcc = find_nvcc()
         if nvcc is None:
             raise RuntimeError("nvcc not found: cannot build libdint_b200.so (there is no CPU fallback)")
-        # DINT_NVCC_DEFINES="-DDINT_TILE_TICKETS -DDINT_VER16": experimental variants; default: none
+        # DINT_NVCC_DEFINES: extra -D flags for A/B builds of a development variant (none exist at the moment)
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DINT_NVCC_DEFINES", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
               ["-o", LIB, os.path.join(CSRC, "engine.cu")]
         subprocess.run(cmd, check=True)

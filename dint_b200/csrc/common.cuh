@@ -227,11 +227,6 @@ DINT_D void tma_store_commit_and_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
-// Programmatic dependent launch (sm_90+): a kernel launched with programmaticStreamSerializationAllowed may start
-// while its predecessor in the stream still runs; griddep_wait() blocks until that predecessor has completed and
-// its writes are visible (a no-op for an ordinary launch), griddep_launch() lets the successor start early.
-DINT_D void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-DINT_D void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 DINT_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 #endif  // __CUDACC__

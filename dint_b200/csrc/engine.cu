@@ -2,6 +2,7 @@
 // host<->device pipelining for dint_submit(), state inspection, and the extern "C" ABI of
 // include/dint_b200.h.  No CPU implementation of the request path exists here: without a CUDA
 // device every compute entry point returns DINT_ENODEV.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,11 +56,12 @@ struct dint_engine {
   uint8_t* d_resp[kHostBufs] = {nullptr};
   cudaEvent_t ev_in[kHostBufs]{}, ev_comp[kHostBufs]{}, ev_out[kHostBufs]{};
   uint32_t host_chunk = 0;                   // requests per host-path slice
-  bool pdl = false;                          // DINT_PDL=1: programmatic dependent launches for K1 / K2 (experimental)
   bool plain_launches = false;               // inside the multi-GPU step: no cooperative launches (see GridBar)
   uint32_t host_min_slice = 0;               // smallest slice of the pyramid a host-path call is cut into
   bool host_ramp_up = true;
   unsigned long long* h_counters = nullptr;  // pinned mirror of ctx.counters (host path reads it without a blocking copy)
+  unsigned long long* h_kvcnt = nullptr;     // pinned mirror of every table's {live, used} (kv_maintain)
+  cudaEvent_t ev_kvcnt = nullptr;
   int coop_grid = 0;
   int sms = 0;
   int grid_classify = 0, grid_apply = 0;     // persistent CTAs (SMs x resident CTAs per SM)
@@ -71,6 +73,12 @@ struct dint_engine {
   uint32_t prev_n = 0;                       // requests of the previous chunk whose flags are still set
   bool ord_pending = false;                  // the previous chunk's listed requests await their replay
   uint8_t* ord_resp = nullptr;               //   ... and live in this reply array
+  const uint8_t* ord_req = nullptr;          //   ... their request bytes in this one
+  uint32_t ord_tile0 = 0;                    //   ... which starts at this tile of its batch
+  // segmented replies (multi-GPU step): set around run_device by the sharded step, zero otherwise
+  uint32_t seg_tiles = 0;
+  uint64_t seg_resp[kMaxShards]{};
+  bool pad_ok = false;
   uint32_t smem_classify = 0;                // K1: max(stages, ordered-replay slices)
   uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
   uint32_t* d_route = nullptr;               // multi-GPU dispatch scratch (per-tile per-shard counts)
@@ -150,11 +158,6 @@ static cudaError_t launch_ex(dint_engine* e, void (*kern)(Args...), int grid, in
   cudaLaunchAttribute at[3];
   int na = 0;
   if (coop) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
-  else if (e->pdl) {                                    // DINT_PDL=1: the launch may overlap its predecessor's tail
-    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[na].val.programmaticStreamSerializationAllowed = 1;
-    na++;
-  }
   if (e->use_window) { at[na].id = cudaLaunchAttributeAccessPolicyWindow; at[na].val.accessPolicyWindow = e->window; na++; }
   cfg.attrs = at;
   cfg.numAttrs = na;
@@ -188,6 +191,8 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
     Ctx f = c;           // this chunk's own counters / replies
     f.nc_ord = c.nc_cur;
     f.ord_resp = c.resp;
+    f.ord_req = c.req;
+    f.ord_tile0 = c.tile0;
     f.coop_launch = e->plain_launches ? 0u : 1u;
     int g3 = e->coop_grid;
     if (e->plain_launches && e->sms > 0) {             // leave room for the one-warp flag-polling kernels of the other streams
@@ -221,7 +226,6 @@ static int grids_for(dint_engine* e) {
     CU(cudaFuncSetAttribute(k_classify<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
     CU(cudaFuncSetAttribute(k_apply<KIND, HAS_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_stage));
   }
-  { const char* pad = getenv("DINT_APPLY_SMEM_PAD"); if (pad) e->smem_stage += (uint32_t)atoi(pad); }   // occupancy experiments
   e->smem_classify = e->smem_stage;
   if (KIND != K_LOG && (kTile / 32) * OrdSlice<KIND>::BYTES > e->smem_classify) e->smem_classify = (kTile / 32) * OrdSlice<KIND>::BYTES;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify<KIND, HAS_LOG>, kTile, e->smem_classify));
@@ -250,15 +254,21 @@ static void fill_chunk_ctx(dint_engine* e, Ctx& c) {
   c.nc_ord = e->d_nc + 4 * (cur ^ 1);
   c.ord_pending = e->ord_pending ? 1u : 0u;
   c.ord_resp = e->ord_resp;
+  c.ord_req = e->ord_req;
+  c.ord_tile0 = e->ord_tile0;
+  c.seg_tiles = e->seg_tiles;
+  c.pad_ok = e->pad_ok ? 1u : 0u;
+  for (int i = 0; i < kMaxShards; i++) c.seg_resp[i] = e->seg_resp[i];
 }
 
 // one chunk (n <= e->chunk); leaves its listed requests pending until the next chunk or flush_ordered()
-static int submit_chunk(dint_engine* e, const uint8_t* req, uint32_t n, uint8_t* resp, cudaStream_t s) {
+static int submit_chunk(dint_engine* e, const uint8_t* req, uint32_t n, uint8_t* resp, cudaStream_t s, uint32_t tile0 = 0) {
   Ctx c = e->ctx;
   c.n = n;
   c.n_tiles = (n + kTile - 1) / kTile;
   c.req = req;
   c.resp = resp;
+  c.tile0 = tile0;
   fill_chunk_ctx(e, c);
   int rc = launch_chunk(e, c, s);
   if (rc) return rc;
@@ -266,6 +276,8 @@ static int submit_chunk(dint_engine* e, const uint8_t* req, uint32_t n, uint8_t*
   e->prev_n = n;
   e->ord_pending = e->kind != DINT_LOG;
   e->ord_resp = resp;
+  e->ord_req = req;
+  e->ord_tile0 = tile0;
   e->stats.chunks++;
   e->stats.requests += n;
   return DINT_OK;
@@ -287,13 +299,64 @@ static int flush_ordered(dint_engine* e, cudaStream_t s) {
   return DINT_OK;
 }
 
+// Tombstone reclamation (kv.cuh): after every call the per-table {live, used} counters travel to a pinned mirror;
+// before the next call a table whose FULL + TOMB entries exceed 70 % of its capacity is rehashed into a fresh
+// array (doubled when the live keys alone exceed 35 %).  Synchronous and rare: at load <= 0.5 it takes an
+// insert / delete churn of 20 % of the capacity to get there.
+static int kv_maintain(dint_engine* e, cudaStream_t s) {
+  if (e->ctx.n_tables == 0) return DINT_OK;
+  if (!e->h_kvcnt) {
+    CU(cudaHostAlloc((void**)&e->h_kvcnt, 2 * kMaxTables * sizeof(unsigned long long), cudaHostAllocDefault));
+    memset(e->h_kvcnt, 0, 2 * kMaxTables * sizeof(unsigned long long));
+    CU(cudaEventCreateWithFlags(&e->ev_kvcnt, cudaEventDisableTiming));
+    return DINT_OK;
+  }
+  if (cudaEventQuery(e->ev_kvcnt) != cudaSuccess) { cudaGetLastError(); return DINT_OK; }   // mirror not refreshed yet
+  for (uint32_t t = 0; t < e->ctx.n_tables; t++) {
+    KvTable& T = e->ctx.tbl[t];
+    const unsigned long long live = e->h_kvcnt[2 * t], used = e->h_kvcnt[2 * t + 1];
+    const unsigned long long cap = T.cap_mask + 1;
+    if (used * 10 < cap * 7) continue;
+    KvTable N = T;
+    if (live * 20 > cap * 7) { N.cap_log2++; N.cap_mask = (1ULL << N.cap_log2) - 1; }
+    void* fresh = nullptr;
+    const size_t bytes = (size_t)(N.cap_mask + 1) << N.ent_shift;
+    CU(cudaMalloc(&fresh, bytes));
+    CU(cudaMemsetAsync(fresh, 0, bytes, s));
+    CU(cudaMemsetAsync(T.live, 0, 16, s));                   // the rehash re-counts both
+    N.entries = (uint8_t*)fresh;
+    {
+      ProfScope ps(e, s, KT_LOAD);
+      if (e->kind == DINT_SMALLBANK) k_kv_rehash<8><<<148 * 8, 256, 0, s>>>(T, N);
+      else k_kv_rehash<40><<<148 * 8, 256, 0, s>>>(T, N);
+    }
+    CU(cudaStreamSynchronize(s));
+    for (auto& p : e->allocs) if (p == (void*)T.entries) p = fresh;
+    CU(cudaFree(T.entries));
+    T = N;
+    e->kv[t].capacity = N.cap_mask + 1;
+    e->h_kvcnt[2 * t + 1] = live;
+    e->stats.kv_rebuilds++;
+  }
+  return DINT_OK;
+}
+static int kv_publish_counts(dint_engine* e, cudaStream_t s) {
+  if (e->ctx.n_tables == 0 || !e->h_kvcnt) return DINT_OK;
+  for (uint32_t t = 0; t < e->ctx.n_tables; t++)
+    CU(cudaMemcpyAsync(e->h_kvcnt + 2 * t, e->ctx.tbl[t].live, 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(e->ev_kvcnt, s));
+  return DINT_OK;
+}
+
 static int run_device(dint_engine* e, const uint8_t* req, uint64_t n, uint8_t* resp, cudaStream_t s) {
+  { int rc = kv_maintain(e, s); if (rc) return rc; }
   for (uint64_t off = 0; off < n; off += e->chunk) {
     uint32_t cn = (uint32_t)((n - off < e->chunk) ? (n - off) : e->chunk);
-    int rc = submit_chunk(e, req + off * e->msg, cn, resp + off * e->msg, s);
+    int rc = submit_chunk(e, req + off * e->msg, cn, resp ? resp + off * e->msg : nullptr, s, (uint32_t)(off / kTile));
     if (rc) return rc;
   }
-  return flush_ordered(e, s);
+  int rc = flush_ordered(e, s);
+  return rc ? rc : kv_publish_counts(e, s);
 }
 
 static int pull_counters(dint_engine* e) {
@@ -360,7 +423,7 @@ template <int KIND>
 static int route_dispatch_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) {
   using RT = RTile<Wire<KIND>::MSG>;
   if (!e->d_route2) {
-    { const char* g = getenv("DINT_ROUTE_GRID"); e->grid_route = g ? atoi(g) : 148 * 4; if (e->grid_route < 1) e->grid_route = 1; }
+    e->grid_route = 148 * 4;
     const size_t words = 16 + (size_t)(e->grid_route / 32 + 2) * kMaxShards + (size_t)e->grid_route * kMaxShards;
     CU(cudaMalloc(&e->d_route2, words * sizeof(uint32_t)));
     CU(cudaMemsetAsync(e->d_route2, 0, words * sizeof(uint32_t), s));
@@ -431,6 +494,8 @@ void dint_destroy(dint_engine* e) {
   if (e->d_route) cudaFree(e->d_route);
   if (e->d_route2) cudaFree(e->d_route2);
   if (e->h_counters) cudaFreeHost(e->h_counters);
+  if (e->h_kvcnt) cudaFreeHost(e->h_kvcnt);
+  if (e->ev_kvcnt) cudaEventDestroy(e->ev_kvcnt);
   for (auto& ep : e->ev_pool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
   for (int i = 0; i < kHostBufs; i++) {
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
@@ -472,12 +537,7 @@ static int create_impl(dint_engine* e) {
       break;
     case DINT_FASST:
       groups = local_groups(cf.lock_slots);
-#ifdef DINT_VER16
-      if ((rc = dalloc(e, &c.ver16, groups))) return rc;
-      if ((rc = dalloc(e, &c.ver_hi, groups))) return rc;
-#else
       if ((rc = dalloc(e, &c.ver, groups))) return rc;     // lock bits: in the hot arena, below
-#endif
       break;
     case DINT_LOG:
       groups = 0;
@@ -510,8 +570,7 @@ static int create_impl(dint_engine* e) {
     int max_persist = 0, max_win = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
     cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
-    const char* env = getenv("DINT_L2_PERSIST");
-    if ((!env || atoi(env) != 0) && max_persist > 0 && max_win > 0) {
+    if (max_persist > 0 && max_win > 0) {
       size_t want = e->hot_bytes < (size_t)max_persist ? e->hot_bytes : (size_t)max_persist;
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
         e->window.base_ptr = e->hot_arena;
@@ -522,8 +581,6 @@ static int create_impl(dint_engine* e) {
         e->use_window = true;
       } else cudaGetLastError();
     }
-    const char* g = getenv("DINT_L2_FETCH");
-    if (g) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); cudaGetLastError(); }
   }
   uint32_t bits = 1;
   while ((1ULL << bits) < groups) bits++;
@@ -557,9 +614,7 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.log_total, 2))) return rc;
   if ((rc = dalloc(e, &c.counters, 4))) return rc;
   if ((rc = dalloc(e, &c.gbar, 4))) return rc;
-#ifdef DINT_TILE_TICKETS
   if ((rc = dalloc(e, &c.tickets, 4))) return rc;
-#endif
 
   switch (e->kind) {
     case DINT_LOCK2PL: rc = grids_for<K_LOCK2PL, false>(e); break;
@@ -597,16 +652,11 @@ int dint_create(int kind, const dint_cfg* cfg, int device, dint_engine** out) {
   if (cf.chunk == 0) cf.chunk = 1u << 20;
   e->chunk = (cf.chunk + kTile - 1) / kTile * kTile;
   {
-    const char* hc = getenv("DINT_HOST_CHUNK");
-    uint32_t want = hc ? (uint32_t)atoi(hc) : (1u << 18);
-    if (want < (uint32_t)kTile) want = kTile;
-    e->host_chunk = want < e->chunk ? (want + kTile - 1) / kTile * kTile : e->chunk;
-    { const char* pd = getenv("DINT_PDL"); e->pdl = pd && atoi(pd) == 1; }
-    const char* ms = getenv("DINT_HOST_MIN_SLICE");
-    e->host_min_slice = ms ? (uint32_t)atoi(ms) : 131072u;
-    const char* ru = getenv("DINT_HOST_RAMP_UP");
-    e->host_ramp_up = ru ? atoi(ru) != 0 : true;
-    if (e->host_min_slice < (uint32_t)kTile) e->host_min_slice = kTile;
+    // host-path slice schedule (measured, tools/e2e_probe.py round 1: every schedule between 128 K and 1 M lands within 5 %)
+    const uint32_t want = 1u << 18;
+    e->host_chunk = want < e->chunk ? want : e->chunk;
+    e->host_min_slice = 131072u;
+    e->host_ramp_up = true;
   }
   e->msg = kMsgSize[kind];
   e->has_log = kLogEntry[kind] != 0;
@@ -805,45 +855,12 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
   static const bool trace = getenv("DINT_HOST_TRACE") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
   CU(cudaDeviceSynchronize());     // order after anything submitted on user streams
+  { int rc = kv_maintain(e, e->stream); if (rc) return rc; }
   const uint8_t* rq = (const uint8_t*)req;
   uint8_t* rs = (uint8_t*)resp;
   unsigned long long err_before = e->stats.errors;
-  // DINT_HOST_ZEROCOPY=1 (experimental, not yet measured): no D2H stage -- the kernels store the replies straight
-  // into `resp` when it is pinned, device-mapped host memory (dint_host_alloc): the tiles leave K2 as bulk stores
-  // over PCIe while the next slice's H2D runs the other way, the replay patches its few records in place.
-  static const bool zero_copy = getenv("DINT_HOST_ZEROCOPY") != nullptr && atoi(getenv("DINT_HOST_ZEROCOPY")) == 1;
-  if (zero_copy && n && ((uintptr_t)resp & 15) == 0 && resp != req) {
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, resp) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-      uint8_t* rs_dev = (uint8_t*)at.devicePointer;
-      uint64_t k = 0;
-      for (uint64_t off = 0; off < n; off += hchunk, k++) {       // slices of hchunk (a multiple of 128 records): every
-        const int b = (int)(k % kHostBufs);                        // slice of resp starts 16-byte aligned
-        const uint64_t cn = (n - off < hchunk) ? (n - off) : hchunk;
-        const size_t bytes = (size_t)cn * e->msg;
-        if (k >= (uint64_t)kHostBufs) CU(cudaStreamWaitEvent(e->s_in, e->ev_comp[b], 0));      // slice k-kHostBufs replayed
-        CU(cudaMemcpyAsync(e->d_req[b], rq + off * e->msg, bytes, cudaMemcpyHostToDevice, e->s_in));
-        CU(cudaEventRecord(e->ev_in[b], e->s_in));
-        CU(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
-        int rc = submit_chunk(e, e->d_req[b], (uint32_t)cn, rs_dev + off * e->msg, e->stream);
-        if (rc) return rc;
-        if (k >= 1) CU(cudaEventRecord(e->ev_comp[(int)((k - 1) % kHostBufs)], e->stream));     // slice k-1 is final now
-        e->stats.h2d_bytes += bytes;
-        e->stats.d2h_bytes += bytes;
-      }
-      int rc = flush_ordered(e, e->stream);
-      if (rc) return rc;
-      if (!e->h_counters) CU(cudaHostAlloc((void**)&e->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
-      CU(cudaMemcpyAsync(e->h_counters, e->ctx.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-      CU(cudaStreamSynchronize(e->stream));
-      if ((rc = prof_flush(e))) return rc;
-      e->stats.errors = e->h_counters[0];
-      e->stats.conflicted = e->h_counters[1];
-      e->stats.max_run = e->h_counters[2];
-      return e->stats.errors != err_before ? DINT_EPROTO : DINT_OK;
-    }
-    cudaGetLastError();                                    // not device-mapped host memory: the copying path below
-  }
+  // (Zero-copy replies -- K2 storing straight into pinned host memory instead of a D2H stage -- were measured in
+  // round 2 and dropped: 1.42 vs 1.73 G req/s at 2^20 requests per call, profiles/r02_variants.md.)
   // three-stage pipeline: H2D (s_in) | kernels (stream) | D2H (s_out).  Slice k's replies are final only
   // after the launch that replays its listed requests -- K1 of slice k+1, or the flush after the last
   // slice -- so D2H(k) is ordered behind that.
@@ -890,6 +907,7 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
   }
   if (!e->h_counters) CU(cudaHostAlloc((void**)&e->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
   CU(cudaMemcpyAsync(e->h_counters, e->ctx.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  { int rc2 = kv_publish_counts(e, e->stream); if (rc2) return rc2; }
   const auto t_enq = std::chrono::steady_clock::now();
   CU(cudaStreamSynchronize(e->s_out));
   CU(cudaStreamSynchronize(e->stream));
@@ -931,17 +949,7 @@ int dint_lock_state(dint_engine* e, int table, uint32_t slot, uint32_t out[2]) {
     uint32_t w;
     CU(cudaMemcpy(&w, c.lockbits + (g >> 5), 4, cudaMemcpyDeviceToHost));
     out[0] = (w >> (g & 31)) & 1u;
-#ifdef DINT_VER16
-    if (e->kind == DINT_FASST) {
-      uint16_t lo = 0;
-      uint32_t hi = 0;
-      CU(cudaMemcpy(&lo, c.ver16 + g, 2, cudaMemcpyDeviceToHost));
-      if (lo & 0x8000u) CU(cudaMemcpy(&hi, c.ver_hi + g, 4, cudaMemcpyDeviceToHost));
-      out[1] = (lo & 0x7fffu) | (hi << 15);
-    }
-#else
     if (e->kind == DINT_FASST) CU(cudaMemcpy(&out[1], c.ver + g, 4, cudaMemcpyDeviceToHost));
-#endif
   }
   return DINT_OK;
 }
@@ -1021,7 +1029,8 @@ int dint_load(dint_engine* e, int table, const uint64_t* keys, const void* vals,
   CU(cudaMalloc(&dk, batch * 8));
   cudaError_t ce = cudaMalloc(&dv, batch * vs);
   if (ce != cudaSuccess) { cudaFree(dk); return set_err(DINT_ENOMEM, "cudaMalloc", ce); }
-  int rc = DINT_OK;
+  int rc = pull_counters(e);                      // failures are counted in counters[0]: compare against its value NOW, not against 0
+  const unsigned long long err_before = e->stats.errors;
   for (uint64_t off = 0; off < n && rc == DINT_OK; off += batch) {
     uint64_t m = (n - off < batch) ? (n - off) : batch;
     if (cudaMemcpyAsync(dk, keys + off, m * 8, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
@@ -1038,9 +1047,11 @@ int dint_load(dint_engine* e, int table, const uint64_t* keys, const void* vals,
   cudaFree(dk);
   cudaFree(dv);
   if (rc == DINT_OK) {
+    kv_publish_counts(e, e->stream);
+    cudaStreamSynchronize(e->stream);
     int r2 = pull_counters(e);
     if (r2) return r2;
-    if (e->stats.errors) return set_err(DINT_ENOMEM, "KV table full during load");
+    if (e->stats.errors != err_before) return set_err(DINT_ENOMEM, "KV table full during load");
   }
   return rc;
 }
@@ -1069,76 +1080,216 @@ int64_t dint_kv_count(dint_engine* e, int table) {
   return (int64_t)v;
 }
 
-// ---- the whole sharded step over NVLink peer memory, driven from one host call -----------------------------
-// Three streams per rank: `side` partitions batch j+1 into the owners' inboxes while the caller's stream runs
-// the engine on batch j and `ret` pulls the replies of batch j-1 out of the owners' outboxes.  The only
-// cross-GPU synchronisation is three arrays of epoch words per rank (requests written / replies written /
-// replies read), n_sets buffer sets deep.
+}  // extern "C"
+
+// ---- the whole sharded step over NVLink peer memory ---------------------------------------------------------
+// A "rank" = one engine (one shard of the key space) with three streams: `side` partitions batch j+1 into the
+// OWNERS' inboxes (dispatch), the caller's stream runs the engine on batch j -- K2 stores every reply tile
+// straight into its SOURCE's return buffer (Ctx::seg_resp; posted stores over NVLink) -- and `ret` reassembles
+// the replies of batch j-1 from the local return buffer (combine).  Cross-GPU synchronisation: two arrays of
+// epoch words per rank (requests written / replies written; st.release.sys / ld.acquire.sys, bounded spin);
+// buffer reuse needs no third flag: a source re-fills inbox set s only after its combine of the batch that used
+// it, i.e. after every owner's "replies written", and an owner re-fills return-buffer set s only after the
+// source's next dispatch into that set arrived, which the source ordered behind its combine.
+// Ranks may live in different processes (one per GPU, buffers mapped through CUDA IPC / torch symmetric memory:
+// dint_shard_*) or in ONE process (dint_cluster_*: cudaMalloc + peer access; several ranks may even share a
+// device, then everything runs on one stream in dependency order).
+constexpr int kMaxSets = 4;
 struct dint_shard_ctx {
   dint_engine* e = nullptr;
   uint32_t W = 0, me = 0, cap = 0, S = 0;
-  uint64_t inbox[4][kMaxShards]{}, outbox[4][kMaxShards]{}, retbox[4][kMaxShards]{};
-  bool push = false;                       // DINT_SHARD_PUSH=1 and return buffers given: owners push the replies
-  cudaEvent_t ev_eng[4]{};
-  PeerPtrs sigreq{}, sigrsp{}, sigdone{};
-  uint32_t *my_req = nullptr, *my_rsp = nullptr, *my_done = nullptr;
+  uint64_t inbox[kMaxSets][kMaxShards]{}, retbox[kMaxSets][kMaxShards]{};
+  PeerPtrs sigreq{}, sigrsp{};
+  uint32_t *my_req = nullptr, *my_rsp = nullptr;
   uint32_t epoch = 0;
-  cudaStream_t side = nullptr, ret = nullptr;
-  cudaEvent_t ev_disp[4]{}, ev_comb[4]{}, ev_fork = nullptr;
-  uint8_t* owner[4]{};
-  uint32_t* tilebase[4]{};
+  cudaStream_t side = nullptr, ret = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_disp[kMaxSets]{}, ev_comb[kMaxSets]{}, ev_fork = nullptr;
+  cudaEvent_t ev_h2d[kMaxSets]{}, ev_d2h[kMaxSets]{};
+  uint8_t* owner[kMaxSets]{};
+  uint32_t* tilebase[kMaxSets]{};
+  uint8_t *st_req[kMaxSets]{}, *st_dst[kMaxSets]{}, *st_out[kMaxSets]{};   // host-path staging (allocated on first use)
   uint32_t* flags = nullptr;
   uint64_t max_n = 0;
-  bool three_streams = true;               // DINT_SHARD_STREAMS=1: everything on the caller's stream
+  bool one_stream = false;                 // ranks sharing a device: dispatch, engine and combine on ONE stream, in dependency order
   bool trace = false;                      // DINT_SHARD_TRACE: per-phase CUDA-event timing, printed at destroy
-  std::vector<cudaEvent_t> tev;            // 9 events per batch
-  double tsum[8]{};
+  std::vector<cudaEvent_t> tev;            // 6 events per batch
+  double tsum[4]{};
   uint64_t tcount = 0;
 };
 
-int dint_shard_create(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets, const dint_peer_ptrs* inbox_sets,
-                      const dint_peer_ptrs* outbox_sets, const dint_peer_ptrs* retbox_sets, const dint_peer_ptrs* sig_blocks, uint64_t max_n,
+static int shard_make(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets, const dint_peer_ptrs* inbox_sets,
+                      const dint_peer_ptrs* retbox_sets, const dint_peer_ptrs* sig_blocks, uint64_t max_n, bool one_stream,
                       dint_shard_ctx** out) {
-  if (!e || !out || !inbox_sets || !outbox_sets || !sig_blocks || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 ||
-      n_sets < 2 || n_sets > 4 || max_n == 0 || max_n > 0xffffffffULL)
-    return set_err(DINT_EINVAL, "bad argument");
+  if (!e || !out || !inbox_sets || !retbox_sets || !sig_blocks || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 ||
+      cap % kTile != 0 || n_sets < 2 || n_sets > (uint32_t)kMaxSets || max_n == 0 || max_n > 0xffffffffULL)
+    return set_err(DINT_EINVAL, "bad argument (cap must be a multiple of 128, 2 <= n_sets <= 4)");
   CU(cudaSetDevice(e->device));
   dint_shard_ctx* c = new dint_shard_ctx();
   e->plain_launches = true;
-  c->e = e; c->W = n_shards; c->me = rank; c->cap = cap; c->S = n_sets; c->max_n = max_n;
+  c->e = e; c->W = n_shards; c->me = rank; c->cap = cap; c->S = n_sets; c->max_n = max_n; c->one_stream = one_stream;
   for (uint32_t s = 0; s < n_sets; s++)
     for (uint32_t o = 0; o < n_shards; o++) {
       c->inbox[s][o] = inbox_sets[s].p[o];
-      c->outbox[s][o] = outbox_sets[s].p[o];
-      c->retbox[s][o] = retbox_sets ? retbox_sets[s].p[o] : 0;
+      c->retbox[s][o] = retbox_sets[s].p[o];
     }
   for (uint32_t o = 0; o < n_shards; o++) {
     c->sigreq.p[o] = sig_blocks->p[o];
     c->sigrsp.p[o] = sig_blocks->p[o] + 64;
-    c->sigdone.p[o] = sig_blocks->p[o] + 128;
   }
   c->my_req = (uint32_t*)sig_blocks->p[rank];
   c->my_rsp = (uint32_t*)(sig_blocks->p[rank] + 64);
-  c->my_done = (uint32_t*)(sig_blocks->p[rank] + 128);
-  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->ret, cudaStreamNonBlocking));
+  if (!one_stream) {
+    CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->ret, cudaStreamNonBlocking));
+  }
+  CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   const uint32_t tr = route_tile_records(e);
   const size_t tiles = (size_t)((max_n + tr - 1) / tr);
   for (uint32_t s = 0; s < n_sets; s++) {
     CU(cudaEventCreateWithFlags(&c->ev_disp[s], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_comb[s], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_eng[s], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_d2h[s], cudaEventDisableTiming));
     CU(cudaMalloc(&c->owner[s], max_n + 16));
     CU(cudaMalloc(&c->tilebase[s], tiles * kMaxShards * sizeof(uint32_t)));
   }
   CU(cudaMalloc(&c->flags, 2 * sizeof(uint32_t)));
   CU(cudaMemset(c->flags, 0, 2 * sizeof(uint32_t)));
   c->trace = getenv("DINT_SHARD_TRACE") != nullptr;
-  { const char* ps = getenv("DINT_SHARD_PUSH"); c->push = retbox_sets && ps && atoi(ps) == 1 && ((size_t)cap * e->msg) % 16 == 0; }
-  { const char* ts = getenv("DINT_SHARD_STREAMS"); c->three_streams = !ts || atoi(ts) == 3; }
   *out = c;
   return DINT_OK;
+}
+
+// ---- the three phases of one batch on one rank (all asynchronous) -------------------------------------------
+static void shard_mark(dint_shard_ctx* c, uint32_t slot, int which, cudaStream_t st) {
+  if (!c->trace) return;
+  const size_t need = (size_t)6 * (slot + 1);
+  while (c->tev.size() < need) { cudaEvent_t ev; cudaEventCreate(&ev); c->tev.push_back(ev); }
+  cudaEventRecord(c->tev[(size_t)6 * slot + which], st);
+}
+// dispatch: partition n records of this rank into the owners' inbox set (epoch ep)
+static int shard_dispatch(dint_shard_ctx* c, uint32_t slot, uint32_t ep, const void* req_dev, const uint8_t* dst_dev, uint64_t n, cudaStream_t st) {
+  dint_engine* e = c->e;
+  CU(cudaSetDevice(e->device));
+  const uint32_t s = ep % c->S;
+  const size_t slab = (size_t)c->cap * e->msg;
+  if (ep > c->S && !c->one_stream) CU(cudaStreamWaitEvent(st, c->ev_comb[s], 0));   // my combine of batch ep - S: every owner is done with inbox set s
+  shard_mark(c, slot, 0, st);
+  dint_peer_ptrs in{}, sg{};
+  for (uint32_t o = 0; o < c->W; o++) { in.p[o] = c->inbox[s][o] + (uint64_t)c->me * slab; sg.p[o] = c->sigreq.p[o]; }
+  int rc = dint_route_dispatch(e, req_dev, dst_dev, n, c->W, c->me, c->cap, &in, &sg, ep, c->owner[s], c->tilebase[s], c->flags, st);
+  if (rc) return rc;
+  shard_mark(c, slot, 1, st);
+  if (!c->one_stream) CU(cudaEventRecord(c->ev_disp[s], st));
+  return DINT_OK;
+}
+// engine: this rank's shard serves inbox set (epoch ep); every reply tile goes to its source's return buffer
+static int shard_engine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, cudaStream_t st) {
+  dint_engine* e = c->e;
+  CU(cudaSetDevice(e->device));
+  const uint32_t s = ep % c->S;
+  const size_t slab = (size_t)c->cap * e->msg;
+  k_p2p_wait<<<1, 32, 0, st>>>(c->my_req, c->W, ep, c->flags + 1);                    // every source's slab has arrived
+  shard_mark(c, slot, 2, st);
+  e->seg_tiles = c->cap / kTile;
+  e->pad_ok = true;
+  for (uint32_t r = 0; r < c->W; r++) e->seg_resp[r] = c->retbox[s][r] + (uint64_t)c->me * slab;   // my slab inside source r's return buffer
+  int rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)c->W * c->cap, nullptr, st);
+  e->seg_tiles = 0;
+  e->pad_ok = false;
+  if (rc) return rc;
+  k_p2p_signal<<<1, 32, 0, st>>>(c->sigrsp, c->W, c->me, ep);
+  shard_mark(c, slot, 3, st);
+  e->stats.kernel_launches += 2;
+  return DINT_OK;
+}
+// combine: the replies of batch ep are in my return-buffer set; put them back in request order
+static int shard_combine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, void* out_dev, uint64_t n, cudaStream_t st) {
+  dint_engine* e = c->e;
+  CU(cudaSetDevice(e->device));
+  const uint32_t s = ep % c->S;
+  const size_t slab = (size_t)c->cap * e->msg;
+  if (!c->one_stream) CU(cudaStreamWaitEvent(st, c->ev_disp[s], 0));
+  k_p2p_wait<<<1, 32, 0, st>>>(c->my_rsp, c->W, ep, c->flags + 1);
+  shard_mark(c, slot, 4, st);
+  dint_peer_ptrs rb{};
+  for (uint32_t o = 0; o < c->W; o++) rb.p[o] = c->retbox[s][c->me] + (uint64_t)o * slab;
+  int rc = dint_route_combine(e, &rb, c->owner[s], c->tilebase[s], n, c->W, c->cap, out_dev, st);
+  if (rc) return rc;
+  shard_mark(c, slot, 5, st);
+  if (!c->one_stream) CU(cudaEventRecord(c->ev_comb[s], st));
+  e->stats.kernel_launches += 1;
+  return DINT_OK;
+}
+static void shard_trace_collect(dint_shard_ctx* c, uint32_t k) {
+  if (!c->trace) return;
+  cudaSetDevice(c->e->device);
+  cudaDeviceSynchronize();
+  static const int pairs[4][2] = {{0, 1}, {2, 3}, {4, 5}, {0, 5}};
+  for (uint32_t j = 0; j < k && (size_t)6 * (j + 1) <= c->tev.size(); j++)
+    for (int q = 0; q < 4; q++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, c->tev[(size_t)6 * j + pairs[q][0]], c->tev[(size_t)6 * j + pairs[q][1]]) == cudaSuccess) c->tsum[q] += ms;
+    }
+  c->tcount += k;
+}
+
+// One pipelined sequence of k batches over the ranks of THIS process (1 in the one-process-per-GPU deployment,
+// G in a cluster).  Host enqueue order per batch: every rank's dispatch of j+1, every rank's engine of j, every
+// rank's combine of j (of j-1 when the ranks share one stream) -- each phase only waits for phases enqueued
+// before it, on this or another GPU, so one host thread can drive all ranks without blocking.
+struct ShardBatch { const void* req; const uint8_t* dst; void* out; uint64_t n; };
+static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const std::vector<std::vector<ShardBatch>>& b, cudaStream_t const* mains) {
+  if (k == 0) return DINT_OK;
+  const bool one = ranks[0]->one_stream;
+  const uint32_t lag = one ? 1u : 0u;
+  for (uint32_t r = 0; r < R; r++) {
+    dint_shard_ctx* c = ranks[r];
+    if (one) continue;
+    CU(cudaSetDevice(c->e->device));
+    CU(cudaEventRecord(c->ev_fork, mains[r]));
+    CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    CU(cudaStreamWaitEvent(c->ret, c->ev_fork, 0));
+  }
+  auto side = [&](uint32_t r) { return one ? mains[r] : ranks[r]->side; };
+  auto retS = [&](uint32_t r) { return one ? mains[r] : ranks[r]->ret; };
+  int rc;
+  for (uint32_t r = 0; r < R; r++)
+    if ((rc = shard_dispatch(ranks[r], 0, ranks[r]->epoch + 1, b[r][0].req, b[r][0].dst, b[r][0].n, side(r)))) return rc;
+  for (uint32_t j = 0; j < k; j++) {
+    if (j + 1 < k)
+      for (uint32_t r = 0; r < R; r++)
+        if ((rc = shard_dispatch(ranks[r], j + 1, ranks[r]->epoch + 2 + j, b[r][j + 1].req, b[r][j + 1].dst, b[r][j + 1].n, side(r)))) return rc;
+    for (uint32_t r = 0; r < R; r++)
+      if ((rc = shard_engine(ranks[r], j, ranks[r]->epoch + 1 + j, mains[r]))) return rc;
+    if (j >= lag)
+      for (uint32_t r = 0; r < R; r++)
+        if ((rc = shard_combine(ranks[r], j - lag, ranks[r]->epoch + 1 + j - lag, b[r][j - lag].out, b[r][j - lag].n, retS(r)))) return rc;
+  }
+  for (uint32_t j = k - (lag < k ? lag : k); j < k; j++)
+    for (uint32_t r = 0; r < R; r++)
+      if ((rc = shard_combine(ranks[r], j, ranks[r]->epoch + 1 + j, b[r][j].out, b[r][j].n, retS(r)))) return rc;
+  for (uint32_t r = 0; r < R; r++) {
+    dint_shard_ctx* c = ranks[r];
+    const uint32_t last = c->epoch + k;
+    c->epoch = last;
+    if (one) continue;
+    CU(cudaSetDevice(c->e->device));
+    for (uint32_t s = 0; s < c->S && s < k; s++) CU(cudaStreamWaitEvent(mains[r], c->ev_comb[(last - s) % c->S], 0));   // join
+    CU(cudaStreamWaitEvent(mains[r], c->ev_disp[last % c->S], 0));
+  }
+  CU(cudaGetLastError());
+  for (uint32_t r = 0; r < R; r++) shard_trace_collect(ranks[r], k);
+  return DINT_OK;
+}
+
+extern "C" {
+
+int dint_shard_create(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets, const dint_peer_ptrs* inbox_sets,
+                      const dint_peer_ptrs* retbox_sets, const dint_peer_ptrs* sig_blocks, uint64_t max_n, dint_shard_ctx** out) {
+  return shard_make(e, n_shards, rank, cap, n_sets, inbox_sets, retbox_sets, sig_blocks, max_n, false, out);
 }
 
 void dint_shard_destroy(dint_shard_ctx* c) {
@@ -1146,24 +1297,30 @@ void dint_shard_destroy(dint_shard_ctx* c) {
   cudaSetDevice(c->e->device);
   cudaDeviceSynchronize();
   if (c->trace && c->tcount) {
-    static const char* names[8] = {"side: wait inbox free", "side: dispatch", "main: wait requests", "main: engine + signal",
-                                   "ret: wait replies", "ret: combine + signal", "batch: dispatch start -> combine end", "main: total"};
+    static const char* names[4] = {"dispatch", "engine", "combine", "dispatch start -> combine end"};
     fprintf(stderr, "[dint_shard rank %u] %llu batches, us per batch:", c->me, (unsigned long long)c->tcount);
-    for (int q = 0; q < 8; q++) fprintf(stderr, " | %s %.1f", names[q], c->tsum[q] * 1e3 / (double)c->tcount);
+    for (int q = 0; q < 4; q++) fprintf(stderr, " | %s %.1f", names[q], c->tsum[q] * 1e3 / (double)c->tcount);
     fprintf(stderr, "\n");
   }
   for (cudaEvent_t ev : c->tev) cudaEventDestroy(ev);
   for (uint32_t s = 0; s < c->S; s++) {
     if (c->ev_disp[s]) cudaEventDestroy(c->ev_disp[s]);
     if (c->ev_comb[s]) cudaEventDestroy(c->ev_comb[s]);
-    if (c->ev_eng[s]) cudaEventDestroy(c->ev_eng[s]);
+    if (c->ev_h2d[s]) cudaEventDestroy(c->ev_h2d[s]);
+    if (c->ev_d2h[s]) cudaEventDestroy(c->ev_d2h[s]);
     if (c->owner[s]) cudaFree(c->owner[s]);
     if (c->tilebase[s]) cudaFree(c->tilebase[s]);
+    if (c->st_req[s]) cudaFree(c->st_req[s]);
+    if (c->st_dst[s]) cudaFree(c->st_dst[s]);
+    if (c->st_out[s]) cudaFree(c->st_out[s]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->flags) cudaFree(c->flags);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ret) cudaStreamDestroy(c->ret);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  c->e->plain_launches = false;
   delete c;
 }
 
@@ -1179,111 +1336,251 @@ int dint_shard_flags(dint_shard_ctx* c, uint32_t out[2]) {
 int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req_dev, const uint8_t* const* dst_dev, uint64_t n,
                            void* const* out_dev, void* cuda_stream) {
   if (!c || !req_dev || !out_dev || n == 0 || n > c->max_n) return set_err(DINT_EINVAL, "bad argument");
-  dint_engine* e = c->e;
-  CU(cudaSetDevice(e->device));
+  if (k == 0) return DINT_OK;
+  std::vector<std::vector<ShardBatch>> b(1, std::vector<ShardBatch>(k));
+  for (uint32_t j = 0; j < k; j++) b[0][j] = ShardBatch{req_dev[j], dst_dev ? dst_dev[j] : nullptr, out_dev[j], n};
   cudaStream_t main = (cudaStream_t)cuda_stream;
-  // Default: dispatch, engine and combine on three streams.  DINT_SHARD_STREAMS=1 issues everything on the
-  // caller's stream in the order D(j+1) E(j) C(j-1) (each cross-GPU wait then has a whole batch of slack and the
-  // SM-filling kernels never compete); measured on 2 GPUs: 177 us per 2^20-request batch against 148 us for the
-  // three streams, although the kernels of the three streams slow each other down (engine 114 us vs 86).
-  const bool one_stream = !c->three_streams;
-  cudaStream_t side = one_stream ? main : c->side, ret = one_stream ? main : c->ret;
-  const uint32_t lag = one_stream ? 1u : 0u;
-  const uint32_t W = c->W, S = c->S;
-  const size_t slab = (size_t)c->cap * e->msg;
-  if (!one_stream) {
-    CU(cudaEventRecord(c->ev_fork, main));
-    CU(cudaStreamWaitEvent(side, c->ev_fork, 0));
-    CU(cudaStreamWaitEvent(ret, c->ev_fork, 0));
-  }
-  if (c->trace && c->tev.size() < (size_t)9 * k) {
-    const size_t old = c->tev.size();
-    c->tev.resize((size_t)9 * k);
-    for (size_t i = old; i < c->tev.size(); i++) CU(cudaEventCreate(&c->tev[i]));
-  }
-  auto mark = [&](uint32_t j, int which, cudaStream_t st) { if (c->trace) cudaEventRecord(c->tev[(size_t)9 * j + which], st); };
-  auto dispatch = [&](uint32_t j, uint32_t ep) -> int {
-    const uint32_t s = ep % S;
-    mark(j, 0, side);
-    if (ep > S && !one_stream) {                                                // (one stream: both hold by program order)
-      k_p2p_wait<<<1, 32, 0, side>>>(c->my_rsp, W, ep - S, c->flags + 1);       // every owner has consumed inbox set s
-      CU(cudaStreamWaitEvent(side, c->ev_comb[s], 0));                          // and my combine is done with its state
-    }
-    mark(j, 1, side);
-    dint_peer_ptrs in{}, sg{};
-    for (uint32_t o = 0; o < W; o++) { in.p[o] = c->inbox[s][o] + (uint64_t)c->me * slab; sg.p[o] = c->sigreq.p[o]; }
-    int rc = dint_route_dispatch(e, req_dev[j], dst_dev ? dst_dev[j] : nullptr, n, W, c->me, c->cap, &in, &sg, ep, c->owner[s],
-                                 c->tilebase[s], c->flags, side);
-    if (rc) return rc;
-    mark(j, 2, side);
-    if (!one_stream) CU(cudaEventRecord(c->ev_disp[s], side));
-    return DINT_OK;
-  };
-  auto combine = [&](uint32_t j, uint32_t ep) -> int {     // the replies of batch j come home
-    const uint32_t s = ep % S;
-    if (!one_stream) CU(cudaStreamWaitEvent(ret, c->ev_disp[s], 0));
-    mark(j, 6, ret);
-    if (c->push) {                                         // my replies to the other sources go out first, then the flag
-      if (!one_stream) CU(cudaStreamWaitEvent(ret, c->ev_eng[s], 0));
-      if (W > 1) {
-        PeerPtrs rb{};
-        for (uint32_t o = 0; o < W; o++) rb.p[o] = c->retbox[s][o];
-        const uint32_t slab16 = (uint32_t)(slab / 16);
-        k_push_slabs<<<148 * 2, kThreads, 0, ret>>>((const uint8_t*)c->outbox[s][c->me], rb, W, c->me, slab16);
-      }
-      k_p2p_signal<<<1, 32, 0, ret>>>(c->sigrsp, W, c->me, ep);
-    }
-    k_p2p_wait<<<1, 32, 0, ret>>>(c->my_rsp, W, ep, c->flags + 1);
-    mark(j, 7, ret);
-    dint_peer_ptrs ob{};
-    for (uint32_t o = 0; o < W; o++)
-      ob.p[o] = c->push ? (o == c->me ? c->outbox[s][c->me] + (uint64_t)c->me * slab : c->retbox[s][c->me] + (uint64_t)o * slab)
-                        : c->outbox[s][o] + (uint64_t)c->me * slab;
-    int rc = dint_route_combine(e, &ob, c->owner[s], c->tilebase[s], n, W, c->cap, out_dev[j], ret);
-    if (rc) return rc;
-    k_p2p_signal<<<1, 32, 0, ret>>>(c->sigdone, W, c->me, ep);
-    mark(j, 8, ret);
-    if (!one_stream) CU(cudaEventRecord(c->ev_comb[s], ret));
-    return DINT_OK;
-  };
-  uint32_t ep0 = c->epoch;
-  int rc = dispatch(0, ep0 + 1);
-  if (rc) return rc;
-  for (uint32_t j = 0; j < k; j++) {
-    const uint32_t ep = ep0 + 1 + j, s = ep % S;
-    if (j + 1 < k && (rc = dispatch(j + 1, ep + 1))) return rc;
-    // the engine sees the batches in order
-    mark(j, 3, main);
-    k_p2p_wait<<<1, 32, 0, main>>>(c->my_req, W, ep, c->flags + 1);                    // every source's slab has arrived
-    if (ep > S) k_p2p_wait<<<1, 32, 0, main>>>(c->my_done, W, ep - S, c->flags + 1);   // outbox set s has been read
-    mark(j, 4, main);
-    rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)W * c->cap, (uint8_t*)c->outbox[s][c->me], main);
-    if (rc) return rc;
-    if (!c->push) k_p2p_signal<<<1, 32, 0, main>>>(c->sigrsp, W, c->me, ep);
-    else if (!one_stream) CU(cudaEventRecord(c->ev_eng[s], main));
-    mark(j, 5, main);
-    if (j >= lag && (rc = combine(j - lag, ep - lag))) return rc;
-    e->stats.kernel_launches += 5;
-  }
-  for (uint32_t j = k - (lag < k ? lag : k); j < k; j++)
-    if ((rc = combine(j, ep0 + 1 + j))) return rc;
-  c->epoch = ep0 + k;
-  if (!one_stream) {
-    for (uint32_t s = 0; s < S; s++) CU(cudaStreamWaitEvent(main, c->ev_comb[s], 0));   // join
-    CU(cudaStreamWaitEvent(main, c->ev_disp[(ep0 + k) % S], 0));
-  }
-  CU(cudaGetLastError());
-  if (c->trace) {                                        // diagnostic mode: synchronises
-    CU(cudaStreamSynchronize(main));
-    static const int pairs[8][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {6, 7}, {7, 8}, {0, 8}, {3, 5}};
-    for (uint32_t j = 0; j < k; j++)
-      for (int q = 0; q < 8; q++) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->tev[(size_t)9 * j + pairs[q][0]], c->tev[(size_t)9 * j + pairs[q][1]]) == cudaSuccess) c->tsum[q] += ms;
-      }
-    c->tcount += k;
+  return shard_run(&c, 1, k, b, &main);
+}
+
+}  // extern "C"
+
+// ---- host buffers through the sharded step: H2D | dispatch | engine | combine | D2H, S sets deep ---------------------
+// (what a transport front-end calls at N > 1: the same slice ring as dint_submit, with the exchange in the middle)
+static int shard_staging(dint_shard_ctx* c) {
+  if (c->st_req[0]) return DINT_OK;
+  CU(cudaSetDevice(c->e->device));
+  for (uint32_t s = 0; s < c->S; s++) {
+    CU(cudaMalloc(&c->st_req[s], c->max_n * c->e->msg + 16));
+    CU(cudaMalloc(&c->st_dst[s], c->max_n + 16));
+    CU(cudaMalloc(&c->st_out[s], c->max_n * c->e->msg + 16));
   }
   return DINT_OK;
+}
+struct HostBatch { const uint8_t* req; const uint8_t* dst; uint8_t* out; uint64_t n; };
+// k batches per rank from / to HOST memory.  Batches are processed in groups of S (one per buffer set): the copies of
+// a group overlap the exchange of the same group, the groups follow each other on the streams without a host sync.
+static int shard_run_host(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const std::vector<std::vector<HostBatch>>& hb) {
+  int rc;
+  for (uint32_t r = 0; r < R; r++) if ((rc = shard_staging(ranks[r]))) return rc;
+  const uint32_t S = ranks[0]->S;
+  std::vector<cudaStream_t> mains(R);
+  for (uint32_t r = 0; r < R; r++) mains[r] = ranks[r]->e->stream;
+  if (ranks[0]->one_stream) for (uint32_t r = 0; r < R; r++) mains[r] = ranks[0]->e->stream;   // ranks sharing a device: one stream
+  for (uint32_t j0 = 0; j0 < k; j0 += S) {
+    const uint32_t g = (k - j0 < S) ? (k - j0) : S;
+    std::vector<std::vector<ShardBatch>> b(R, std::vector<ShardBatch>(g));
+    for (uint32_t r = 0; r < R; r++) {
+      dint_shard_ctx* c = ranks[r];
+      dint_engine* e = c->e;
+      CU(cudaSetDevice(e->device));
+      for (uint32_t j = 0; j < g; j++) {
+        const HostBatch& h = hb[r][j0 + j];
+        if (h.n > c->max_n) return set_err(DINT_EINVAL, "batch size");
+        const uint32_t s = j;                                 // staging set (any fixed mapping works: groups are serialised per set)
+        CU(cudaStreamWaitEvent(c->s_in, c->ev_d2h[s], 0));    // the previous user of this staging set has left
+        if (h.n) CU(cudaMemcpyAsync(c->st_req[s], h.req, h.n * e->msg, cudaMemcpyHostToDevice, c->s_in));
+        if (h.dst && h.n) CU(cudaMemcpyAsync(c->st_dst[s], h.dst, h.n, cudaMemcpyHostToDevice, c->s_in));
+        CU(cudaEventRecord(c->ev_h2d[s], c->s_in));
+        e->stats.h2d_bytes += h.n * e->msg + (h.dst ? h.n : 0);
+        b[r][j] = ShardBatch{c->st_req[s], h.dst ? c->st_dst[s] : nullptr, c->st_out[s], h.n};
+      }
+      for (uint32_t j = 0; j < g; j++) CU(cudaStreamWaitEvent(mains[r], c->ev_h2d[j], 0));   // (main forks side / ret)
+    }
+    if ((rc = shard_run(ranks, R, g, b, mains.data()))) return rc;
+    for (uint32_t r = 0; r < R; r++) {
+      dint_shard_ctx* c = ranks[r];
+      dint_engine* e = c->e;
+      CU(cudaSetDevice(e->device));
+      for (uint32_t j = 0; j < g; j++) {
+        const HostBatch& h = hb[r][j0 + j];
+        const uint32_t ep = c->epoch - g + 1 + j;
+        if (c->one_stream) { CU(cudaEventRecord(c->ev_comb[ep % c->S], mains[r])); }
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_comb[ep % c->S], 0));
+        if (h.n) CU(cudaMemcpyAsync(h.out, c->st_out[j], h.n * e->msg, cudaMemcpyDeviceToHost, c->s_out));
+        CU(cudaEventRecord(c->ev_d2h[j], c->s_out));
+        e->stats.d2h_bytes += h.n * e->msg;
+      }
+    }
+  }
+  for (uint32_t r = 0; r < R; r++) {
+    CU(cudaSetDevice(ranks[r]->e->device));
+    CU(cudaStreamSynchronize(ranks[r]->s_out));
+    CU(cudaStreamSynchronize(mains[r]));
+  }
+  return DINT_OK;
+}
+
+extern "C" {
+
+int dint_shard_submit_host(dint_shard_ctx* c, uint32_t k, const void* const* req_host, const uint8_t* const* dst_host, uint64_t n,
+                           void* const* out_host) {
+  if (!c || !req_host || !out_host || n == 0 || n > c->max_n) return set_err(DINT_EINVAL, "bad argument");
+  std::vector<std::vector<HostBatch>> hb(1, std::vector<HostBatch>(k));
+  for (uint32_t j = 0; j < k; j++) hb[0][j] = HostBatch{(const uint8_t*)req_host[j], dst_host ? dst_host[j] : nullptr, (uint8_t*)out_host[j], n};
+  return shard_run_host(&c, 1, k, hb);
+}
+
+// ---- dint_cluster_*: G shards driven by ONE process (dint_create(kind, cfg, n_gpus) / dint_submit(..., dst_shard, ...)) ----
+struct dint_cluster {
+  int kind = 0;
+  uint32_t G = 0, cap = 0;
+  uint64_t max_n = 0;
+  bool by_dst = false, shared_device = false;
+  std::vector<int> dev;
+  std::vector<dint_engine*> eng;
+  std::vector<dint_shard_ctx*> sh;
+  std::vector<void*> bufs;                  // per rank: one allocation {inbox sets | return-buffer sets | signal block}
+};
+
+void dint_cluster_destroy(dint_cluster* cl) {
+  if (!cl) return;
+  for (auto* c : cl->sh) dint_shard_destroy(c);
+  for (size_t r = 0; r < cl->bufs.size(); r++) { cudaSetDevice(cl->dev[r]); cudaFree(cl->bufs[r]); }
+  for (auto* e : cl->eng) dint_destroy(e);
+  delete cl;
+}
+
+int dint_cluster_create(int kind, const dint_cfg* cfg, int n_gpus, const int* devices, uint64_t max_batch, dint_cluster** out) {
+  if (!out || kind < 0 || kind >= DINT_NUM_KINDS || n_gpus < 1 || n_gpus > kMaxShards) return set_err(DINT_EINVAL, "bad kind / n_gpus");
+  *out = nullptr;
+  const bool by_dst = kind == DINT_TATP || kind == DINT_SMALLBANK;
+  if (by_dst && n_gpus == 2) return set_err(DINT_EINVAL, "tatp / smallbank placement needs 1 or >= 3 shards (primary + 2 backups)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(DINT_ENODEV, "no CUDA device: dint_b200 has no CPU fallback"); }
+  dint_cluster* cl = new dint_cluster();
+  cl->kind = kind; cl->G = (uint32_t)n_gpus; cl->by_dst = by_dst;
+  for (int r = 0; r < n_gpus; r++) {
+    const int d = devices ? devices[r] : r % ndev;
+    if (d < 0 || d >= ndev) { delete cl; return set_err(DINT_EINVAL, "bad device ordinal"); }
+    cl->dev.push_back(d);
+    for (int q = 0; q < r; q++) if (cl->dev[q] == d) cl->shared_device = true;
+  }
+  if (cl->shared_device)
+    for (int r = 1; r < n_gpus; r++)
+      if (cl->dev[r] != cl->dev[0]) { delete cl; return set_err(DINT_EINVAL, "devices must be all distinct or all the same"); }
+  const uint32_t G = cl->G;
+  const uint32_t msg = kMsgSize[kind];
+  if (max_batch == 0) max_batch = 1u << 18;
+  cl->max_n = max_batch;
+  {
+    // slab capacity per (source, owner): hashing spreads records evenly (mean + 25 % + 8 sigma); a client-chosen
+    // placement is pre-counted on the host by dint_cluster_submit, which cuts a round where a slab would overflow
+    const double mean = (double)max_batch / G;
+    uint64_t cap = (uint64_t)(mean * (by_dst ? 2.0 : 1.25) + 8.0 * sqrt(mean) + 64);
+    if (G == 1) cap = max_batch;
+    cl->cap = (uint32_t)((cap + kTile - 1) / kTile * kTile);
+  }
+  int rc = DINT_OK;
+  dint_cfg base;
+  if (cfg) base = *cfg; else dint_default_cfg(kind, &base);
+  const uint32_t chunk_need = (uint32_t)(((uint64_t)G * cl->cap + kTile - 1) / kTile * kTile);
+  for (uint32_t r = 0; r < G && rc == DINT_OK; r++) {
+    dint_cfg c = base;
+    if (by_dst) { c.n_shards = 1; c.shard_id = 0; c.txn_shards = G; c.txn_shard_id = r; }
+    else { c.n_shards = G; c.shard_id = r; }
+    if (c.chunk == 0 || c.chunk < chunk_need) c.chunk = chunk_need;        // one batch of the exchange = one engine chunk
+    dint_engine* e = nullptr;
+    rc = dint_create(kind, &c, cl->dev[r], &e);
+    if (rc == DINT_OK) cl->eng.push_back(e);
+  }
+  const uint32_t S = 3;
+  const size_t region = ((size_t)G * cl->cap * msg + 255) / 256 * 256;
+  std::vector<uint64_t> base_ptr(G);
+  for (uint32_t r = 0; r < G && rc == DINT_OK; r++) {
+    void* p = nullptr;
+    if (cudaSetDevice(cl->dev[r]) != cudaSuccess || cudaMalloc(&p, 2 * S * region + 4096) != cudaSuccess) { rc = set_err(DINT_ENOMEM, "cluster buffers", cudaGetLastError()); break; }
+    cudaMemset(p, 0, 2 * S * region + 4096);
+    cl->bufs.push_back(p);
+    base_ptr[r] = (uint64_t)p;
+    if (!cl->shared_device)
+      for (uint32_t q = 0; q < G; q++)
+        if (q != r) {
+          int can = 0;
+          cudaDeviceCanAccessPeer(&can, cl->dev[r], cl->dev[q]);
+          if (!can) { rc = set_err(DINT_ENODEV, "GPUs without peer access"); break; }
+          cudaError_t ce = cudaDeviceEnablePeerAccess(cl->dev[q], 0);
+          if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) { rc = set_err(DINT_EIO, "cudaDeviceEnablePeerAccess", ce); break; }
+          cudaGetLastError();
+        }
+  }
+  for (uint32_t r = 0; r < G && rc == DINT_OK; r++) {
+    cudaSetDevice(cl->dev[r]);
+    cudaDeviceSynchronize();
+  }
+  for (uint32_t r = 0; r < G && rc == DINT_OK; r++) {
+    dint_peer_ptrs in[kMaxSets]{}, rb[kMaxSets]{}, sig{};
+    for (uint32_t s = 0; s < S; s++)
+      for (uint32_t o = 0; o < G; o++) { in[s].p[o] = base_ptr[o] + (2 * s) * region; rb[s].p[o] = base_ptr[o] + (2 * s + 1) * region; }
+    for (uint32_t o = 0; o < G; o++) sig.p[o] = base_ptr[o] + 2 * S * region;
+    dint_shard_ctx* c = nullptr;
+    rc = shard_make(cl->eng[r], G, r, cl->cap, S, in, rb, &sig, cl->max_n, cl->shared_device, &c);
+    if (rc == DINT_OK) cl->sh.push_back(c);
+  }
+  if (rc != DINT_OK) { std::string keep = g_last_error; dint_cluster_destroy(cl); g_last_error = keep; return rc; }
+  *out = cl;
+  return DINT_OK;
+}
+
+int dint_cluster_populate(dint_cluster* cl) {
+  if (!cl) return DINT_EINVAL;
+  for (auto* e : cl->eng) { int rc = dint_populate(e); if (rc) return rc; }
+  return DINT_OK;
+}
+dint_engine* dint_cluster_engine(dint_cluster* cl, int shard) { return (cl && shard >= 0 && shard < (int)cl->G) ? cl->eng[shard] : nullptr; }
+uint32_t dint_cluster_size(dint_cluster* cl) { return cl ? cl->G : 0; }
+
+int dint_cluster_submit(dint_cluster* cl, const void* req, uint64_t n, const uint8_t* dst_shard, void* resp) {
+  if (!cl || (n && (!req || !resp))) return set_err(DINT_EINVAL, "null argument");
+  if (cl->by_dst && cl->G > 1 && !dst_shard) return set_err(DINT_EINVAL, "tatp / smallbank: the client names the shard of every record (dst_shard)");
+  if (n == 0) return DINT_OK;
+  const uint32_t G = cl->G, msg = kMsgSize[cl->kind];
+  const uint8_t* rq = (const uint8_t*)req;
+  uint8_t* rs = (uint8_t*)resp;
+  unsigned long long err_before = 0;
+  for (auto* e : cl->eng) err_before += e->stats.errors;
+  // Rounds: a round hands rank r the r-th of G contiguous pieces (rank-major order = index order).
+  // For a client-chosen placement the pieces are cut so that no (source, owner) slab can overflow.
+  std::vector<std::vector<HostBatch>> hb(G);
+  uint64_t off = 0;
+  while (off < n) {
+    uint64_t m = n - off < (uint64_t)G * cl->max_n ? n - off : (uint64_t)G * cl->max_n;
+    for (;;) {
+      const uint64_t q = (m + G - 1) / G;
+      bool fits = true;
+      if (dst_shard && G > 1) {
+        for (uint32_t r = 0; r < G && fits; r++) {
+          const uint64_t lo = off + (uint64_t)r * q, hi = lo + q < off + m ? lo + q : off + m;
+          uint32_t cnt[kMaxShards] = {0};
+          for (uint64_t i = lo; i < hi; i++) { const uint8_t o = dst_shard[i]; if (o < G) cnt[o]++; }
+          for (uint32_t o = 0; o < G; o++) if (cnt[o] > cl->cap) fits = false;
+        }
+      }
+      if (fits || m <= G) break;
+      m = (m + 1) / 2;
+    }
+    const uint64_t q = (m + G - 1) / G;
+    for (uint32_t r = 0; r < G; r++) {
+      const uint64_t lo = off + (uint64_t)r * q;
+      const uint64_t hi = lo + q < off + m ? lo + q : off + m;
+      // (a rank without records in a tail round still takes part in the exchange: its slabs are all padding)
+      hb[r].push_back(HostBatch{rq + lo * msg, dst_shard ? dst_shard + lo : nullptr, rs + lo * msg, lo < hi ? hi - lo : 0});
+    }
+    off += m;
+  }
+  const uint32_t k = (uint32_t)hb[0].size();
+  int rc = shard_run_host(cl->sh.data(), G, k, hb);
+  if (rc) return rc;
+  unsigned long long err_after = 0;
+  for (uint32_t r = 0; r < G; r++) {
+    uint32_t fl[2] = {0, 0};
+    if ((rc = dint_shard_flags(cl->sh[r], fl))) return rc;
+    if (fl[0] || fl[1]) return set_err(DINT_EIO, fl[0] ? "slab overflow in the exchange (adversarially skewed keys): server state has advanced" : "exchange timed out");
+    dint_engine* e = cl->eng[r];
+    if ((rc = pull_counters(e))) return rc;
+    err_after += e->stats.errors;
+  }
+  return err_after != err_before ? DINT_EPROTO : DINT_OK;
 }
 
 }  // extern "C"

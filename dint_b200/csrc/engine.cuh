@@ -83,7 +83,7 @@ struct KvTable {
   FastMod lock_mod;        // kKeysPerEntry * hash_size of the reference (tatp.h:12-14, smallbank.h:12-14)
   uint32_t grp_base;       // first group id of this table
   uint32_t n_groups;       // local groups of this table
-  unsigned long long* live;  // live-key counter
+  unsigned long long* live;  // [0] live keys, [1] entries that have left EMPTY (FULL + TOMB)
 };
 
 struct Ctx {
@@ -134,16 +134,29 @@ struct Ctx {
   unsigned long long* log_total;     // [2]: [0] appends before this chunk ... running total, [1] this chunk's total
   // bookkeeping
   unsigned long long* counters;   // [0] errors [1] conflicted [2] max_run
-#ifdef DINT_VER16
-  uint16_t* ver16;                // lock_fasst, experimental layout: low 15 bits of the version + flag 0x8000 "see ver_hi"
-  uint32_t* ver_hi;               //   high 17 bits, cold: read / written only for slots past 32767 commits
-#endif
-#ifdef DINT_TILE_TICKETS
   uint32_t* tickets;              // [0] k_classify's, [1] k_apply's tile ticket counter
-#endif
   uint32_t* gbar;                 // k_ordered's grid barrier when it is not launched cooperatively
   uint32_t coop_launch;           // 1: k_ordered was launched cooperatively
+  // where the replies go.  Default: `resp`, one contiguous array.  Inside the multi-GPU step the batch is W source
+  // slabs of seg_tiles tiles each and the replies of slab s are stored straight into source s's return buffer over
+  // NVLink (seg_resp[s]; posted stores), so no separate push / pull pass exists.
+  const uint8_t* ord_req;         // request array of the chunk being replayed (replies may live in remote memory)
+  uint32_t seg_tiles;             // tiles per source slab; 0 = contiguous replies
+  uint32_t tile0, ord_tile0;      // index, inside the batch, of the first tile of this chunk / of the replayed chunk
+  uint32_t pad_ok;                // 1 inside the multi-GPU step: type 0xFE records are slab padding (else: invalid)
+  uint64_t seg_resp[8];           // reply slab of source s (device address, possibly peer memory)
 };
+
+// address of tile T's replies (T counted from the start of the batch) when the replies are segmented by source
+template <int MSG> DINT_D uint8_t* seg_tile_ptr(const Ctx& c, uint32_t T) {
+  const uint32_t s = T / c.seg_tiles;
+  return (uint8_t*)c.seg_resp[s] + (size_t)(T - s * c.seg_tiles) * (kTile * MSG);
+}
+// address of the reply of record `idx` of the chunk being replayed
+template <int MSG> DINT_D uint8_t* ord_out_ptr(const Ctx& c, uint32_t idx) {
+  if (c.seg_tiles) return seg_tile_ptr<MSG>(c, c.ord_tile0 + idx / kTile) + (size_t)(idx % kTile) * MSG;
+  return c.ord_resp + (size_t)idx * MSG;
+}
 
 // ---- bitmap helpers -------------------------------------------------------------------------------
 DINT_D bool bm_test(const uint32_t* bm, uint32_t g) { return (bm[g >> 5] >> (g & 31)) & 1u; }
@@ -295,28 +308,11 @@ template <> DINT_D KeyInfo key_info<K_FASST>(const Ctx& c, const uint8_t* rec) {
   if (!to_local_group(c, fast_mod(k.h, c.slot_mod), k.grp)) k.grp = kNoGroup;   // :82
   return k;
 }
-// The version of a lock_fasst slot.  Default layout: `ver` u32 per slot (144 MB at 36 M slots: every READ is an HBM
-// sector for 4 bytes).  -DDINT_VER16 (experimental, not yet measured): a 16-bit hot array (72 MB, can stay in L2)
-// holding the low 15 bits and a flag; the high 17 bits live in a cold u32 array that only slots with more than
-// 32767 commits ever touch.  Exact for the whole u32 range (wrap included); 16-bit stores leave the neighbouring
-// slot alone, and a solo or replayed request owns its slot's version exclusively.
-DINT_D uint32_t ver_load(const Ctx& c, uint32_t g) {
-#ifdef DINT_VER16
-  const uint32_t lo = __ldcg(&c.ver16[g]);
-  return (lo & 0x8000u) ? ((lo & 0x7fffu) | (__ldcg(&c.ver_hi[g]) << 15)) : lo;
-#else
-  return __ldcg(&c.ver[g]);
-#endif
-}
-DINT_D void ver_store(const Ctx& c, uint32_t g, uint32_t v) {
-#ifdef DINT_VER16
-  const uint32_t hi = v >> 15;
-  if (hi) c.ver_hi[g] = hi;                              // (a stale ver_hi under a cleared flag is never read)
-  c.ver16[g] = (uint16_t)((v & 0x7fffu) | (hi ? 0x8000u : 0u));
-#else
-  c.ver[g] = v;
-#endif
-}
+// The version of a lock_fasst slot: `ver` u32 per slot (144 MB at 36 M slots -- every READ costs one 64-byte HBM burst
+// for 4 bytes used).  A 16-bit hot array + cold high bits was measured (round 2, profiles/r02_variants.md): K2 -6 %,
+// step -2.4 %, and it degenerates to two accesses once a slot has seen 32768 commits (minutes of service): dropped.
+DINT_D uint32_t ver_load(const Ctx& c, uint32_t g) { return __ldcg(&c.ver[g]); }
+DINT_D void ver_store(const Ctx& c, uint32_t g, uint32_t v) { c.ver[g] = v; }
 template <> struct Pre<K_FASST> { uint32_t ver; };
 template <> DINT_D Pre<K_FASST> prefetch<K_FASST>(const Ctx& c, const uint8_t*, const KeyInfo& ki, const TypeInfo& ti) {
   return Pre<K_FASST>{(ti.mask & (C_RA | C_WA)) ? ver_load(c, ki.grp) : 0u};

@@ -57,54 +57,31 @@ template <int MSG> struct Stage {
   static constexpr uint32_t N = (BYTES > 8192) ? 2 : kStages;
 };
 
-// Persistent-CTA tile pipeline: CTA b owns tiles b, b + gridDim.x, ...; thread 0 keeps kStages - 1
-// TMA bulk loads in flight ahead of the tile being processed.
-//
-// -DDINT_TILE_TICKETS (experimental, not yet measured): tiles are handed out by a global ticket counter instead.
-// A statically striped persistent grid loses a whole wave when some of its CTAs cannot be resident next to another
-// stream's kernel (the multi-GPU step: engine 114 us instead of 62 next to a dispatch); with tickets the CTAs that
-// are resident simply take more tiles.  Thread 0 draws the ticket when it issues the load and publishes the tile
-// id in a shared-memory ring; the CTA barriers of the tile loop make it visible one iteration before it is used.
-#ifdef DINT_TILE_TICKETS
+// Persistent-CTA tile pipeline with DYNAMIC tile assignment.  Tiles are handed out by a global ticket counter: a
+// statically striped persistent grid loses a whole wave whenever some of its CTAs cannot be resident next to another
+// stream's kernel (the multi-GPU step: dispatch / combine of the neighbouring batches; the host path: nothing, but
+// the copies' completion kernels), with tickets the CTAs that ARE resident simply take more tiles.  Thread 0 draws:
+// the first kStages tickets with one atomic at kernel start, afterwards one ticket per tile ONE ITERATION AHEAD of
+// its use (the atomic's round trip, ~0.7 us, hides behind a tile's work: drawing at the point of use measured
+// +17 % on K1 + K2).  The tile id of every pipeline stage is published in a shared-memory ring; the CTA barriers of
+// the tile loop make it visible one iteration before it is used.
 constexpr uint32_t kNoTile = 0xffffffffu;
 struct TileIter {
   uint32_t n_tiles, ns;
   uint32_t* ctr;        // global ticket counter of this kernel (reset by the OTHER kernel of the K1 / K2 pair)
   uint32_t* ring;       // shared memory, [ns]: tile id held by each pipeline stage, kNoTile = no more tiles
+  uint32_t pending;     // thread 0: the next ticket, already drawn
   DINT_D uint32_t tile(uint32_t i) const { return ring[i % ns]; }
   DINT_D bool has(uint32_t i) const { return ring[i % ns] != kNoTile; }
-  DINT_D bool may_issue(uint32_t) const { return true; }
 };
-DINT_D TileIter tile_iter(uint32_t n_tiles, uint32_t ns, uint32_t* ctr, uint32_t* ring) {
-  return TileIter{n_tiles, ns, ctr, ring};
-}
-#else
-struct TileIter {
-  uint32_t n_my;        // tiles owned by this CTA
-  DINT_D uint32_t tile(uint32_t i) const { return blockIdx.x + i * gridDim.x; }
-  DINT_D bool has(uint32_t i) const { return i < n_my; }
-  DINT_D bool may_issue(uint32_t i) const { return i < n_my; }
-};
-DINT_D TileIter tile_iter(uint32_t n_tiles) {
-  TileIter it;
-  it.n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  return it;
-}
-#endif
+// thread 0: stage i takes the pending ticket (and the next one is drawn, to be used one iteration later)
 template <int MSG>
-DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, const TileIter& it, uint32_t i) {
-#ifdef DINT_TILE_TICKETS
-  uint32_t t = kNoTile;
-  if (it.n_tiles) {                                      // (a flush launch has no tiles and must not touch the counter)
-    t = atomicAdd(it.ctr, 1u);
-    if (t >= it.n_tiles) t = kNoTile;
-  }
+DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, TileIter& it, uint32_t i) {
+  const uint32_t t = it.pending < it.n_tiles ? it.pending : kNoTile;
   it.ring[i % it.ns] = t;
-  if (t == kNoTile) return;
+  if (t == kNoTile) return;                              // (the counter only grows: no need to draw again)
+  it.pending = atomicAdd(it.ctr, 1u);
   const uint32_t first = t * kTile;
-#else
-  const uint32_t t = it.tile(i), first = t * kTile;
-#endif
   const uint32_t cnt = min((uint32_t)kTile, c.n - first);
   const uint32_t body = (cnt * MSG) & ~15u;
   const uint32_t buf = i % Stage<MSG>::N;
@@ -112,6 +89,25 @@ DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, const T
     mbar_expect_tx(&full[buf], body);
     tma_load_1d(smem + buf * Stage<MSG>::BYTES, c.req + (size_t)first * MSG, body, &full[buf]);
   }
+}
+// thread 0, once per kernel: the first NS stages with ONE atomic (NS + 1 consecutive tickets: NS used now, one pending)
+template <int MSG>
+DINT_D void issue_first_tiles(const Ctx& c, uint8_t* smem, uint64_t* full, TileIter& it, uint32_t NS) {
+  uint32_t t0 = kNoTile;
+  if (it.n_tiles) t0 = atomicAdd(it.ctr, NS + 1);        // (a flush launch has no tiles and must not touch the counter)
+  for (uint32_t i = 0; i < NS; i++) {
+    const uint32_t t = (t0 != kNoTile && t0 + i < it.n_tiles) ? t0 + i : kNoTile;
+    it.ring[i % it.ns] = t;
+    if (t == kNoTile) continue;
+    const uint32_t first = t * kTile;
+    const uint32_t cnt = min((uint32_t)kTile, c.n - first);
+    const uint32_t body = (cnt * MSG) & ~15u;
+    if (body) {
+      mbar_expect_tx(&full[i], body);
+      tma_load_1d(smem + i * Stage<MSG>::BYTES, c.req + (size_t)first * MSG, body, &full[i]);
+    }
+  }
+  it.pending = (t0 != kNoTile) ? t0 + NS : kNoTile;
 }
 // all threads: wait for tile i's bulk load, fetch the (<16-byte) tail of the very last tile by hand
 template <int MSG>
@@ -135,7 +131,7 @@ DINT_D uint8_t* acquire_tile(const Ctx& c, uint8_t* smem, uint64_t* full, const 
 template <int KIND>
 DINT_D uint32_t route_owner_of(const Ctx& c, const uint8_t* rec) {
   using W = Wire<KIND>;
-  const TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
+  const TypeInfo ti = type_info<KIND>(rec);
   if (ti.invalid || !ti.mask) return c.shard_id;         // no per-key state touched: serve it where it arrived
   uint32_t gglobal = 0;
   if constexpr (KIND == K_LOCK2PL || KIND == K_FASST) gglobal = fast_mod(fasthash64_u32(ld_u32_unaligned(rec + W::KEY)), c.slot_mod);
@@ -250,20 +246,6 @@ __global__ void k_p2p_wait(const uint32_t* my_sig, uint32_t world, uint32_t epoc
   __threadfence_system();
 }
 
-// push variant of the combine's transport: the owner copies the reply slab of every source into that source's
-// return buffer with posted remote stores (a remote load stalls the issuing warp for an NVLink round trip, a
-// remote store does not); slab bytes are a multiple of 16, all bases 16-byte aligned
-__global__ void __launch_bounds__(kThreads) k_push_slabs(const uint8_t* outbox, PeerPtrs retbox, uint32_t world, uint32_t me, uint32_t slab16) {
-  const uint64_t total = (uint64_t)(world - 1) * slab16;                 // uint4 elements to move
-  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (uint64_t)gridDim.x * kThreads) {
-    uint32_t o = (uint32_t)(i / slab16);
-    const uint32_t j = (uint32_t)(i - (uint64_t)o * slab16);
-    if (o >= me) o++;                                                    // every source but myself
-    const uint4 v = __ldcg((const uint4*)(outbox + (size_t)o * slab16 * 16) + j);
-    ((uint4*)retbox.p[o])[(size_t)me * slab16 + j] = v;                  // my slab inside source o's return buffer
-  }
-}
-
 // combine: replies arrive in partition order; put each back at its original index
 template <int MSG>
 __global__ void __launch_bounds__(kThreads) k_exact_unpermute(const uint8_t* sorted, const uint32_t* perm, uint32_t n, uint8_t* out) {
@@ -290,13 +272,12 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[kStages];
   __shared__ uint32_t scratch[kTile / 32];
-  griddep_wait();                                        // everything below depends on the previous launch of the stream
-  griddep_launch();
+  __shared__ uint32_t s_ring[kStages];
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     // [2] (a writer exists) is OR-ed by any CTA of this launch, so it is cleared one launch early: each K1
     // clears the slot of the chunk it replays, which is the slot the NEXT chunk will use
-    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; c.nc_ord[2] = 0; }
+    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; c.nc_ord[2] = 0; c.tickets[1] = 0; }   // (K2 is not running: its ticket counter is reset here)
   }
   __syncthreads();
   // The previous chunk's listed requests are replayed by this launch too (their buckets were filled by its
@@ -308,18 +289,9 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     ordered_buckets<KIND>(c, smem);
     __syncthreads();
   }
-#ifdef DINT_TILE_TICKETS
-  __shared__ uint32_t s_ring[kStages];
-  if (blockIdx.x == 0 && threadIdx.x == 0) c.tickets[1] = 0;          // K2 is not running: its counter is reset here
-  const TileIter it = tile_iter(c.n_tiles, NS, &c.tickets[0], s_ring);
-  if (threadIdx.x == 0)
-    for (uint32_t i = 0; i < NS; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+  TileIter it{c.n_tiles, NS, &c.tickets[0], s_ring, kNoTile};
+  if (threadIdx.x == 0) issue_first_tiles<W::MSG>(c, smem, full, it, NS);
   __syncthreads();
-#else
-  const TileIter it = tile_iter(c.n_tiles);
-  if (threadIdx.x == 0)
-    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
-#endif
 
   // retire the previous chunk's flags: every word it touched is zeroed (all of that set's nibbles
   // were written by that chunk, so whole-word stores are exact).  Loads are batched four deep so that
@@ -344,7 +316,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   bool saw_writer = false;          // any request of this CTA's tiles that writes A or L
   for (uint32_t i = 0; it.has(i); i++) {
     // the stage that held tile i-1 is free (barrier at the end of iteration i-1): refill it now
-    if (threadIdx.x == 0 && i && it.may_issue(i + NS - 1)) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
+    if (threadIdx.x == 0 && i) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
     uint32_t first, cnt;
     const uint8_t* tile = acquire_tile<W::MSG>(c, smem, full, it, i, first, cnt);
     const bool valid = threadIdx.x < cnt;
@@ -353,7 +325,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     uint32_t* new_w = nullptr;
     if (valid) {
       const uint8_t* rec = tile + threadIdx.x * W::MSG;
-      TypeInfo ti = rec[W::TYPE] == kPadType ? TypeInfo{0, false, false} : type_info<KIND>(rec);
+      TypeInfo ti = (c.pad_ok && rec[W::TYPE] == kPadType) ? TypeInfo{0, false, false} : type_info<KIND>(rec);
       uint32_t g = kNoGroup;
       if (!ti.invalid && ti.mask) {
         g = key_info<KIND>(c, rec).grp;
@@ -443,25 +415,15 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
   // lock servers: the group id K1 stored is all K2 needs of the key -- fetch it (coalesced, independent of
   // the TMA stage) instead of re-hashing; KV servers need the hash itself to find the table entry
   constexpr bool kGrpFromK1 = (KIND == K_LOCK2PL || KIND == K_FASST);
-  if (threadIdx.x == 0)
-    for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
-  __syncthreads();
-#ifdef DINT_TILE_TICKETS
   __shared__ uint32_t s_ring[kStages];
-  griddep_wait();                                        // (the ticket counter itself is K1's to reset: wait first)
-  griddep_launch();
-  if (blockIdx.x == 0 && threadIdx.x == 0) c.tickets[0] = 0;          // K1 is not running: its counter is reset here
-  const TileIter it = tile_iter(c.n_tiles, NS, &c.tickets[1], s_ring);
-  if (threadIdx.x == 0)
-    for (uint32_t i = 0; i < NS; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
+    if (blockIdx.x == 0) c.tickets[0] = 0;               // K1 is not running: its ticket counter is reset here
+  }
   __syncthreads();
-#else
-  const TileIter it = tile_iter(c.n_tiles);
-  if (threadIdx.x == 0)                                  // the request tiles do not depend on K1: their loads may start
-    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);   // before K1 has drained
-  griddep_wait();                                        // flags, group ids, counters: K1's output
-  griddep_launch();
-#endif
+  TileIter it{c.n_tiles, NS, &c.tickets[1], s_ring, kNoTile};
+  if (threadIdx.x == 0) issue_first_tiles<W::MSG>(c, smem, full, it, NS);
+  __syncthreads();
   const bool chunk_has_writer = c.nc_cur[2] != 0;      // set by K1; false = nothing in this chunk can conflict
 
   for (uint32_t i = 0; it.has(i); i++) {
@@ -471,7 +433,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
       const uint32_t idx = it.tile(i) * kTile + threadIdx.x;
       if (idx < c.n) g_k1 = __ldcg(&c.grp[idx]);
     }
-    if (threadIdx.x == 0 && i && it.may_issue(i + NS - 1)) {
+    if (threadIdx.x == 0 && i) {
       // the stage that held tile i-1 is refilled as soon as its bulk store has finished READING it
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
@@ -485,7 +447,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
     KeyInfo ki{0, 0, kNoGroup};
     Pre<KIND> pf;
     bool listed = false;
-    const bool pad = valid && rec[W::TYPE] == kPadType;
+    const bool pad = valid && c.pad_ok && rec[W::TYPE] == kPadType;
     if (valid && !pad) {
       ti = type_info<KIND>(rec);
       if (!ti.invalid && ti.mask) {
@@ -535,7 +497,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
     }
     // ---- write the tile back; keep the load pipeline kStages - 1 tiles ahead ----
     const uint32_t bytes = cnt * W::MSG, body = bytes & ~15u;
-    uint8_t* gdst = c.resp + (size_t)first * W::MSG;
+    uint8_t* gdst = c.seg_tiles ? seg_tile_ptr<W::MSG>(c, c.tile0 + t) : c.resp + (size_t)first * W::MSG;
     fence_proxy_async_smem();
     __syncthreads();
     for (uint32_t b = body + threadIdx.x; b < bytes; b += blockDim.x) gdst[b] = tile[b];
@@ -554,18 +516,21 @@ constexpr int kSortItems = 8;                         // items per thread per ra
 constexpr int kSortTile = kThreads * kSortItems;      // 2048
 
 template <int KIND>
-DINT_D void replay_run(const Ctx& c, uint8_t* resp, const uint64_t* sorted, uint32_t p, uint32_t nc) {
+DINT_D void replay_run(const Ctx& c, const uint64_t* sorted, uint32_t p, uint32_t nc) {
   using W = Wire<KIND>;
   const uint32_t g = (uint32_t)(sorted[p] >> 32);
   uint32_t len = 0;
   for (uint32_t q = p; q < nc; q++) {
     uint64_t e = sorted[q];
     if ((uint32_t)(e >> 32) != g) break;
-    uint8_t* rec = resp + (size_t)(uint32_t)e * W::MSG;       // K2 left the request bytes here
+    // the request is applied on a private copy and leaves with word-wide stores: the reply array may be peer memory
+    __align__(4) uint8_t rec[(W::MSG + 3) / 4 * 4];
+    copy_record<W::MSG>(rec, c.ord_req + (size_t)(uint32_t)e * W::MSG);
     const TypeInfo ti = type_info<KIND>(rec);
     const KeyInfo ki = key_info<KIND>(c, rec);
     const Pre<KIND> pf = prefetch<KIND>(c, rec, ki, ti);      // fetched AFTER the previous request of the run
     apply_one<KIND>(c, rec, ki, pf, 0, false);
+    copy_record<W::MSG>(ord_out_ptr<W::MSG>(c, (uint32_t)e), rec);
     len++;
   }
   if (len > 1) atomicMax(&c.counters[2], (unsigned long long)len);
@@ -652,7 +617,7 @@ DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch) {
         if constexpr (FastReplay<KIND>::ok) {
           using FR = FastReplay<KIND>;
           using Wq = Wire<KIND>;
-          for (uint32_t p = lane; p < m; p += 32) wops[p] = FR::load_op(c.ord_resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG);
+          for (uint32_t p = lane; p < m; p += 32) wops[p] = FR::load_op(c.ord_req + (size_t)(uint32_t)wkeys[p] * Wq::MSG);
           __syncwarp();
           for (uint32_t p = lane; p < m; p += 32)
             if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) {
@@ -664,10 +629,10 @@ DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch) {
               if (q - p > 1) atomicMax(&c.counters[2], (unsigned long long)(q - p));
             }
           __syncwarp();
-          for (uint32_t p = lane; p < m; p += 32) FR::write_result(c.ord_resp + (size_t)(uint32_t)wkeys[p] * Wq::MSG, wres[p]);
+          for (uint32_t p = lane; p < m; p += 32) FR::write_result(ord_out_ptr<Wq::MSG>(c, (uint32_t)wkeys[p]), wres[p]);
         } else {
           for (uint32_t p = lane; p < m; p += 32)
-            if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, c.ord_resp, wkeys, p, m);
+            if (p == 0 || (uint32_t)(wkeys[p - 1] >> 32) != (uint32_t)(wkeys[p] >> 32)) replay_run<KIND>(c, wkeys, p, m);
         }
         __syncwarp();
       }
@@ -751,7 +716,6 @@ struct GridBar {
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
-  griddep_wait();
   const uint32_t nc = c.nc_ord[0];
   const uint32_t overflow = c.nc_ord[1];
   if (nc == 0 || overflow == 0) return;               // the bucket path (inside the next K1) handles this chunk
@@ -938,7 +902,7 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
           if ((uint32_t)k < cnt) {
             const uint32_t p = base + k;
             const uint64_t e = src[p];
-            ty[k] = FR::load_op(c.ord_resp + (size_t)(uint32_t)e * Wq::MSG);
+            ty[k] = FR::load_op(c.ord_req + (size_t)(uint32_t)e * Wq::MSG);
             const bool head = p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(e >> 32);
             f[k] = fx_of(ty[k], head);
           } else { ty[k] = 0; f[k] = kFxId; }
@@ -1008,7 +972,7 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
               st.dirty_ver = (uint32_t)ex != 0;
             }
             const uint64_t r = FR::step(st, ty[k]);
-            FR::write_result(c.ord_resp + (size_t)(uint32_t)e * Wq::MSG, r);
+            FR::write_result(ord_out_ptr<Wq::MSG>(c, (uint32_t)e), r);
             // the run's final state is written only after EVERY entry has read the initial one (next pass)
             const bool last = p + 1 == nc || (uint32_t)(src[p + 1] >> 32) != g;
             if (last) dst[p] = (uint64_t)st.ver | ((uint64_t)st.lock << 32) | ((uint64_t)(st.dirty_ver ? 1u : 0u) << 33);
@@ -1034,7 +998,7 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
       uint32_t* ops_g = c.clist;
       uint64_t* res_g = dst;
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        ops_g[p] = FR::load_op(c.ord_resp + (size_t)(uint32_t)src[p] * Wq::MSG);
+        ops_g[p] = FR::load_op(c.ord_req + (size_t)(uint32_t)src[p] * Wq::MSG);
       grid.sync();
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
         if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) {
@@ -1047,11 +1011,11 @@ __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
         }
       grid.sync();
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        FR::write_result(c.ord_resp + (size_t)(uint32_t)src[p] * Wq::MSG, res_g[p]);
+        FR::write_result(ord_out_ptr<Wq::MSG>(c, (uint32_t)src[p]), res_g[p]);
     } else {
       // replay: one thread per same-group run
       for (uint32_t p = blockIdx.x * kThreads + tid; p < nc; p += gridDim.x * kThreads)
-        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, c.ord_resp, src, p, nc);
+        if (p == 0 || (uint32_t)(src[p - 1] >> 32) != (uint32_t)(src[p] >> 32)) replay_run<KIND>(c, src, p, nc);
     }
   }
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&c.counters[1], (unsigned long long)nc);

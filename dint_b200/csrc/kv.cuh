@@ -10,7 +10,12 @@
 // on its first probe is exactly one aligned 64-byte HBM access:
 //     { u64 key; u32 ver; u32 meta; u8 val[VALSZ]; pad }
 // meta: EMPTY (never used) / FULL / TOMB (deleted) / BUSY (insert in flight).  Entries never return to
-// EMPTY, so a probe sequence that reaches EMPTY proves absence.  Requests on the same key are never
+// EMPTY inside a launch, so a probe sequence that reaches EMPTY proves absence.  Deletes leave tombstones
+// (an insert reuses the first one on its probe path); the engine counts the entries that have left EMPTY
+// (`live[1]`) and, between calls, rehashes a table into a fresh array once FULL + TOMB passes 70 % of its
+// capacity (k_kv_rehash, engine.cu kv_maintain) -- the reference's chained kvs frees entries on delete
+// (store/udp/kvs.h:124-133), so without this a long insert/delete churn would grow the probe chains without
+// bound.  Requests on the same key are never
 // concurrent (same group -> K3 replays them in one thread); requests on different keys only meet on
 // the `meta` word, which is claimed with atomicCAS.
 #pragma once
@@ -93,7 +98,7 @@ DINT_D bool kv_set_from(const KvTable& t, uint64_t key, uint64_t h, uint4 (&v)[E
 // kvs_insert (kvs.h:77-104): take the first free entry on the probe path, ver = 0.  Like the
 // reference it does not look for an existing copy of the key.
 template <int VALSZ>
-DINT_D bool kv_insert_words(const KvTable& t, uint64_t key, uint64_t h, const uint32_t (&w)[Ent<VALSZ>::NW]) {
+DINT_D bool kv_insert_words(const KvTable& t, uint64_t key, uint64_t h, const uint32_t (&w)[Ent<VALSZ>::NW], uint32_t ver0 = 0) {
   uint64_t i = kv_home(t, h);
   for (uint64_t probe = 0; probe <= t.cap_mask; probe++) {
     uint8_t* e = t.entries + (i << t.ent_shift);
@@ -103,11 +108,12 @@ DINT_D bool kv_insert_words(const KvTable& t, uint64_t key, uint64_t h, const ui
       uint32_t old = atomicCAS(meta, m, (uint32_t)ENT_BUSY);
       if (old == m) {
         *((uint64_t*)e) = key;
-        *((uint32_t*)(e + 8)) = 0;
+        *((uint32_t*)(e + 8)) = ver0;
         kv_write_val<VALSZ>(e, w);
         __threadfence();
         *((volatile uint32_t*)meta) = ENT_FULL;
         atomicAdd(t.live, 1ULL);
+        if (m == ENT_EMPTY) atomicAdd(t.live + 1, 1ULL);   // one more entry that can never prove absence again
         return true;
       }
       m = old;
@@ -226,13 +232,14 @@ DINT_D void apply_one<K_STORE>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, co
 // =================================== tatp ===========================================================
 template <> DINT_D TypeInfo type_info<K_TATP>(const uint8_t* rec) {
   using W = Wire<K_TATP>;
+  // kCommitLog / kDeleteLog never index tables[]: they log msg.table verbatim (tatp/udp/server_shard.cc:182-207)
+  if (rec[W::TYPE] == 14 || rec[W::TYPE] == 24) return TypeInfo{0, false, true};
   if (rec[W::TABLE] >= 5) return TypeInfo{0, true, false};
   switch (rec[W::TYPE]) {
     case 0: return TypeInfo{C_RA, false, false};                    // kRead
     case 1: case 2: return TypeInfo{C_WL, false, false};            // kAcquireLock, kAbort
     case 12: case 18: case 22: return TypeInfo{C_WA | C_WL, false, false};  // kCommitPrim, kInsertPrim, kDeletePrim
     case 13: case 19: case 23: return TypeInfo{C_WA, false, false};         // kCommitBck, kInsertBck, kDeleteBck
-    case 14: case 24: return TypeInfo{0, false, true};              // kCommitLog, kDeleteLog
     default: return TypeInfo{0, true, false};                       // tatp/udp/server_shard.cc:209
   }
 }
@@ -293,9 +300,10 @@ DINT_D void apply_one<K_TATP>(const Ctx& c, uint8_t* rec, const KeyInfo& ki, con
     case 0: rec[W::TYPE] = kv_get_into<40>(t, key, h, v, rec + W::VAL, rec + W::VER) ? 4 : 6; break;  // :116-121
     case 1: rec[W::TYPE] = bm_fetch_set(c.lockbits, g) ? 8 : 7; break;                                // :123-132
     case 2: bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 9; break;                                     // :134-138
-    case 12: ok = kv_set_from<40>(t, key, h, v, rec + W::VAL); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 15; break;  // :140-146
-    case 18: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 20; break;  // :148-154
-    case 22: ok = kv_delete<40>(t, key, h, v); bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 25; break;                  // :156-162
+    // a would-panic request (kvs_set / kvs_delete on a missing key) applies NOTHING: the reference dies before the unlock
+    case 12: ok = kv_set_from<40>(t, key, h, v, rec + W::VAL); if (ok) bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 15; break;  // :140-146
+    case 18: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); if (ok) bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 20; break;  // :148-154
+    case 22: ok = kv_delete<40>(t, key, h, v); if (ok) bm_clear_bit(c.lockbits, g); rec[W::TYPE] = 25; break;                  // :156-162
     case 13: ok = kv_set_from<40>(t, key, h, v, rec + W::VAL); rec[W::TYPE] = 16; break;              // :164-168
     case 19: ok = kv_insert_from<40>(t, key, h, rec + W::VAL); rec[W::TYPE] = 21; break;              // :170-174
     default: ok = kv_delete<40>(t, key, h, v); rec[W::TYPE] = 26; break;                              // 23 :176-180
@@ -397,6 +405,23 @@ __global__ void __launch_bounds__(256) k_kv_load(const Ctx c, int table, const u
   if (!kv_insert_words<VALSZ>(t, key, h, w)) atomicAdd(&c.counters[0], 1ULL);
 }
 
+// Rehash of one table into a fresh (zeroed) array: every FULL entry moves with its version, tombstones vanish.
+template <int VALSZ>
+__global__ void __launch_bounds__(256) k_kv_rehash(const KvTable from, const KvTable to) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= from.cap_mask; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* e = from.entries + (i << from.ent_shift);
+    uint4 v[Ent<VALSZ>::NV];
+    kv_load_entry<VALSZ>(e, v);
+    if (v[0].w != ENT_FULL) continue;
+    const uint64_t key = ((uint64_t)v[0].y << 32) | v[0].x;
+    uint32_t w[Ent<VALSZ>::NW];
+    const uint32_t* flat = (const uint32_t*)v;
+#pragma unroll
+    for (int k = 0; k < Ent<VALSZ>::NW; k++) w[k] = flat[4 + k];
+    kv_insert_words<VALSZ>(to, key, fasthash64_u64(key), w, v[0].z);   // (`to` is at least as large: cannot fail)
+  }
+}
+
 template <int VALSZ>
 __global__ void k_kv_get1(const Ctx c, int table, uint64_t key, uint32_t* out /* [0]=found [1]=ver [2..]=val */) {
   uint4 v[Ent<VALSZ>::NV];
@@ -472,7 +497,7 @@ int kv_create_tables(int kind, const dint_cfg& cf, Ctx& c, KvHost* kv, uint64_t*
     int rc = alloc(&p, (size_t)(1ULL << lg) << T.ent_shift);
     if (rc) return rc;
     T.entries = (uint8_t*)p;
-    rc = alloc(&p, 8);
+    rc = alloc(&p, 16);
     if (rc) return rc;
     T.live = (unsigned long long*)p;
     kv[t].capacity = 1ULL << lg;

@@ -184,7 +184,8 @@ int main(int argc, char** argv) {
         x.n = keep;
         x.state = Worker::READY;
         cv_engine.notify_one();
-        cv_workers.wait(lk, [&] { return x.state == Worker::DONE || g_stop.load(); });
+        // (bounded waits: the signal handler only stores the flag, so a wakeup may be missed -- never a hang)
+        while (!cv_workers.wait_for(lk, std::chrono::milliseconds(100), [&] { return x.state == Worker::DONE || g_stop.load(); })) {}
         if (x.state != Worker::DONE) return;
         x.state = Worker::FILLING;
       }
@@ -245,7 +246,10 @@ int main(int argc, char** argv) {
     }
     cv_workers.notify_all();
   }
-  g_stop.store(true);
+  {
+    std::lock_guard<std::mutex> lk(mu);               // under the mutex: no worker sits between its predicate and its wait
+    g_stop.store(true);
+  }
   cv_workers.notify_all();
   for (std::thread& t : threads) t.join();
   uint64_t total = 0, dropped = 0;

@@ -26,7 +26,7 @@ class DintCfg(C.Structure):
 class DintStats(C.Structure):
     _fields_ = [("requests", C.c_uint64), ("chunks", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("conflicted", C.c_uint64), ("max_run", C.c_uint64), ("errors", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kv_rebuilds", C.c_uint64), ("reserved", C.c_uint64 * 3)]
 
 
 class DintPeerPtrs(C.Structure):
@@ -49,7 +49,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_flags", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_submit_host", "dint_shard_flags", "dint_cluster_create", "dint_cluster_populate", "dint_cluster_submit", "dint_cluster_engine", "dint_cluster_size", "dint_cluster_destroy", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod", "dint_test_host_slices",
@@ -84,7 +84,14 @@ def lib():
     L.dint_route_combine.restype = i32; L.dint_route_combine.argtypes = [vp, pp, vp, vp, u64, u32, u32, vp, vp]
     L.dint_p2p_wait.restype = i32; L.dint_p2p_wait.argtypes = [vp, vp, u32, u32, vp, vp]
     L.dint_p2p_signal.restype = i32; L.dint_p2p_signal.argtypes = [vp, pp, u32, u32, u32, vp]
-    L.dint_shard_create.restype = i32; L.dint_shard_create.argtypes = [vp, u32, u32, u32, u32, pp, pp, pp, pp, u64, C.POINTER(vp)]
+    L.dint_shard_create.restype = i32; L.dint_shard_create.argtypes = [vp, u32, u32, u32, u32, pp, pp, pp, u64, C.POINTER(vp)]
+    L.dint_shard_submit_host.restype = i32; L.dint_shard_submit_host.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), u64, C.POINTER(vp)]
+    L.dint_cluster_create.restype = i32; L.dint_cluster_create.argtypes = [i32, C.POINTER(DintCfg), i32, C.POINTER(i32), u64, C.POINTER(vp)]
+    L.dint_cluster_populate.restype = i32; L.dint_cluster_populate.argtypes = [vp]
+    L.dint_cluster_submit.restype = i32; L.dint_cluster_submit.argtypes = [vp, vp, u64, vp, vp]
+    L.dint_cluster_engine.restype = vp; L.dint_cluster_engine.argtypes = [vp, i32]
+    L.dint_cluster_size.restype = u32; L.dint_cluster_size.argtypes = [vp]
+    L.dint_cluster_destroy.restype = None; L.dint_cluster_destroy.argtypes = [vp]
     L.dint_shard_destroy.restype = None; L.dint_shard_destroy.argtypes = [vp]
     L.dint_shard_submit_many.restype = i32; L.dint_shard_submit_many.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), u64, C.POINTER(vp), vp]
     L.dint_shard_flags.restype = i32; L.dint_shard_flags.argtypes = [vp, C.POINTER(u32)]
@@ -370,3 +377,58 @@ class Engine:
         arr = (DintKernelTime * 16)()
         k = lib().dint_kernel_times(self.h, arr, 16)
         return {arr[i].name.decode(): (arr[i].launches, arr[i].total_ms) for i in range(max(k, 0))}
+
+
+class GpuCluster:
+    """G shard engines driven by ONE process (dint_cluster_*): the C-level multi-GPU server.  devices: CUDA ordinals,
+    all distinct (NVLink peer access) or all the same (several shards resident on one GPU)."""
+
+    def __init__(self, kind, n_shards, devices=None, max_batch=0, populate=False, **cfg_over):
+        self.kind, self.msg, self.G = kind, MSG_SIZE[kind], n_shards
+        cfg = default_cfg(kind, **cfg_over)
+        dv = (C.c_int * n_shards)(*devices) if devices is not None else None
+        h = C.c_void_p()
+        rc = lib().dint_cluster_create(kind, C.byref(cfg), n_shards, dv, max_batch, C.byref(h))
+        if rc != 0:
+            raise DintError(rc, f"dint_cluster_create({KIND_NAMES[kind]}, {n_shards})")
+        self.h = h
+        if populate:
+            rc = lib().dint_cluster_populate(self.h)
+            if rc != 0:
+                raise DintError(rc, "dint_cluster_populate")
+
+    def submit(self, req, dst=None, out=None, check=True):
+        raw = np.ascontiguousarray(req).view(np.uint8).reshape(-1)
+        n = raw.size // self.msg
+        if out is None:
+            out = np.empty_like(raw)
+        d = None if dst is None else np.ascontiguousarray(dst, dtype=np.uint8)
+        rc = lib().dint_cluster_submit(self.h, raw.ctypes.data, n, None if d is None else d.ctypes.data, out.ctypes.data)
+        if rc != 0 and (check or rc != DINT_EPROTO):
+            raise DintError(rc, "dint_cluster_submit")
+        return out
+
+    def engine(self, shard):
+        """A non-owning Engine view of one shard (state inspection)."""
+        e = Engine.__new__(Engine)
+        e.kind, e.msg, e.device, e.cfg = self.kind, self.msg, None, None
+        e.h = C.c_void_p(lib().dint_cluster_engine(self.h, shard))
+        e.close = lambda: None
+        return e
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().dint_cluster_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

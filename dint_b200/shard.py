@@ -100,7 +100,7 @@ class ShardedEngine:
     def _cap(self, n):
         mean = (n + self.world - 1) // self.world
         cap = int(mean * self.slab_slack) + int(8 * (mean ** 0.5)) + 64
-        return (cap + 15) // 16 * 16
+        return (cap + 127) // 128 * 128          # whole engine tiles: a reply tile never straddles two sources' slabs
 
     def _init_p2p(self, max_n, n_sets=3):
         """Symmetric buffer per rank: n_sets x {inbox [world][cap] | outbox [world][cap]} | signal block, mapped by
@@ -111,8 +111,7 @@ class ShardedEngine:
         self.p2p_max_n = max_n
         cap = self._cap(max_n)
         region = (W * cap * self.msg + 255) // 256 * 256
-        push = os.environ.get("DINT_SHARD_PUSH") == "1"          # experimental: owners store the replies into return buffers
-        k = 3 if push else 2                                     # regions per set: inbox | outbox [| return buffer]
+        k = 2                                                    # regions per set: inbox | return buffer
         self.sym = symm_mem.empty(n_sets * k * region + 4096, dtype=torch.uint8, device=self.device)
         grp = self.group if self.group is not None else dist.group.WORLD
         self.sym_hdl = symm_mem.rendezvous(self.sym, group=grp.group_name)
@@ -121,11 +120,10 @@ class ShardedEngine:
         self.sym_hdl.barrier()
         ptrs = [int(p) for p in self.sym_hdl.buffer_ptrs]
         inbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region for p in ptrs]) for s in range(n_sets)])
-        outbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region + region for p in ptrs]) for s in range(n_sets)])
-        retbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region + 2 * region for p in ptrs]) for s in range(n_sets)]) if push else None
+        retbox = (DintPeerPtrs * n_sets)(*[DintPeerPtrs.of([p + s * k * region + region for p in ptrs]) for s in range(n_sets)])
         sig = DintPeerPtrs.of([p + n_sets * k * region for p in ptrs])
         ctx = C.c_void_p()
-        rc = lib().dint_shard_create(self.engine.h, W, self.rank, cap, n_sets, inbox, outbox, retbox, C.byref(sig), max_n, C.byref(ctx))
+        rc = lib().dint_shard_create(self.engine.h, W, self.rank, cap, n_sets, inbox, retbox, C.byref(sig), max_n, C.byref(ctx))
         if rc != 0:
             raise DintError(rc, "dint_shard_create")
         self.p2p_ctx = ctx
@@ -144,6 +142,19 @@ class ShardedEngine:
         rc = lib().dint_shard_submit_many(self.p2p_ctx, k, a_req, a_dst, n, a_out, C.c_void_p(s) if s else None)
         if rc != 0:
             raise DintError(rc, "dint_shard_submit_many")
+        return outs
+
+    def submit_many_host(self, reqs, outs, dsts=None):
+        """k equally sized batches from / to pinned HOST tensors through dint_shard_submit_host (H2D | dispatch | engine |
+        combine | D2H pipelined inside the library); returns when every out is complete."""
+        k = len(reqs)
+        n = reqs[0].numel() // self.msg
+        a_req = (C.c_void_p * k)(*[r.data_ptr() for r in reqs])
+        a_out = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
+        a_dst = None if dsts is None or dsts[0] is None else (C.c_void_p * k)(*[d.data_ptr() for d in dsts])
+        rc = lib().dint_shard_submit_host(self.p2p_ctx, k, a_req, a_dst, n, a_out)
+        if rc != 0:
+            raise DintError(rc, "dint_shard_submit_host")
         return outs
 
     def _submit_gpu_p2p(self, req, n, dst):

@@ -88,7 +88,9 @@ typedef struct dint_stats {
   uint64_t max_run;         /* longest same-slot run seen on the ordered path */
   uint64_t errors;          /* requests answered with type 0xFF */
   uint64_t h2d_bytes, d2h_bytes;
-  uint64_t reserved[4];
+  uint64_t kv_rebuilds;     /* KV tables rehashed to reclaim tombstones (the reference frees entries on delete:
+                               store/udp/kvs.h:124-133) */
+  uint64_t reserved[3];
 } dint_stats;
 
 /* Per-kernel device time, accumulated with CUDA events while profiling is on. */
@@ -173,27 +175,54 @@ int dint_p2p_wait(dint_engine *e, const uint32_t *local_sig_dev, uint32_t n_shar
 int dint_p2p_signal(dint_engine *e, const dint_peer_ptrs *sig_ptrs, uint32_t n_shards, uint32_t rank, uint32_t epoch,
                     void *cuda_stream);
 /* The whole sharded step over NVLink peer memory, driven from ONE host call per sequence of batches (what
- * dint_b200/shard.py uses at N > 1).  Every rank owns n_sets (2..4) buffer sets {inbox, outbox}, each
- * n_shards * cap records, plus one 256-byte signal block (three arrays of 8 epoch words: requests written /
- * replies written / replies read), all in memory its peers map (CUDA IPC / torch symmetric memory), zeroed once.
- *   inbox_sets[s].p[o], outbox_sets[s].p[o]: device address of rank o's set s; sig_blocks->p[o]: rank o's block.
- *   retbox_sets (optional, same shape): return buffers; with DINT_SHARD_PUSH=1 the owners STORE the replies into the
- *   sources' return buffers (posted writes) instead of the sources loading them from the owners' outboxes.
- * dint_shard_submit_many: k batches of n (<= max_n) records each, the same k and n on every rank; batch j+1 is
- * partitioned into the owners' inboxes (dint_route_dispatch) while batch j runs through the local engine on
- * cuda_stream and the replies of batch j-1 are pulled from the owners' outboxes (dint_route_combine); out_dev[j]
- * is complete when cuda_stream reaches the end of the call.  The engine sees the batches in order, so the
- * result equals k sequential collective steps.  dst_dev: NULL, or per batch the client-chosen shard of every
- * record.  dint_shard_flags (synchronises): [0] records that overflowed a slab, [1] timed-out waits, since the
- * last call; both must be 0 for the replies to stand. */
+ * dint_b200/shard.py uses at N > 1, one process per GPU).  Every rank owns n_sets (2..4) buffer sets {inbox, return
+ * buffer}, each n_shards * cap records (cap a multiple of 128), plus one 256-byte signal block (two arrays of 8 epoch
+ * words: requests written / replies written), all in memory its peers map (CUDA IPC / torch symmetric memory), zeroed once.
+ *   inbox_sets[s].p[o], retbox_sets[s].p[o]: device address of rank o's set s; sig_blocks->p[o]: rank o's block.
+ * dint_shard_submit_many: k batches of n (<= max_n) records each, the same k on every rank; batch j+1 is partitioned
+ * into the OWNERS' inboxes (dint_route_dispatch) while batch j runs through the local engine on cuda_stream -- its
+ * apply kernel stores every reply tile straight into the SOURCE's return buffer (posted stores) -- and the replies of
+ * batch j-1 are put back in request order from the local return buffer (dint_route_combine); out_dev[j] is complete
+ * when cuda_stream reaches the end of the call.  The engine sees the batches in order, so the result equals k
+ * sequential collective steps.  dst_dev: NULL, or per batch the client-chosen shard of every record.
+ * dint_shard_submit_host: the same with HOST buffers (pinned recommended): H2D | dispatch | engine | combine | D2H
+ * pipelined n_sets deep; returns when every out_host[j] is complete.
+ * dint_shard_flags (synchronises): [0] records that overflowed a slab, [1] timed-out waits, since the last call;
+ * both must be 0 for the replies to stand. */
 typedef struct dint_shard_ctx dint_shard_ctx;
 int dint_shard_create(dint_engine *e, uint32_t n_shards, uint32_t rank, uint32_t cap, uint32_t n_sets,
-                      const dint_peer_ptrs *inbox_sets, const dint_peer_ptrs *outbox_sets, const dint_peer_ptrs *retbox_sets,
+                      const dint_peer_ptrs *inbox_sets, const dint_peer_ptrs *retbox_sets,
                       const dint_peer_ptrs *sig_blocks, uint64_t max_n, dint_shard_ctx **out);
 void dint_shard_destroy(dint_shard_ctx *c);
 int dint_shard_submit_many(dint_shard_ctx *c, uint32_t k, const void *const *req_dev, const uint8_t *const *dst_dev, uint64_t n,
                            void *const *out_dev, void *cuda_stream);
+int dint_shard_submit_host(dint_shard_ctx *c, uint32_t k, const void *const *req_host, const uint8_t *const *dst_host, uint64_t n,
+                           void *const *out_host);
 int dint_shard_flags(dint_shard_ctx *c, uint32_t out[2]);
+
+/*
+ * Multi-GPU server in ONE process: SURVEY.md section 8(b)'s `dint_create(kind, cfg, n_gpus)` / `dint_submit(e, req, n,
+ * dst_shard, resp)`.  This is what a C/C++ transport front-end binds to serve one key space from all GPUs of a box
+ * (the reference runs one `server_shard <id>` process per machine and lets the CLIENT pick the shard:
+ * tatp/udp/server_shard.cc:278-320, tatp/caladan/client_udp_shard.cc:187,490-531).
+ *   dint_cluster_create: n_gpus shard engines; devices[i] = CUDA ordinal of shard i (NULL: 0..n_gpus-1).  All
+ *     ordinals distinct (peer access over NVLink is enabled between them), or all the same (several shards resident
+ *     on one GPU: same results, used by the 1-GPU tests).  max_batch = records per shard and round (0 = 262144).
+ *     lock_2pl / lock_fasst / store: shard i owns the lock slots / buckets with slot % n_gpus == i -- the slot ONE
+ *     reference server would compute, so the cluster answers exactly like ONE server.  tatp / smallbank: shard i
+ *     is `server_shard i+1` of an n_gpus-machine deployment (primary key % n_gpus, backups +1 and +2; n_gpus = 1 or
+ *     >= 3) and holds only the keys it is a replica of.
+ *   dint_cluster_submit: req/resp are HOST arrays of n wire structs; dst_shard[i] (tatp / smallbank: required, the
+ *     shard the client would have sent record i to; other kinds: NULL) -- resp[i] answers req[i]; semantics: every
+ *     shard sees its records in index order.  Returns 0, DINT_EPROTO, or an error; never blocks on the network.
+ */
+typedef struct dint_cluster dint_cluster;
+int dint_cluster_create(int kind, const dint_cfg *cfg, int n_gpus, const int *devices, uint64_t max_batch, dint_cluster **out);
+int dint_cluster_populate(dint_cluster *c);
+int dint_cluster_submit(dint_cluster *c, const void *req, uint64_t n, const uint8_t *dst_shard, void *resp);
+dint_engine *dint_cluster_engine(dint_cluster *c, int shard);   /* state inspection of one shard */
+uint32_t dint_cluster_size(dint_cluster *c);
+void dint_cluster_destroy(dint_cluster *c);
 int dint_route_unpermute(dint_engine *e, const void *sorted_dev, const uint32_t *perm_dev, uint64_t n, void *out_dev,
                          void *cuda_stream);
 int dint_sync(dint_engine *e);   /* waits for everything submitted on this engine's device */

@@ -237,7 +237,7 @@ static inline uint32_t fastrand(uint64_t *seed) {      /* store/udp/tatp.h:31-34
 }
 
 /* store/udp/tatp.h:45-66.  The reference leaves val.numberx[1..38] uninitialised (a stack struct);
- * in the oracle/_ref build those bytes read back as zero (checked by tests/test_oracle_vs_ref.py), so
+ * in the oracle/_ref build those bytes read back as zero (checked by tests/test_oracle_golden.py), so
  * the restatement zero-fills them. */
 static void populate_store(dint_oracle *o) {
   uint64_t seed = 0xdeadbeef;

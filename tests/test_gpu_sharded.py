@@ -40,8 +40,6 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
             mk, cfg = (lambda r: T.lock2pl_random(n_per_rank, 500, seed=5 + r)), {}
         else:
             mk, cfg = (lambda r: T.store_random(n_per_rank, 400, seed=5 + r)), dict(subs_populate=400)
-        if mode == 'p2p_push':
-            os.environ["DINT_SHARD_PUSH"] = "1"           # owners store the replies into the sources' return buffers
         se = ShardedEngine(kind, chunk=1 << 13, use_slabs=(mode == 'slabs'), use_p2p=mode.startswith('p2p'), p2p_max_n=n_per_rank, **cfg)
         if kind == wire.STORE:
             se.populate()
@@ -71,8 +69,7 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
         dist.destroy_process_group()
 
 
-# p2p_push was written after the last GPU session of round 1: opt-in until it has run once
-MODES = ["exact", "slabs", "p2p"] + (["p2p_push"] if os.environ.get("DINT_FULL_PROPERTIES") == "1" else [])
+MODES = ["exact", "slabs", "p2p"]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
