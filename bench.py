@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- the driver-facing benchmark (see DESIGN.md "Measurement").
+"""bench.py -- the driver-facing benchmark (DESIGN.md section 6 "Measurement").
 
   python bench.py --gpus N --steps K --warmup W            # this repo's GPU engine
   python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU server (oracle/_ref)
 
-Metric (BASELINE.json): committed txns/sec on lock_fasst.  Workload at N = 1: the reference's own
-lock_fasst trace shape (lock_fasst/caladan/trace_init.sh: 24,000,000 lock ids, uniform, 5-10 ids per
-transaction, write probability 0.2) driven closed-loop by 1,048,576 logical clients through the FaSST
-protocol of lock_fasst/caladan/client.cc against a 36,000,000-slot lock table ("REF" in SURVEY.md 8(d)).
-One STEP = one batch of 4 client rounds = 4,194,304 wire requests.  Every step replays a DIFFERENT
-segment of one long recorded closed-loop trace (so inputs are never L2-resident from the previous
-step) from a freshly reset server state, and the reply stream of every step is checked bit-for-bit
-against the closed-loop recording.  BASELINE.json's literal "4800 keys, Zipf 0.8" reading ("HOT") and
-the store GET path are measured too and reported under "extra".
+Metric (BASELINE.json): committed txns/sec on lock_fasst.  Workload at N = 1: the reference's own lock_fasst trace
+shape (lock_fasst/caladan/trace_init.sh: 24,000,000 lock ids, uniform, 5-10 ids per transaction, write probability
+0.2) driven closed-loop by 1,048,576 logical clients through the FaSST protocol of lock_fasst/caladan/client.cc
+against a 36,000,000-slot lock table ("REF" in SURVEY.md 8(d)).  One STEP = one batch of 4 client rounds =
+4,194,304 wire requests.  W + K steps of the closed loop are recorded (every reply of the recording is compared with
+the UNMODIFIED reference server binary fed the same stream); the timed region replays the K recorded steps, device
+resident, in cycles -- the server state is restored from a snapshot at the start of every cycle (inside the timed
+region) so that every cycle reproduces the recording bit for bit -- until it is at least one second long.  Every step
+reads a different 37.7 MB trace segment (K segments >> L2).  At N > 1 every rank drives its own 1,048,576 clients and
+the key space grows with N (36 M slots and 24 M ids PER GPU: constant contention), requests travel to the owning GPU
+through the dispatch / engine / combine step over NVLink; the reference's fixed 36 M / 24 M constants at N > 1, TATP
+and SmallBank on the reference's shard placement, HOT, store GET, lock_2pl, log_server and the UDP front-end are
+reported under "extra".
 """
 import argparse
 import json
@@ -26,13 +30,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CLIENTS = 1 << 20
 ROUNDS_PER_STEP = 4
 STEP_REQS = CLIENTS * ROUNDS_PER_STEP
+TIMED_SECONDS = float(os.environ.get("DINT_BENCH_SECONDS", "1.0"))      # minimum length of every timed region
 # algorithmic bytes per request: wire in + wire out + state at the reference's field granularity
 FASST_BYTES = {4: 22, 5: 26, 6: 22, 7: 22, 8: 30}          # by reply type
 STORE_GET_BYTES = 186
+WORKLOAD = ("lock_fasst REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(write)=0.2, closed-loop FaSST clients "
+            "(read/acquire/validate/commit), 36,000,000-slot table; 1048576 logical clients, 4 rounds = 4194304 requests per step")
 
 
 def peaks():
@@ -43,8 +51,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~1 ms period; the timed region
-    is only tens of milliseconds long, too short for `nvidia-smi -lms`)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period)."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
@@ -63,7 +70,7 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     reasons = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.samples.append((N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), reasons))
-                time.sleep(0.001)
+                time.sleep(0.002)
         except Exception as ex:       # no NVML: report that rather than inventing numbers
             self.samples.append((None, repr(ex)))
 
@@ -81,147 +88,54 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in names.items() if bits & b], "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------------
-def record_closed_loop(eng, wl, n_steps, pinned):
-    """Drive the client state machines against the engine; returns per-step request / reply arrays
-    and per-step committed-transaction counts."""
-    msg = eng.msg
-    reqs = np.empty((n_steps, STEP_REQS * msg), dtype=np.uint8)
-    resps = np.empty_like(reqs)
-    committed = []
-    rq, rs = pinned
-    for s in range(n_steps):
-        before = wl.stats()["committed"]
-        for r in range(ROUNDS_PER_STEP):
-            wl.next(rq.array[: CLIENTS * msg])
-            eng.submit(rq.array[: CLIENTS * msg], out=rs.array[: CLIENTS * msg])
-            wl.feed(rs.array[: CLIENTS * msg])
-            reqs[s, r * CLIENTS * msg:(r + 1) * CLIENTS * msg] = rq.array[: CLIENTS * msg]
-            resps[s, r * CLIENTS * msg:(r + 1) * CLIENTS * msg] = rs.array[: CLIENTS * msg]
-        committed.append(wl.stats()["committed"] - before)
-    return reqs, resps, committed
+class Background(threading.Thread):
+    """fn() on a host thread while the GPU work goes on; .result after join (or an {"unavailable": ...} dict)."""
+
+    def __init__(self, fn):
+        super().__init__(daemon=True)
+        self.fn, self.result = fn, {"unavailable": "did not finish"}
+        self.start()
+
+    def run(self):
+        try:
+            self.result = self.fn()
+        except Exception as ex:
+            self.result = {"unavailable": repr(ex)[:300]}
+
+    def get(self, timeout):
+        self.join(timeout=timeout)
+        return self.result
 
 
-def run_fasst(args, torch, dist, rank, world, fam_name, fam, steps, warmup, do_e2e=True, do_cpu=True):
-    from dint_b200 import Engine, PinnedBuffer, wire
-    from dint_b200.workloads import Workload
-
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    n_steps = steps + warmup
-    msg = 9
-    pinned = (PinnedBuffer(STEP_REQS * msg), PinnedBuffer(STEP_REQS * msg))
-    # ---- record the closed-loop trace against the GPU engine itself ----
-    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
-        wl = Workload(wire.FASST, n_clients=CLIENTS, seed=20230 + rank, **fam)
-        reqs, resps, committed = record_closed_loop(eng, wl, n_steps, pinned)
-        wl_stats = wl.stats()
-    # ---- device-resident replay from a fresh state: the timed region ----
-    out = {}
-    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
-        d_req = torch.from_numpy(reqs).to(dev)
-        d_resp = torch.empty((STEP_REQS * msg,), dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream(dev)
-        ok = True
-        for s in range(warmup):
-            eng.submit_tensor(d_req[s], d_resp)
-        torch.cuda.synchronize(dev)
-        ok &= bool((d_resp.cpu().numpy() == resps[warmup - 1]).all()) if warmup else True
-        eng.reset_stats()
-        eng.profile(Engine.PROF_APPLY)        # events around the dominant kernel only: all-kernel profiling costs ~20 %
-        sampler = ClockSampler(dev.index)
-        sampler.start()
-        time.sleep(0.01)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for s in range(warmup, n_steps):
-            eng.submit_tensor(d_req[s], d_resp)
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
-        eng.profile(False)
-        kt = eng.kernel_times()
-        st = eng.stats()
-        ok &= bool((d_resp.cpu().numpy() == resps[n_steps - 1]).all())
-        out.update(ms=ms, kernel_times=kt, stats=st, clocks=clocks, parity_last_step=ok)
-        # a second, fully profiled replay (not the timed one) for the per-kernel breakdown
-        eng.reset_stats()
-        eng.profile(True)
-        for s in range(warmup, n_steps):
-            eng.submit_tensor(d_req[s], d_resp)
-        torch.cuda.synchronize(dev)
-        eng.profile(False)
-        out["all_kernel_times"] = eng.kernel_times()
-        del d_req
-    timed_committed = sum(committed[warmup:])
-    timed_reqs = steps * STEP_REQS
-    out.update(committed=timed_committed, requests=timed_reqs, wl_stats=wl_stats)
-    # algorithmic bytes of the timed region, from the reply types
-    types = np.concatenate([resps[s].reshape(-1, msg)[:, 0] for s in range(warmup, n_steps)])
-    cnt = np.bincount(types, minlength=9)
-    out["alg_bytes"] = int(sum(FASST_BYTES[t] * int(cnt[t]) for t in FASST_BYTES))
-    out["reply_mix"] = {str(t): int(cnt[t]) for t in FASST_BYTES}
-    # ---- end to end through the host-facing C ABI call (pinned host buffers, H2D + D2H inside) ----
-    if do_e2e:
-        with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
-            rq, rs = pinned
-            for s in range(warmup):
-                rq.array[:] = reqs[s]
-                eng.submit(rq.array, out=rs.array)
-            host_in = [PinnedBuffer(STEP_REQS * msg) for _ in range(min(steps, 4))]
-            t_e2e, ok2 = 0.0, True
-            for s in range(warmup, n_steps):
-                b = host_in[(s - warmup) % len(host_in)]
-                b.array[:] = reqs[s]                        # staging into pinned memory: not timed
-                if dist is not None:
-                    dist.barrier()
-                torch.cuda.synchronize(dev)
-                t0 = time.perf_counter()
-                eng.submit(b.array, out=rs.array)           # timed: H2D + kernels + D2H, returns when resp is complete
-                t_e2e += time.perf_counter() - t0
-                if s == n_steps - 1:
-                    ok2 = bool((rs.array == resps[s]).all())
-            out.update(e2e_s=t_e2e, e2e_parity=ok2)
-    # ---- CPU baseline: the unmodified reference server, one handler thread, bounded sample ----
-    if do_cpu and rank == 0:
-        out["cpu_baseline"] = cpu_baseline(wire.FASST, reqs[0], wl_stats["committed"] / wl_stats["requests"], threads=1,
-                                           target_s=12.0, check_against=resps[0])
-    return out
+def masked_equal(kind, got, want):
+    """Replies equal up to the value bytes the reference's populate_* leaves indeterminate (tests/golden_util.py)."""
+    import golden_util as G
+    from dint_b200 import wire
+    if kind not in (wire.STORE, wire.TATP):
+        return bool(np.array_equal(got, want))
+    return G.mismatch(kind, np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)) is None
 
 
-def cpu_baseline(kind, sample_req, txn_per_req, threads, target_s, check_against=None):
-    """Time oracle/_ref (the reference's own server.cc under the replay shim) on the host cores."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def reference_check(kind, req, resp, txn_per_req, what, threads=1, timeout=600):
+    """The UNMODIFIED reference server (oracle/_ref, replay shim, `server 1`) over the very request stream the GPU
+    served: are the GPU's replies the reference's?  The same run is the 1-core handler-only CPU baseline."""
     import oracle_lib as O
-    if not O.ref_available(kind):
-        # the C restatement, timed in-process ("port")
-        ora = O.Oracle(kind)
-        t0 = time.perf_counter()
-        ora.process(sample_req)
-        dt = time.perf_counter() - t0
-        n = sample_req.size // O.MSG_SIZE[kind]
-        return {"value": n / dt * txn_per_req, "unit": "txn/s", "cores": 1, "kind": "port",
-                "sample": f"{n} requests once through oracle/libdint_oracle.so", "req_per_s": n / dt}
-    n = sample_req.size // O.MSG_SIZE[kind]
-    # calibrate the repeat count on one pass
-    out, st = O.run_ref(kind, sample_req, threads=1, repeat=1, want_out=check_against is not None)
-    parity = None
-    if check_against is not None:
-        parity = bool(np.array_equal(out, check_against))
-    rate1 = st["req_per_s"]
-    repeat = max(1, int(target_s * rate1 * max(1, threads) * 0.7 / n))
-    _, st = O.run_ref(kind, sample_req, threads=threads, repeat=repeat, want_out=False, spread=threads > 1)
-    res = {"value": st["req_per_s"] * txn_per_req, "unit": "txn/s", "cores": threads, "kind": "reference",
-           "sample": f"first step of the trace ({n} requests) x {repeat} passes through oracle/_ref "
-                     f"`server {threads}` under the replay shim ({st['seconds']:.1f} s)",
-           "req_per_s": st["req_per_s"], "gpu_replies_equal_reference": parity}
-    res["udp_as_shipped"] = udp_as_shipped(O, kind, sample_req, txn_per_req)
-    return res
+    n = req.size // O.MSG_SIZE[kind]
+    if O.ref_available(kind):
+        t0 = time.time()
+        out, st = O.run_ref(kind, req, threads=threads, repeat=1, want_out=True, timeout=timeout)
+        eq = masked_equal(kind, resp, out)
+        return {"value": st["req_per_s"] * txn_per_req, "unit": "txn/s", "cores": threads, "kind": "reference", "req_per_s": st["req_per_s"],
+                "sample": f"{what}: {n} requests once through the oracle/_ref server binary under the replay shim "
+                          f"({st['seconds']:.2f} s handler time, {time.time() - t0:.0f} s wall incl. start-up / population)",
+                "gpu_replies_equal_reference": eq, "compared_requests": n}
+    ora = O.Oracle(kind)
+    t0 = time.perf_counter()
+    out = ora.process(req)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt * txn_per_req, "unit": "txn/s", "cores": 1, "kind": "port", "req_per_s": n / dt,
+            "sample": f"{what}: {n} requests once through oracle/libdint_oracle.so (the C restatement; oracle/_ref not built)",
+            "gpu_replies_equal_reference": bool(np.array_equal(out, resp)), "compared_requests": n}
 
 
 def udp_as_shipped(O, kind, sample_req, txn_per_req, seconds=4.0):
@@ -238,6 +152,379 @@ def udp_as_shipped(O, kind, sample_req, txn_per_req, seconds=4.0):
         return {"unavailable": repr(ex)[:200]}
 
 
+# ----------------------------------------------------------------------------------------------------
+def record_closed_loop(submit, wl, n_steps, msg):
+    """Drive the client state machines against `submit(req) -> resp`; per-step request / reply arrays and
+    per-step committed-transaction counts."""
+    reqs = np.empty((n_steps, STEP_REQS * msg), dtype=np.uint8)
+    resps = np.empty_like(reqs)
+    committed = []
+    rb = CLIENTS * msg
+    for s in range(n_steps):
+        before = wl.stats()["committed"]
+        for r in range(ROUNDS_PER_STEP):
+            q = wl.next(reqs[s, r * rb:(r + 1) * rb])
+            a = submit(q)
+            wl.feed(a)
+            resps[s, r * rb:(r + 1) * rb] = a
+        committed.append(wl.stats()["committed"] - before)
+    return reqs, resps, committed
+
+
+def fasst_alg_bytes(resps, msg=9):
+    cnt = np.bincount(resps.reshape(-1, msg)[:, 0], minlength=9)
+    return int(sum(FASST_BYTES[t] * int(cnt[t]) for t in FASST_BYTES)), {str(t): int(cnt[t]) for t in FASST_BYTES}
+
+
+def cycles_for(step_ms, k):
+    return max(1, int(np.ceil(TIMED_SECONDS * 1e3 / max(step_ms * k, 1e-6))))
+
+
+def run_fasst(args, torch, fam_name, fam, steps, warmup, do_e2e=True, do_ref=True, timed_seconds=None):
+    """N = 1.  Returns the result dict main() turns into the JSON line."""
+    from dint_b200 import Engine, PinnedBuffer, wire
+    from dint_b200.workloads import Workload
+    global TIMED_SECONDS
+    if timed_seconds is not None:
+        saved, TIMED_SECONDS = TIMED_SECONDS, timed_seconds
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    n_steps, msg = steps + warmup, 9
+    rq_pin, rs_pin = PinnedBuffer(CLIENTS * msg), PinnedBuffer(CLIENTS * msg)
+    # ---- record the closed loop against the GPU engine (host path: one dint_submit per client round) ----
+    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+        wl = Workload(wire.FASST, n_clients=CLIENTS, seed=20230, **fam)
+
+        def submit(q):
+            rq_pin.array[:] = q
+            return eng.submit(rq_pin.array, out=rs_pin.array)
+        reqs, resps, committed = record_closed_loop(submit, wl, n_steps, msg)
+        wl_stats = wl.stats()
+    txn_per_req = wl_stats["committed"] / wl_stats["requests"]
+    out = {"wl_stats": wl_stats}
+    ref_bg = None
+    if do_ref:                                   # every recorded reply vs the unmodified reference binary, in the background
+        ref_bg = Background(lambda: reference_check(wire.FASST, reqs.reshape(-1), resps.reshape(-1), txn_per_req,
+                                                    f"the whole recorded closed loop ({n_steps} steps)"))
+    # ---- device-resident replay from a fresh state: the timed region ----
+    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+        d_req = torch.from_numpy(reqs).to(dev)
+        d_out = [torch.empty((STEP_REQS * msg,), dtype=torch.uint8, device=dev) for _ in range(steps)]
+        stream = torch.cuda.current_stream(dev)
+        for s in range(warmup):
+            eng.submit_tensor(d_req[s], d_out[0])
+        torch.cuda.synchronize(dev)
+        ok = bool((d_out[0].cpu().numpy() == resps[warmup - 1]).all()) if warmup else True
+        snap = eng.snapshot()                    # the state every cycle starts from
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(stream)
+        for s in range(steps):                   # one untimed cycle: sizes the timed region, warms everything
+            eng.submit_tensor(d_req[warmup + s], d_out[s])
+        ev[1].record(stream)
+        torch.cuda.synchronize(dev)
+        cycles = cycles_for(ev[0].elapsed_time(ev[1]) / steps, steps)
+        eng.reset_stats()
+        eng.profile(Engine.PROF_APPLY)           # events around the dominant kernel only (all-kernel profiling costs ~20 %)
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        time.sleep(0.01)
+        torch.cuda.synchronize(dev)
+        ev[0].record(stream)
+        for _ in range(cycles):
+            eng.restore(snap, stream.cuda_stream)                # inside the timed region
+            for s in range(steps):
+                eng.submit_tensor(d_req[warmup + s], d_out[s])
+        ev[1].record(stream)
+        torch.cuda.synchronize(dev)
+        ms = ev[0].elapsed_time(ev[1])
+        clocks = sampler.stop()
+        eng.profile(False)
+        kt, st = eng.kernel_times(), eng.stats()
+        n_bad = sum(0 if bool((d_out[s].cpu().numpy() == resps[warmup + s]).all()) else 1 for s in range(steps))
+        out.update(ms=ms, cycles=cycles, kernel_times=kt, stats=st, clocks=clocks, parity_replay=(ok and n_bad == 0))
+        # a fully profiled cycle (not the timed one) for the per-kernel breakdown
+        eng.reset_stats()
+        eng.profile(True)
+        eng.restore(snap, stream.cuda_stream)
+        for s in range(steps):
+            eng.submit_tensor(d_req[warmup + s], d_out[s])
+        torch.cuda.synchronize(dev)
+        eng.profile(False)
+        out["all_kernel_times"] = eng.kernel_times()
+        eng.free_snapshot(snap)
+        del d_req, d_out
+    out.update(committed=sum(committed[warmup:]) * cycles, requests=steps * STEP_REQS * cycles, steps_timed=steps * cycles)
+    alg, mix = fasst_alg_bytes(resps[warmup:])
+    out.update(alg_bytes=alg * cycles, reply_mix=mix)
+    # ---- end to end through the host-facing C ABI call (pinned host buffers, H2D + D2H inside) ----
+    if do_e2e:
+        with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+            host_in = [PinnedBuffer(STEP_REQS * msg) for _ in range(steps)]
+            host_out = PinnedBuffer(STEP_REQS * msg)
+            for s in range(warmup):
+                host_in[0].array[:] = reqs[s]
+                eng.submit(host_in[0].array, out=host_out.array)
+            for s in range(steps):
+                host_in[s].array[:] = reqs[warmup + s]              # staging into pinned memory: not timed
+            snap = eng.snapshot()
+            t_e2e, n_e2e, ok2 = 0.0, 0, True
+            while t_e2e < TIMED_SECONDS:
+                eng.restore(snap, 0)
+                torch.cuda.synchronize(dev)
+                for s in range(steps):
+                    t0 = time.perf_counter()
+                    eng.submit(host_in[s].array, out=host_out.array)   # timed: H2D + kernels + D2H, returns when resp is complete
+                    t_e2e += time.perf_counter() - t0
+                    n_e2e += 1
+                ok2 = ok2 and bool((host_out.array == resps[n_steps - 1]).all())
+            eng.free_snapshot(snap)
+            out.update(e2e_s=t_e2e, e2e_steps=n_e2e, e2e_parity=ok2,
+                       e2e_committed=sum(committed[warmup:]) * (n_e2e // steps), e2e_requests=STEP_REQS * n_e2e)
+    if ref_bg is not None:
+        out["cpu_baseline"] = ref_bg.get(timeout=600)
+    if timed_seconds is not None:
+        TIMED_SECONDS = saved
+    out["first_step"] = (reqs[0], resps[0], txn_per_req)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- N > 1
+def gather_prefix(torch, dist, rank, world, arr):
+    """uint8 numpy array of equal size on every rank -> list of all ranks' arrays on rank 0 (NCCL gather)."""
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, parts, dst=0)
+    return [p.cpu().numpy() for p in parts] if rank == 0 else None
+
+
+def run_fasst_sharded(args, torch, dist, rank, world, scaled, steps, warmup, do_e2e=True):
+    """Every rank drives its own 1,048,576 clients; requests are routed to the owning shard through the library's
+    dispatch / engine / combine step over NVLink peer memory (dint_shard_submit_many).  scaled=True: the key space
+    grows with the GPU count (36 M slots and 24 M ids per GPU: the per-GPU state and the contention stay what they are
+    at N = 1); scaled=False: the reference's constants (every added GPU adds clients to the SAME 24 M ids)."""
+    import oracle_lib as O
+    from dint_b200 import wire
+    from dint_b200.shard import ShardedEngine
+    from dint_b200.workloads import Workload
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_steps, msg = steps + warmup, 9
+    big = args.chunk + args.chunk // 2                   # one round + slab padding fits one engine chunk
+    slots = 36_000_000 * (world if scaled else 1)
+    ids = 24_000_000 * (world if scaled else 1)
+    mk = lambda: ShardedEngine(wire.FASST, chunk=big, strict=False, use_p2p=True, p2p_max_n=CLIENTS, lock_slots=slots)
+    se = mk()
+    wl = Workload(wire.FASST, n_clients=CLIENTS, seed=20230 + rank, n_keys=ids, zipf_theta=0.0)
+    reqs, resps, committed = record_closed_loop(se.submit, wl, n_steps, msg)
+    wl_stats = wl.stats()
+    flags_rec = se.check_p2p()
+    se.close()
+    # ---- oracle parity of the sharded run: ONE sequential server fed the rank-major concatenation, round by round ----
+    P = min(n_steps, warmup + 1)                         # a prefix (it must start from the initial state)
+    g_req = gather_prefix(torch, dist, rank, world, reqs[:P])
+    g_resp = gather_prefix(torch, dist, rank, world, resps[:P])
+    par_bg = None
+    if rank == 0:
+        def check():
+            rb = CLIENTS * msg
+            seq_req = np.concatenate([g_req[r][s, k * rb:(k + 1) * rb] for s in range(P) for k in range(ROUNDS_PER_STEP) for r in range(world)])
+            seq_got = np.concatenate([g_resp[r][s, k * rb:(k + 1) * rb] for s in range(P) for k in range(ROUNDS_PER_STEP) for r in range(world)])
+            n = seq_req.size // msg
+            if not scaled and O.ref_available(wire.FASST):
+                want, st = O.run_ref(wire.FASST, seq_req, threads=1, repeat=1, want_out=True, timeout=900)
+                how = "the unmodified reference server binary (oracle/_ref, `server 1`)"
+            else:
+                t0 = time.perf_counter()
+                want = O.Oracle(wire.FASST, lock_slots=slots).process(seq_req)
+                how = (f"the oracle restatement with kLockHashSize = {slots} (the reference binary's table size is a constexpr 36,000,000)"
+                       if scaled else "the oracle restatement")
+            return {"gpu_replies_equal_reference": bool(np.array_equal(want, seq_got)), "compared_requests": int(n), "checker": how,
+                    "order": "rank-major concatenation of every client round (SURVEY.md 8(e)): the first %d steps of all %d ranks" % (P, world)}
+        par_bg = Background(check)
+    # ---- timed replay from fresh shards ----
+    se = mk()
+    d_req = torch.from_numpy(reqs).to(dev)
+    rb = CLIENTS * msg
+    stream = torch.cuda.current_stream(dev)
+    last = [None] * steps
+
+    def step(s_, slot):
+        last[slot] = se.submit_many([d_req[s_][r * rb:(r + 1) * rb] for r in range(ROUNDS_PER_STEP)])
+
+    for s in range(warmup):
+        step(s, 0)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    snap = se.engine.snapshot()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record(stream)
+    for s in range(steps):
+        step(warmup + s, s)
+    ev[1].record(stream)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cycles = cycles_for(float(t[0]), steps)
+    se.engine.reset_stats()
+    se.engine.profile(se.engine.PROF_APPLY)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev[0].record(stream)
+    for _ in range(cycles):
+        se.engine.restore(snap, stream.cuda_stream)          # local state, ordered on the engine's stream between two batches
+        for s in range(steps):
+            step(warmup + s, s)
+    ev[1].record(stream)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop()
+    se.engine.profile(False)
+    n_bad = 0
+    for s in range(steps):
+        got = torch.cat(last[s]).cpu().numpy()
+        n_bad += 0 if bool((got == resps[warmup + s]).all()) else 1
+    ok = n_bad == 0 and se.check_p2p() == (0, 0) and flags_rec == (0, 0)
+    out = dict(ms=ms, cycles=cycles, kernel_times=se.engine.kernel_times(), stats=se.engine.stats(), clocks=clocks, parity_replay=ok,
+               committed=sum(committed[warmup:]) * cycles, requests=steps * STEP_REQS * cycles, steps_timed=steps * cycles, wl_stats=wl_stats)
+    alg, mix = fasst_alg_bytes(resps[warmup:])
+    out.update(alg_bytes=alg * cycles, reply_mix=mix)
+    se.engine.free_snapshot(snap)
+    se.close()
+    del d_req
+    # ---- end to end: pinned host -> H2D | dispatch | engine | combine | D2H (dint_shard_submit_host), per step ----
+    if do_e2e:
+        se = mk()
+        pin_in = [torch.from_numpy(reqs[warmup + s].copy()).pin_memory() for s in range(steps)]
+        pin_w = [torch.from_numpy(reqs[s].copy()).pin_memory() for s in range(warmup)]
+        pin_out = torch.empty(STEP_REQS * msg, dtype=torch.uint8).pin_memory()
+        rounds = lambda p: [p[r * rb:(r + 1) * rb] for r in range(ROUNDS_PER_STEP)]
+        for s in range(warmup):
+            se.submit_many_host(rounds(pin_w[s]), rounds(pin_out))
+        snap = se.engine.snapshot()
+        t_e2e, n_e2e, ok2 = 0.0, 0, True
+        go = torch.ones(1, device=dev)
+        while True:
+            se.engine.restore(snap, 0)
+            torch.cuda.synchronize(dev)
+            for s in range(steps):
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                se.submit_many_host(rounds(pin_in[s]), rounds(pin_out))
+                t_e2e += time.perf_counter() - t0
+                n_e2e += 1
+            ok2 = ok2 and bool((pin_out.numpy() == resps[n_steps - 1]).all())
+            go[0] = 1.0 if t_e2e < TIMED_SECONDS else 0.0       # all ranks stop together
+            dist.all_reduce(go, op=dist.ReduceOp.MAX)
+            if float(go[0]) == 0.0:
+                break
+        ok2 = ok2 and se.check_p2p() == (0, 0)
+        se.engine.free_snapshot(snap)
+        out.update(e2e_s=t_e2e, e2e_steps=n_e2e, e2e_parity=ok2, e2e_committed=sum(committed[warmup:]) * (n_e2e // steps),
+                   e2e_requests=STEP_REQS * n_e2e)
+        se.close()
+    if par_bg is not None:
+        out["oracle_parity"] = par_bg.get(timeout=900)
+    out["first_step"] = (reqs[0], resps[0], wl_stats["committed"] / wl_stats["requests"])
+    return out
+
+
+def run_txn_sharded(args, torch, dist, rank, world, kind_name, rounds_timed=12, rounds_warm=8, clients=1 << 19):
+    """BASELINE.json configs[3] / [4]: the TATP mix and SmallBank with hot accounts on N >= 3 GPUs, the reference's
+    placement generalised from 3 to N shard servers (primary key % N, backups +1 / +2, log on the three replica
+    holders: tatp/caladan/client_udp_shard.cc:187,490-531, smallbank/caladan/client_udp_shard.cc:441-577).  Every rank
+    IS one shard server (it holds only the keys it is a replica of) and also receives the requests of its own
+    `clients` closed-loop clients, which name the destination shard of every record; the exchange step delivers them."""
+    from dint_b200 import wire
+    from dint_b200.shard import ShardedEngine
+    from dint_b200.txn_workloads import TxnWorkload
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kind = wire.TATP if kind_name == "tatp" else wire.SMALLBANK
+    subscribers = 7_000_000 if kind == wire.TATP else 24_000_000
+    msg = wire.MSG_SIZE[kind]
+    wl = TxnWorkload(kind, n_clients=clients, n_shards=world, subscribers=subscribers, gid0=rank * clients)
+    max_n = int(wl._dst.size)
+    big = 1 << 22
+    t0 = time.time()
+    mk = lambda: ShardedEngine(kind, by_dst=True, chunk=big, strict=False, use_p2p=True, p2p_max_n=max_n, slab_slack=2.0)
+    se = mk()
+    se.populate()
+    t_pop = time.time() - t0
+    rec, committed = [], []
+    mine_req, mine_resp = [], []                          # what rank 0's shard is sent by this rank, per round
+    for r in range(rounds_warm + rounds_timed):
+        before = wl.stats()["committed"]
+        rq, dst = wl.next()
+        rs = se.submit(rq, dst)
+        wl.feed(rs)
+        rec.append((rq.copy(), dst.copy(), np.array(rs, copy=True)))
+        committed.append(wl.stats()["committed"] - before)
+        sel = dst == 0
+        mine_req.append(np.ascontiguousarray(rq.reshape(-1, msg)[sel]).reshape(-1))
+        mine_resp.append(np.ascontiguousarray(np.asarray(rs).reshape(-1, msg)[sel]).reshape(-1))
+    st = wl.stats()
+    flags_rec = se.check_p2p()
+    se.close()
+    # shard 0's whole input stream (round by round, source-rank-major) and what it answered, to rank 0
+    payload = [None] * world if rank == 0 else None
+    dist.gather_object((mine_req, mine_resp), payload, dst=0)
+    bg = None
+    if rank == 0:
+        n_rounds = rounds_warm + rounds_timed
+        s_req = np.concatenate([payload[r][0][k] for k in range(n_rounds) for r in range(world)])
+        s_resp = np.concatenate([payload[r][1][k] for k in range(n_rounds) for r in range(world)])
+        bg = Background(lambda: reference_check(kind, s_req, s_resp, st["committed"] / max(1, st["requests"]),
+                                                f"shard server 0's whole input stream of the recorded closed loop ({n_rounds} rounds, all {world} ranks' clients)", timeout=900))
+    # timed: device-resident replay from freshly populated shards; the state is restored per cycle OUTSIDE the timed region
+    se = mk()
+    se.populate()
+    d = [(torch.from_numpy(q).to(dev), torch.from_numpy(dd).to(dev)) for q, dd, _ in rec]
+    stream = torch.cuda.current_stream(dev)
+    for r in range(rounds_warm):
+        se.submit_many([d[r][0]], dsts=[d[r][1]])
+    torch.cuda.synchronize(dev)
+    snap = se.engine.snapshot()
+    total_ms, cycles, outs = 0.0, 0, None
+    go = torch.ones(1, device=dev)
+    while True:
+        se.engine.restore(snap, stream.cuda_stream)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        outs = [se.submit_many([d[r][0]], dsts=[d[r][1]])[0] for r in range(rounds_warm, rounds_warm + rounds_timed)]
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms += float(t[0])
+        cycles += 1
+        if total_ms >= TIMED_SECONDS * 1e3 or cycles >= 400:
+            break
+    ok = all(bool((outs[i].cpu().numpy() == rec[rounds_warm + i][2]).all()) for i in range(rounds_timed))
+    ok = ok and se.check_p2p() == (0, 0) and flags_rec == (0, 0)
+    est = se.engine.stats()
+    se.engine.free_snapshot(snap)
+    se.close()
+    w = torch.tensor([sum(committed[rounds_warm:]), sum(x[1].size for x in rec[rounds_warm:]), st["committed"], st["txns"], st["requests"],
+                      est["kernel_launches"], est["conflicted"], 1.0 if ok else 0.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    tc, tr = float(w[0]) * cycles, float(w[1]) * cycles
+    res = {"workload": f"{kind_name} mix, {clients} closed-loop clients per GPU, {world} shard servers (one per GPU, reference placement generalised to "
+                       f"{world} shards), {subscribers} {'subscribers' if kind == wire.TATP else 'accounts'}; {rounds_timed} protocol rounds per cycle, "
+                       f"{cycles} cycles timed (device-resident replay of the recorded closed loop, state restored between cycles)",
+           "txn_per_s": tc / (total_ms * 1e-3), "requests_per_s": tr / (total_ms * 1e-3), "abort_rate": 1.0 - float(w[2]) / max(1.0, float(w[3])),
+           "requests_per_txn": float(w[4]) / max(1.0, float(w[3])), "timed_region_s": total_ms * 1e-3,
+           "replies_bit_exact_vs_closed_loop_recording": float(w[7]) == world, "gpu_launches": int(w[5]),
+           "conflicted_fraction": float(w[6]) / max(1.0, float(w[1])), "populate_s": round(t_pop, 1)}
+    res["cpu_baseline"] = bg.get(timeout=900)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------- extras (N = 1)
 def run_closed_loop_extra(args, torch, rank, kind_name, rounds=16, warm=24):
     """lock_2pl / log_server side measurement: the reference's closed-loop clients (workloads.cc) recorded against
     the GPU engine through the host path, then replayed device-resident and timed; replies must be bit-exact."""
@@ -259,33 +546,48 @@ def run_closed_loop_extra(args, torch, rank, kind_name, rounds=16, warm=24):
             reqs.append(q.copy()); resps.append(a.copy())
             committed.append(wl.stats()["committed"] - before)   # transactions whose last reply arrived this round
     st = wl.stats()
+    n_chk = min(len(reqs), 8 if kind == wire.LOG else warm + rounds)
+    bg = Background(lambda: reference_check(kind, np.concatenate(reqs[:n_chk]), np.concatenate(resps[:n_chk]), st["committed"] / max(1, st["requests"]),
+                                            f"the first {n_chk} rounds of the recorded closed loop"))
     with Engine(kind, device=dev.index, chunk=args.chunk) as eng:
         d_req = [torch.from_numpy(r).to(dev) for r in reqs]
-        d_out = torch.empty_like(d_req[0])
+        d_out = [torch.empty_like(d_req[0]) for _ in range(rounds)]
         for r in range(warm):
-            eng.submit_tensor(d_req[r], d_out)
+            eng.submit_tensor(d_req[r], d_out[0])
         torch.cuda.synchronize(dev)
-        eng.reset_stats()
+        snap = eng.snapshot()
+        stream = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for r in range(warm, warm + rounds):
-            eng.submit_tensor(d_req[r], d_out)
+        for r in range(rounds):
+            eng.submit_tensor(d_req[warm + r], d_out[r])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        cycles = max(1, int(np.ceil(min(TIMED_SECONDS, 0.5) * 1e3 / max(e0.elapsed_time(e1), 1e-3))))
+        eng.reset_stats()
+        e0.record()
+        for _ in range(cycles):
+            eng.restore(snap, stream.cuda_stream)
+            for r in range(rounds):
+                eng.submit_tensor(d_req[warm + r], d_out[r])
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
-        ok = bool((d_out.cpu().numpy() == resps[-1]).all())
+        ok = all(bool((d_out[r].cpu().numpy() == resps[warm + r]).all()) for r in range(rounds))
         est = eng.stats()
-    n_req = rounds * CLIENTS
+        eng.free_snapshot(snap)
+    n_req = rounds * CLIENTS * cycles
     res = {"workload": ("lock_2pl REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(exclusive)=0.2, closed-loop 2PL clients "
                         "(acquire in id order, release in reverse, retry after a reject)" if kind == wire.LOCK2PL else
                         "log_server: key uniform [0, 7,009,999], ver [0,127], 40 random bytes per append") +
-                       f"; {CLIENTS} logical clients, {rounds} rounds timed (device-resident replay of the recorded closed loop)",
-           "requests_per_s": n_req / (ms * 1e-3), "replies_bit_exact": ok, "gpu_launches": est["kernel_launches"],
-           "conflicted_fraction": est["conflicted"] / max(1, est["requests"])}
+                       f"; {CLIENTS} logical clients, {rounds} rounds x {cycles} cycles timed (device-resident replay of the recorded closed loop)",
+           "requests_per_s": n_req / (ms * 1e-3), "timed_region_s": ms * 1e-3, "replies_bit_exact_vs_closed_loop_recording": ok,
+           "gpu_launches": est["kernel_launches"], "conflicted_fraction": est["conflicted"] / max(1, est["requests"])}
     if kind == wire.LOCK2PL:
-        res["txn_per_s"] = sum(committed[warm:]) / (ms * 1e-3)
-        res["requests_per_txn"] = n_req / max(1, sum(committed[warm:]))
+        res["txn_per_s"] = sum(committed[warm:]) * cycles / (ms * 1e-3)
+        res["requests_per_txn"] = rounds * CLIENTS / max(1, sum(committed[warm:]))
         res["lock_rejects"] = st["lock_rejects"]
+    res["cpu_baseline"] = bg.get(timeout=300)
     return res
 
 
@@ -308,10 +610,12 @@ def run_udp_front_end(seconds=4.0):
     with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s0:
         s0.bind(("127.0.0.1", 0))
         port = s0.getsockname()[1]
+    cores = os.cpu_count() or 8
+    n_sock = max(8, min(32, cores // 4))
     with tempfile.TemporaryDirectory() as td:
         tp = os.path.join(td, "trace.bin")
         wire.as_bytes(rec).tofile(tp)
-        srv = subprocess.Popen([_build.UDP_SERVER, "lock_fasst", "--bind", "127.0.0.1", "--port", str(port), "--sockets", "8"],
+        srv = subprocess.Popen([_build.UDP_SERVER, "lock_fasst", "--bind", "127.0.0.1", "--port", str(port), "--sockets", str(n_sock)],
                                stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, start_new_session=True)
         try:
             t0 = time.time()
@@ -325,7 +629,6 @@ def run_udp_front_end(seconds=4.0):
                     banner += srv.stderr.read() or b""
                 except (BlockingIOError, TypeError):
                     pass
-            cores = os.cpu_count() or 8
             ct = max(8, min(32, cores // 4))
             r = subprocess.run([blast, tp, "9", str(port), str(ct), "64", str(seconds)], capture_output=True, timeout=seconds + 60)
             out = json.loads(r.stdout.decode().strip().splitlines()[-1])
@@ -339,10 +642,12 @@ def run_udp_front_end(seconds=4.0):
             except subprocess.TimeoutExpired:
                 os.killpg(srv.pid, signal.SIGKILL)
                 srv.wait()
-    return {"req_per_s": out["req_per_s"], "lost_datagrams": out["lost"], "server_sockets": 8, "client_threads": out["client_threads"],
+    return {"req_per_s": out["req_per_s"], "lost_datagrams": out["lost"], "server_sockets": n_sock, "client_threads": out["client_threads"],
             "window": out["window"], "seconds": out["seconds"],
             "note": "loopback UDP, one datagram per request, recvmmsg/sendmmsg front-end + dint_submit; same replayer as "
-                    "cpu_baseline.udp_as_shipped; replies counted, not compared (parity of this path: tests)"}
+                    "cpu_baseline.udp_as_shipped (which serves the same trace with the unmodified reference server).  Both are bound by the "
+                    "kernel's UDP path (two syscalls' worth of socket work per datagram on both ends), not by the handler; replies are "
+                    "compared bit for bit by tests/test_gpu_parity.py::test_udp_front_end_serves_the_wire_protocol_bit_exact"}
 
 
 def run_store_get(args, torch, rank, steps, warmup):
@@ -353,22 +658,31 @@ def run_store_get(args, torch, rank, steps, warmup):
     n = 1 << 22
     wl = Workload(wire.STORE, n_clients=n, seed=1 + rank)
     first = wl.next().copy()
-    deferred = None
-    if rank == 0:                                          # BASELINE.json configs[0]: the reference store server on the host CPU
-        deferred = DeferredCpuBaseline(wire.STORE, first, 1.0, "the first step of the GET trace")
-        deferred.start()
     with Engine(wire.STORE, device=dev.index, chunk=args.chunk, populate=True) as eng:
         bufs = [torch.from_numpy(first).to(dev)] + [torch.from_numpy(wl.next().copy()).to(dev) for _ in range(steps + warmup - 1)]   # open-loop
         d_out = torch.empty_like(bufs[0])
-        for s in range(warmup):
+        eng.submit_tensor(bufs[0], d_out)
+        torch.cuda.synchronize(dev)
+        first_resp = d_out.cpu().numpy().copy()
+        bg = None
+        if rank == 0:                                      # BASELINE.json configs[0]: the reference store server on the host CPU
+            bg = Background(lambda: reference_check(wire.STORE, first, first_resp, 1.0, "the first step of the GET trace", timeout=300))
+        for s in range(1, warmup):
             eng.submit_tensor(bufs[s], d_out)
         torch.cuda.synchronize(dev)
-        eng.reset_stats()
-        eng.profile(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(warmup, warmup + steps):
             eng.submit_tensor(bufs[s], d_out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        cycles = max(1, int(np.ceil(min(TIMED_SECONDS, 0.5) * 1e3 / max(e0.elapsed_time(e1), 1e-3))))   # reads only: the state never changes
+        eng.reset_stats()
+        eng.profile(Engine.PROF_APPLY)
+        e0.record()
+        for _ in range(cycles):
+            for s in range(warmup, warmup + steps):
+                eng.submit_tensor(bufs[s], d_out)
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
@@ -377,37 +691,20 @@ def run_store_get(args, torch, rank, steps, warmup):
         hits = int((d_out.view(-1, 53)[:, 0] == 3).sum().item())
     peak, how = peaks()
     l, t = kt["k_apply"]
-    ach = STORE_GET_BYTES * n * steps / l / (t / l * 1e-3) / 1e9
-    return {"workload": "store kRead, NURand keys, 24,000,000-key table (reference population), device-resident",
-            "get_per_s": n * steps / (ms * 1e-3), "hit_fraction_last_step": hits / n,
-            "roofline": {"kernel": "k_apply<store>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "peak_source": how, "avg_launch_us": t / l * 1e3},
-            "kernel_ms": {k: v[1] for k, v in kt.items()}, "_deferred_cpu": deferred}
-
-
-class DeferredCpuBaseline(threading.Thread):
-    """The unmodified reference shard server (oracle/_ref, replay shim, one handler thread) over a recorded request
-    stream, in the background: its table population takes most of a minute of host time, the GPU work goes on."""
-
-    def __init__(self, kind, req, txn_per_req, what):
-        super().__init__(daemon=True)
-        self.kind, self.req, self.txn_per_req, self.what = kind, req, txn_per_req, what
-        self.result = {"unavailable": "did not finish"}
-
-    def run(self):
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import oracle_lib as O
-            if not O.ref_available(self.kind):
-                self.result = {"unavailable": "oracle/_ref not built"}
-                return
-            t0 = time.time()
-            _, st = O.run_ref(self.kind, self.req, threads=1, repeat=1, want_out=False, timeout=240)
-            self.result = {"value": st["req_per_s"] * self.txn_per_req, "unit": "txn/s", "cores": 1, "kind": "reference",
-                           "req_per_s": st["req_per_s"], "sample": f"{self.what}: {st['requests']} requests in {st['seconds']:.2f} s "
-                           f"through the oracle/_ref server under the replay shim (population + replay {time.time() - t0:.0f} s wall)"}
-        except Exception as ex:
-            self.result = {"unavailable": repr(ex)[:200]}
+    ach = STORE_GET_BYTES * n * steps * cycles / l / (t / l * 1e-3) / 1e9
+    ach170 = ach * 170.0 / STORE_GET_BYTES
+    res = {"workload": f"store kRead, NURand keys, 24,000,000-key table (reference population), device-resident, {steps} distinct 222 MB steps x {cycles} cycles",
+           "get_per_s": n * steps * cycles / (ms * 1e-3), "timed_region_s": ms * 1e-3, "hit_fraction_last_step": hits / n,
+           "roofline": {"kernel": "k_apply<store>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "peak_source": how, "avg_launch_us": t / l * 1e3,
+                        "algorithmic_bytes_per_request": STORE_GET_BYTES,
+                        "frac_with_this_engines_64B_entry": ach170 / peak,
+                        "note": "186 B/GET is SURVEY 8(d)'s figure (reference 4-key entry); with this engine's one-key 64-byte entry the "
+                                "minimum is 53 + 53 + 64 = 170 B/GET",
+                        "traffic": load_static_traffic("k_apply<store>")}}
+    if bg is not None:
+        res["cpu_baseline"] = bg.get(timeout=400)
+    return res
 
 
 def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, clients=1 << 20):
@@ -437,7 +734,7 @@ def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, client
         rq, dst = wl.next()
         rs = cl.submit(rq, dst)
         wl.feed(rs)
-        order, counts, parts = partition_by_shard(rq, dst, G, msg)
+        parts = partition_by_shard(rq, dst, G, msg)[2]
         rparts = partition_by_shard(rs, dst, G, msg)[2]
         rec.append((parts, rparts))
         committed.append(wl.stats()["committed"] - before)
@@ -445,12 +742,13 @@ def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, client
     st = wl.stats()
     for e in engs:
         e.close()
-    deferred = None
+    bg = None
     if rank == 0:                                          # shard 0's request stream from the start of the recording
-        sample = np.concatenate([np.ascontiguousarray(parts[0]).reshape(-1) for parts, _ in rec[: rounds_warm + 4]])
-        deferred = DeferredCpuBaseline(kind, sample, st["committed"] / max(1, st["requests"]),
-                                       f"shard 0's first {rounds_warm + 4} rounds of the recorded closed loop")
-        deferred.start()
+        nchk = rounds_warm + 4
+        s_req = np.concatenate([np.ascontiguousarray(parts[0]).reshape(-1) for parts, _ in rec[:nchk]])
+        s_resp = np.concatenate([np.ascontiguousarray(rp[0]).reshape(-1) for _, rp in rec[:nchk]])
+        bg = Background(lambda: reference_check(kind, s_req, s_resp, st["committed"] / max(1, st["requests"]),
+                                                f"shard 0's first {nchk} rounds of the recorded closed loop", timeout=600))
     # device-resident replay from freshly populated shards
     engs = make()
     d = [[torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in parts] for parts, _ in rec]
@@ -460,42 +758,64 @@ def run_txn(args, torch, rank, kind_name, rounds_timed=12, rounds_warm=8, client
             if d[r][s_].numel():
                 engs[s_].submit_tensor(d[r][s_], outs[r][s_])
     torch.cuda.synchronize(dev)
+    snaps = [e.snapshot() for e in engs]
+    stream = torch.cuda.current_stream(dev)
     for e in engs:
         e.reset_stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for r in range(rounds_warm, rounds_warm + rounds_timed):
-        for s_ in range(G):
-            if d[r][s_].numel():
-                engs[s_].submit_tensor(d[r][s_], outs[r][s_])
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    ok = all(bool((outs[r][s_].cpu().numpy() == rec[r][1][s_]).all()) for r in (rounds_warm - 1, rounds_warm + rounds_timed - 1) for s_ in range(G))
+    total_ms, cycles = 0.0, 0
+    while total_ms < min(TIMED_SECONDS, 0.5) * 1e3 and cycles < 200:
+        for e, sn in zip(engs, snaps):
+            e.restore(sn, stream.cuda_stream)                  # outside the timed region (GBs of tables)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(rounds_warm, rounds_warm + rounds_timed):
+            for s_ in range(G):
+                if d[r][s_].numel():
+                    engs[s_].submit_tensor(d[r][s_], outs[r][s_])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        total_ms += e0.elapsed_time(e1)
+        cycles += 1
+    ok = all(bool((outs[r][s_].cpu().numpy() == rec[r][1][s_]).all()) for r in range(rounds_warm, rounds_warm + rounds_timed) for s_ in range(G))
     launches = sum(e.stats()["kernel_launches"] for e in engs)
     conflicted = sum(e.stats()["conflicted"] for e in engs)
-    for e in engs:
+    for e, sn in zip(engs, snaps):
+        e.free_snapshot(sn)
         e.close()
-    tc = sum(committed[rounds_warm:])
-    tr = sum(nreq[rounds_warm:])
-    return {"workload": f"{kind_name} mix, {clients} closed-loop clients, 3 shard servers x {subscribers} "
-                        f"{'subscribers' if kind == wire.TATP else 'accounts'} on one GPU, "
-                        f"{rounds_timed} protocol rounds timed (device-resident replay of the recorded closed-loop trace)",
-            "abort_rate": 1.0 - st["committed"] / max(1, st["txns"]),
-            "txn_per_s": tc / (ms * 1e-3), "requests_per_s": tr / (ms * 1e-3), "requests_per_txn": st["requests"] / max(1, st["txns"]),
-            "commit_rate_by_type": {k: round(v[1] / max(1, v[0]), 4) for k, v in st["by_type"].items()},
-            "replies_bit_exact": ok, "gpu_launches": launches, "conflicted_fraction": conflicted / max(1, tr),
-            "populate_s_per_3_shards": round(t_pop, 1), "_deferred_cpu": deferred}
+    tc = sum(committed[rounds_warm:]) * cycles
+    tr = sum(nreq[rounds_warm:]) * cycles
+    res = {"workload": f"{kind_name} mix, {clients} closed-loop clients, 3 shard servers x {subscribers} "
+                       f"{'subscribers' if kind == wire.TATP else 'accounts'} on one GPU, "
+                       f"{rounds_timed} protocol rounds x {cycles} cycles timed (device-resident replay of the recorded closed-loop trace, state restored between cycles)",
+           "abort_rate": 1.0 - st["committed"] / max(1, st["txns"]), "timed_region_s": total_ms * 1e-3,
+           "txn_per_s": tc / (total_ms * 1e-3), "requests_per_s": tr / (total_ms * 1e-3), "requests_per_txn": st["requests"] / max(1, st["txns"]),
+           "commit_rate_by_type": {k: round(v[1] / max(1, v[0]), 4) for k, v in st["by_type"].items()},
+           "replies_bit_exact_vs_closed_loop_recording": ok, "gpu_launches": launches, "conflicted_fraction": conflicted / max(1, tr),
+           "populate_s_per_3_shards": round(t_pop, 1)}
+    if bg is not None:
+        res["cpu_baseline"] = bg.get(timeout=600)
+    return res
 
 
+def load_static_traffic(name):
+    """dram__bytes_read + dram__bytes_write per launch of the named kernel from the committed ncu capture (profiles/):
+    a STATIC figure measured once per round, not by this run."""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tp):
+        return None
+    return json.load(open(tp)).get(name)
+
+
+# ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dint_b200", choices=["dint_b200", "reference"])
     ap.add_argument("--chunk", type=int, default=1 << 20)
-    ap.add_argument("--no-extra", action="store_true", help="skip the HOT and store GET side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements")
     ap.add_argument("--extra-only", default=None, help=argparse.SUPPRESS)     # child-process mode for a side measurement
     args = ap.parse_args()
     if args.extra_only:
@@ -524,108 +844,159 @@ def main():
         dist = dist_mod
     from dint_b200.workloads import REF, HOT
 
+    t_start = time.time()
     if world > 1:
-        from dint_b200 import shard
-        res = shard.bench_fasst_sharded(args, torch, dist, rank, world, REF)
+        res = run_fasst_sharded(args, torch, dist, rank, world, True, args.steps, args.warmup)
     else:
-        res = run_fasst(args, torch, dist, rank, world, "REF", REF, args.steps, args.warmup)
+        res = run_fasst(args, torch, "REF", REF, args.steps, args.warmup)
 
     # reduce over ranks: time = max, work = sum
     ms, committed, reqs = res["ms"], res["committed"], res["requests"]
-    e2e_s = res.get("e2e_s")
+    e2e_s, e2e_c, e2e_r = res.get("e2e_s"), res.get("e2e_committed", 0), res.get("e2e_requests", 0)
+    launches = res["stats"]["kernel_launches"]
+    parity = 1.0 if (res["parity_replay"] and res.get("e2e_parity", True)) else 0.0
     if dist is not None:
         t = torch.tensor([ms, e2e_s or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([committed, reqs, res["stats"]["kernel_launches"]], device="cuda", dtype=torch.float64)
+        w = torch.tensor([committed, reqs, launches, e2e_c, e2e_r, parity, res["alg_bytes"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         ms, e2e_s = float(t[0]), float(t[1]) or None
-        committed, reqs, launches = int(w[0]), int(w[1]), int(w[2])
+        committed, reqs, launches, e2e_c, e2e_r = int(w[0]), int(w[1]), int(w[2]), int(w[3]), int(w[4])
+        parity_all = float(w[5]) == world
+        alg_total = float(w[6])
     else:
-        launches = res["stats"]["kernel_launches"]
+        parity_all, alg_total = parity == 1.0, float(res["alg_bytes"])
+    extra = {}
+    if not args.no_extra and world > 1:
+        # the reference's fixed constants at N GPUs (contention rises with N), checked against the reference BINARY
+        try:
+            r2 = run_fasst_sharded(args, torch, dist, rank, world, False, max(4, args.steps // 4), 3, do_e2e=False)
+            t = torch.tensor([r2["ms"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            w = torch.tensor([r2["committed"], r2["requests"], 1.0 if r2["parity_replay"] else 0.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                extra["lock_fasst_reference_constants"] = {
+                    "workload": f"36,000,000 slots and 24,000,000 ids in total (the reference's constants) shared by {world} x 1048576 clients",
+                    "txn_per_s": float(w[0]) / (float(t[0]) * 1e-3), "requests_per_s": float(w[1]) / (float(t[0]) * 1e-3),
+                    "committed_per_request": float(w[0]) / max(1.0, float(w[1])), "replies_bit_exact_vs_closed_loop_recording": float(w[2]) == world,
+                    "oracle_parity": r2.get("oracle_parity"), "timed_region_s": float(t[0]) * 1e-3}
+        except Exception as ex:
+            extra["lock_fasst_reference_constants"] = {"error": repr(ex)[:300]}
+        if world >= 3:
+            for kn in ("tatp", "smallbank"):
+                try:
+                    r3 = run_txn_sharded(args, torch, dist, rank, world, kn)
+                    if rank == 0:
+                        extra[kn] = r3
+                except Exception as ex:
+                    extra[kn] = {"error": repr(ex)[:300]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     peak, peak_how = peaks()
     kt = res["kernel_times"]
-    name = "k_apply"
-    nl, tot_ms = kt[name]
+    nl, tot_ms = kt["k_apply"]
     avg_s = tot_ms / nl * 1e-3
     alg_per_launch = res["alg_bytes"] / nl
     achieved = alg_per_launch / avg_s / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(name + "<lock_fasst>")
+    akt = res.get("all_kernel_times", kt)
+    roof = {"kernel": "k_apply<lock_fasst>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": load_static_traffic("k_apply<lock_fasst>"),
+            "traffic_source": "static: profiles/ncu_traffic.json (one single-pass ncu capture per round, --cache-control none; not measured by this run)",
+            "peak_source": peak_how, "avg_launch_us": avg_s * 1e6, "launches": nl, "algorithmic_bytes_per_launch": alg_per_launch,
+            "timing": "CUDA events around every k_apply launch of the timed region",
+            "whole_step": {"achieved": alg_total / (ms * 1e-3) / 1e9 / world, "frac": alg_total / (ms * 1e-3) / 1e9 / world / peak,
+                           "note": "all algorithmic bytes of the timed region / its whole duration (every kernel, launch gaps, state restores), per GPU"},
+            "all_kernels_ms_profiled_cycle": {k: round(v[1], 3) for k, v in akt.items()}}
+    if "k_classify" in akt:
+        l1, t1 = akt["k_classify"]
+        ach1 = (res["alg_bytes"] / res["cycles"]) / max(1, l1) / (t1 / l1 * 1e-3) / 1e9 if world == 1 else None
+        roof["k_classify"] = {"avg_launch_us": t1 / l1 * 1e3, "launches_profiled_cycle": l1,
+                              "achieved_same_algorithmic_bytes": ach1, "frac": (ach1 / peak) if ach1 else None,
+                              "note": "second pass over the same requests (conflict flags + replay of the previous chunk): it moves no algorithmic byte "
+                                      "of its own, so its fraction is quoted against the step's algorithmic bytes; from the fully profiled cycle, not the timed one"}
     line = {
         "metric": "committed txns/sec (lock_fasst)", "value": committed / (ms * 1e-3), "unit": "txn/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / res["steps_timed"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "lock_fasst REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(write)=0.2, closed-loop "
-                               "FaSST clients (read/acquire/validate/commit), 36,000,000-slot table; "
-                               f"{CLIENTS} logical clients per GPU, {ROUNDS_PER_STEP} rounds = {STEP_REQS} requests per step per GPU",
+        "config": {"workload": WORKLOAD + (f" -- per GPU; key space scaled with the GPU count: {36 * world},000,000 slots, {24 * world},000,000 ids in total "
+                                           "(constant contention; the reference's fixed constants: extra.lock_fasst_reference_constants)" if world > 1 else ""),
                    "baseline_config": "BASELINE.json configs[1] (lock_fasst OCC validate/commit, 1 B200).  Its '4800 keys, "
                                       "Zipf-0.8, 24M-op' wording is, in the reference, 4800 trace FILES, read fraction 0.8 and 24 M "
                                       "uniform lock ids (BASELINE.md section 1 note, lock_fasst/caladan/trace_init.sh:9-27): the headline "
                                       "runs that reference shape; the literal reading (4800 ids, Zipf 0.8) is extra.lock_fasst_HOT",
                    "requests_per_step": STEP_REQS * world, "chunk": args.chunk,
-                   "cache": "every step replays a different 37.7 MB trace segment (inputs larger than reuse distance; "
-                            "lock/version tables 148.5 MB > 126 MB L2)",
-                   "parallelism": (f"key-space sharded x{world}, exchange={res.get('exchange', 'slabs')} "
-                                   "(dispatch/combine kernels over NVLink peer memory)") if world > 1 else "single GPU"},
+                   "timed_region": f"{res['cycles']} cycles x {args.steps} recorded steps = {res['steps_timed']} steps, {ms * 1e-3:.3f} s; the server state is "
+                                   "restored from a snapshot at the start of every cycle INSIDE the timed region",
+                   "cache": "every step replays a different 37.7 MB trace segment (K segments larger than L2; lock/version tables 148.5 MB > 126 MB L2)",
+                   "parallelism": (f"key-space sharded x{world}: dispatch / engine / combine kernels over NVLink peer memory (owner = slot % {world}), "
+                                   "one process per GPU") if world > 1 else "single GPU"},
         "requests_per_s": reqs / (ms * 1e-3),
-        "replies_bit_exact_vs_closed_loop_recording": bool(res["parity_last_step"]),
+        "timed_region_s": ms * 1e-3,
+        "replies_bit_exact_vs_closed_loop_recording": bool(parity_all),
         "abort_stats": {k: res["wl_stats"][k] for k in ("committed", "validation_aborts", "lock_rejects")},
+        "committed_per_request": committed / max(1, reqs),
         "conflicted_fraction": res["stats"]["conflicted"] / max(1, res["stats"]["requests"]),
         "clocks": res["clocks"],
         "gpu_launches": launches,
-        "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_how,
-                     "avg_launch_us": avg_s * 1e6, "launches": nl, "algorithmic_bytes_per_launch": alg_per_launch,
-                     "all_kernels_ms_profiled_pass": {k: round(v[1], 3) for k, v in res.get("all_kernel_times", kt).items()}},
+        "roofline": roof,
     }
+    if "oracle_parity" in res:
+        line["oracle_parity"] = res["oracle_parity"]
     if e2e_s:
-        line["e2e"] = {"value": committed / e2e_s, "unit": "txn/s", "h2d_bytes_per_step": STEP_REQS * 9 * world,
-                       "d2h_bytes_per_step": STEP_REQS * 9 * world, "requests_per_s": reqs / e2e_s,
-                       "replies_bit_exact": bool(res.get("e2e_parity", False)),
-                       "path": ("dint_submit(): pinned host wire structs -> H2D -> kernels -> D2H, per step" if world == 1 else
-                                "pinned host wire structs -> H2D -> dint_shard_submit_many (dispatch, engine, combine) -> D2H, per step")}
+        line["e2e"] = {"value": e2e_c / e2e_s, "unit": "txn/s", "h2d_bytes_per_step": STEP_REQS * 9 * world,
+                       "d2h_bytes_per_step": STEP_REQS * 9 * world, "requests_per_s": e2e_r / e2e_s, "timed_region_s": e2e_s,
+                       "steps_timed": res.get("e2e_steps"),
+                       "path": ("dint_submit(): pinned host wire structs -> H2D -> kernels -> D2H, one call per step" if world == 1 else
+                                "dint_shard_submit_host(): pinned host wire structs -> H2D | dispatch | engine | combine | D2H pipelined, one call per step")}
     if "cpu_baseline" in res:
         line["cpu_baseline"] = res["cpu_baseline"]
+        if world == 1 and not args.no_extra:
+            import oracle_lib as O
+            rq0, _, tpr = res["first_step"]
+            if O.ref_available(1):
+                line["cpu_baseline"]["udp_as_shipped"] = udp_as_shipped(O, 1, rq0, tpr)
+    elif world > 1:
+        import oracle_lib as O
+        rq0, rs0, tpr = res["first_step"]
+        rb = CLIENTS * 9
+        line["cpu_baseline"] = reference_check(1, rq0[:rb], rs0[:rb], tpr, "rank 0's first client round (timing only: the replies of a sharded run are "
+                                               "checked in oracle_parity)")
+        line["cpu_baseline"].pop("gpu_replies_equal_reference", None)
     if not args.no_extra and world == 1:
         try:
-            hot = run_fasst(args, torch, None, rank, world, "HOT", HOT, max(3, args.steps // 3), 3, do_e2e=False, do_cpu=False)
-            line["extra"] = {"lock_fasst_HOT": {
+            hot = run_fasst(args, torch, "HOT", HOT, max(3, args.steps // 3), 3, do_e2e=False, do_ref=True, timed_seconds=min(TIMED_SECONDS, 0.5))
+            extra["lock_fasst_HOT"] = {
                 "workload": "BASELINE.json literal: 4800 lock ids, Zipf 0.8, same clients/protocol",
                 "txn_per_s": hot["committed"] / (hot["ms"] * 1e-3), "requests_per_s": hot["requests"] / (hot["ms"] * 1e-3),
+                "timed_region_s": hot["ms"] * 1e-3,
                 "abort_stats": {k: hot["wl_stats"][k] for k in ("committed", "validation_aborts", "lock_rejects")},
                 "conflicted_fraction": hot["stats"]["conflicted"] / max(1, hot["stats"]["requests"]),
-                "replies_bit_exact": bool(hot["parity_last_step"])}}
-            line["extra"]["store_get"] = run_store_get(args, torch, rank, max(3, args.steps // 2), 3)
-            line["extra"]["tatp"] = run_txn(args, torch, rank, "tatp")
-            line["extra"]["smallbank"] = run_txn(args, torch, rank, "smallbank")
+                "replies_bit_exact_vs_closed_loop_recording": bool(hot["parity_replay"]), "cpu_baseline": hot.get("cpu_baseline")}
+            extra["store_get"] = run_store_get(args, torch, rank, max(3, args.steps // 2), 3)
+            extra["tatp"] = run_txn(args, torch, rank, "tatp")
+            extra["smallbank"] = run_txn(args, torch, rank, "smallbank")
         except Exception as ex:  # side measurements must never cost the headline line
-            line.setdefault("extra", {})["error"] = repr(ex)
+            extra["error"] = repr(ex)[:300]
         for kn in ("lock_2pl", "log_server"):
-            # newer side measurements run in a child process with a deadline: whatever happens there, the headline stands
+            # side measurements in a child process with a deadline: whatever happens there, the headline stands
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extra-only", kn, "--chunk", str(args.chunk)],
-                                   capture_output=True, timeout=240)
+                                   capture_output=True, timeout=400)
                 rows = [l for l in r.stdout.decode().splitlines() if l.startswith("{")]
-                line["extra"][kn] = json.loads(rows[-1]) if rows else {"error": f"exit {r.returncode}: {r.stderr.decode()[-300:]}"}
+                extra[kn] = json.loads(rows[-1]) if rows else {"error": f"exit {r.returncode}: {r.stderr.decode()[-300:]}"}
             except Exception as ex:
-                line.setdefault("extra", {})[kn] = {"error": repr(ex)[:300]}
+                extra[kn] = {"error": repr(ex)[:300]}
         try:
             torch.cuda.empty_cache()
-            line["extra"]["udp_front_end"] = run_udp_front_end()
+            extra["udp_front_end"] = run_udp_front_end()
         except Exception as ex:
-            line.setdefault("extra", {})["udp_front_end"] = {"error": repr(ex)[:300]}
-    for v in line.get("extra", {}).values():               # background CPU baselines: collect (bounded wait)
-        if isinstance(v, dict) and "_deferred_cpu" in v:
-            d = v.pop("_deferred_cpu")
-            if d is not None:
-                d.join(timeout=120)
-                v["cpu_baseline"] = d.result
+            extra["udp_front_end"] = {"error": repr(ex)[:300]}
+    if extra:
+        line["extra"] = extra
+    line["bench_wall_s"] = round(time.time() - t_start, 1)
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -634,53 +1005,68 @@ def main():
 
 
 def main_reference(args, rank, world):
-    """--impl reference: the reference's own lock_fasst UDP server (oracle/_ref, built from
-    /root/reference unmodified), all host threads, same trace shape / metric."""
+    """--impl reference: the reference's own lock_fasst server (oracle/_ref, built from /root/reference unmodified) on
+    the host cores, handler only (replay shim: no UDP syscalls), on the GPU arm's workload: the same 1,048,576-client
+    closed-loop trace (same seed; recorded here against the CPU restatement, whose replies are the GPU's bit for bit).
+    A step = the first 4 trace steps (16.8 M requests) x `repeat` passes through `server <all cores>`."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     from dint_b200 import wire
     from dint_b200.workloads import Workload, REF
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # the same closed-loop trace shape, recorded against the CPU restatement (no GPU needed on this arm)
-    clients, rounds = 1 << 16, 48          # long enough for transactions to complete (>= 11 rounds each)
     ora = O.Oracle(wire.FASST)
-    wl = Workload(wire.FASST, n_clients=clients, seed=20230, **REF)
-    reqs = []
-    for _ in range(rounds):
-        r = wl.next()
-        wl.feed(ora.process(r))
-        reqs.append(r.copy())
-    sample = np.concatenate(reqs)
+    wl = Workload(wire.FASST, n_clients=CLIENTS, seed=20230, **REF)
+    n_rec = 4
+    reqs, _, _ = record_closed_loop(ora.process, wl, n_rec, 9)
     st = wl.stats()
-    txn_per_req = st["committed"] / st["requests"]
+    # committed / request of the GPU arm's window (steps W.. of the same closed loop) is a little higher than of the first
+    # 4 steps (transactions take >= 11 rounds to complete): use a longer CPU-side recording for the conversion factor
+    for _ in range(8 * ROUNDS_PER_STEP):
+        wl.feed(ora.process(wl.next()))
+    st2 = wl.stats()
+    txn_per_req = (st2["committed"] - st["committed"]) / max(1, st2["requests"] - st["requests"])
+    sample = reqs.reshape(-1)
     n = sample.size // 9
     kind = "reference" if O.ref_available(wire.FASST) else "port"
-    steps, times, reqs_done = args.steps, [], 0
-    for s in range(args.warmup + steps):
+
+    def one(threads, repeat):
         if kind == "reference":
-            _, stt = O.run_ref(wire.FASST, sample, threads=cores, repeat=max(1, cores // 2), want_out=False, spread=True)
-            dt, nn = stt["seconds"], stt["requests"]
-        else:
-            t0 = time.perf_counter(); O.Oracle(wire.FASST).process(sample); dt = time.perf_counter() - t0; nn = n
+            _, stt = O.run_ref(wire.FASST, sample, threads=threads, repeat=repeat, want_out=False, spread=True)
+            return stt["requests"] / stt["seconds"]
+        t0 = time.perf_counter()
+        O.Oracle(wire.FASST).process(sample)
+        return n / (time.perf_counter() - t0)
+
+    rows = {}
+    if kind == "reference":                          # scaling rows: 1 thread, 8 threads (the reference's own setting), all cores
+        for th in sorted({1, min(8, cores), cores}):
+            rep = max(1, int(3.0 * 40e6 * min(th, 16) / n))
+            rates = [one(th, rep) for _ in range(3)]
+            rows[str(th)] = {"req_per_s_median": sorted(rates)[1], "req_per_s_min": min(rates), "req_per_s_max": max(rates), "repeat": rep}
+    rep_all = max(1, int(2.0 * 40e6 * min(cores, 16) / n))
+    times, rates = [], []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = one(cores if kind == "reference" else 1, rep_all)
         if s >= args.warmup:
-            times.append(dt); reqs_done += nn
-    total = sum(times)
-    val = reqs_done / total * txn_per_req
+            rates.append(r)
+            times.append(time.perf_counter() - t0)
+    rate = float(np.median(rates))
+    val = rate * txn_per_req
     line = {"impl": "reference", "metric": "committed txns/sec (lock_fasst)", "value": val, "unit": "txn/s",
-            "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": total / steps * 1e3,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "lock_fasst REF: 24,000,000 uniform lock ids, 5-10 ids/txn, p(write)=0.2, closed-loop "
-                                   "FaSST clients, 36,000,000-slot table",
+            "config": {"workload": WORKLOAD,
                        "note": "handler only: the reference server.cc under the LD_PRELOAD replay shim (no UDP syscalls), "
-                               f"`server {cores}` re-pinned one thread per host core; a step = {n} requests x {max(1, cores // 2)} passes"},
-            "requests_per_s": reqs_done / total,
+                               f"`server {cores}` re-pinned one thread per host core; a step = the first {n_rec} steps of the same closed-loop trace "
+                               f"({n} requests) x {rep_all} passes; value = median over the {args.steps} steps (min {min(rates) * txn_per_req:.3g}, max {max(rates) * txn_per_req:.3g} txn/s)"},
+            "requests_per_s": rate, "committed_per_request": txn_per_req,
+            "spread": {"min_over_median": min(rates) / rate, "max_over_median": max(rates) / rate},
+            "thread_scaling": rows,
             "cpu_baseline": {"value": val, "unit": "txn/s", "cores": cores if kind == "reference" else 1, "kind": kind,
-                             "sample": f"{n}-request closed-loop trace x {max(1, cores // 2)} passes per step"},
+                             "sample": f"{n}-request closed-loop trace x {rep_all} passes per step"},
             "e2e": {"value": val, "unit": "txn/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if kind == "reference":
-        line["cpu_baseline"]["udp_as_shipped"] = udp_as_shipped(O, wire.FASST, sample, txn_per_req)
     print(json.dumps(line))
 
 

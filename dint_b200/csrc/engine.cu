@@ -925,6 +925,66 @@ int dint_submit(dint_engine* e, const void* req, uint64_t n, void* resp) {
   return e->stats.errors != err_before ? DINT_EPROTO : DINT_OK;
 }
 
+// ---- state snapshots (checkpoint / restore of one engine's whole server state, device to device) --------------
+struct dint_snapshot {
+  dint_engine* e = nullptr;
+  std::vector<std::pair<void*, size_t>> live;   // the engine's state arrays
+  std::vector<void*> copy;
+  uint64_t kv_cap[kMaxTables]{};                 // table capacities at snapshot time (a rehash in between invalidates it)
+};
+static void snapshot_regions(dint_engine* e, std::vector<std::pair<void*, size_t>>& r) {
+  const Ctx& c = e->ctx;
+  const uint64_t g = e->total_groups;
+  if (e->kind == DINT_LOCK2PL || e->kind == DINT_SMALLBANK) r.push_back({c.cnt2, g * sizeof(uint2)});
+  if (e->kind == DINT_FASST) { r.push_back({c.ver, g * sizeof(uint32_t)}); r.push_back({c.lockbits, ((g + 31) / 32) * 4}); }
+  if (e->kind == DINT_TATP) r.push_back({c.lockbits, ((g + 31) / 32) * 4});
+  for (uint32_t t = 0; t < c.n_tables; t++) {
+    r.push_back({c.tbl[t].entries, (size_t)(c.tbl[t].cap_mask + 1) << c.tbl[t].ent_shift});
+    r.push_back({c.tbl[t].live, 16});
+  }
+  if (e->has_log) { r.push_back({c.ring, (size_t)c.ring_n * kLogEntry[e->kind]}); r.push_back({c.log_total, 2 * sizeof(unsigned long long)}); }
+}
+int dint_snapshot_create(dint_engine* e, dint_snapshot** out) {
+  if (!e || !out) return set_err(DINT_EINVAL, "null argument");
+  CU(cudaSetDevice(e->device));
+  CU(cudaDeviceSynchronize());
+  dint_snapshot* s = new dint_snapshot();
+  s->e = e;
+  snapshot_regions(e, s->live);
+  for (uint32_t t = 0; t < e->ctx.n_tables; t++) s->kv_cap[t] = e->ctx.tbl[t].cap_mask + 1;
+  for (auto& r : s->live) {
+    void* p = nullptr;
+    cudaError_t ce = cudaMalloc(&p, r.second ? r.second : 1);
+    if (ce != cudaSuccess) { for (void* q : s->copy) cudaFree(q); delete s; return set_err(DINT_ENOMEM, "snapshot", ce); }
+    s->copy.push_back(p);
+    CU(cudaMemcpyAsync(p, r.first, r.second, cudaMemcpyDeviceToDevice, e->stream));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  *out = s;
+  return DINT_OK;
+}
+int dint_snapshot_restore(dint_snapshot* s, void* cuda_stream) {
+  if (!s) return set_err(DINT_EINVAL, "null argument");
+  dint_engine* e = s->e;
+  CU(cudaSetDevice(e->device));
+  for (uint32_t t = 0; t < e->ctx.n_tables; t++)
+    if (s->kv_cap[t] != e->ctx.tbl[t].cap_mask + 1) return set_err(DINT_EINVAL, "a KV table was rehashed since the snapshot");
+  std::vector<std::pair<void*, size_t>> now;
+  snapshot_regions(e, now);
+  if (now.size() != s->live.size()) return set_err(DINT_EINVAL, "snapshot does not match the engine");
+  for (size_t i = 0; i < now.size(); i++) {
+    if (now[i].second != s->live[i].second) return set_err(DINT_EINVAL, "snapshot does not match the engine");
+    CU(cudaMemcpyAsync(now[i].first, s->copy[i], now[i].second, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  }
+  return DINT_OK;
+}
+void dint_snapshot_destroy(dint_snapshot* s) {
+  if (!s) return;
+  cudaSetDevice(s->e->device);
+  for (void* p : s->copy) cudaFree(p);
+  delete s;
+}
+
 int dint_lock_state(dint_engine* e, int table, uint32_t slot, uint32_t out[2]) {
   if (!e || !out) return DINT_EINVAL;
   CU(cudaSetDevice(e->device));

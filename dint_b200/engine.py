@@ -49,7 +49,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_submit_host", "dint_shard_flags", "dint_cluster_create", "dint_cluster_populate", "dint_cluster_submit", "dint_cluster_engine", "dint_cluster_size", "dint_cluster_destroy", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_submit_host", "dint_shard_flags", "dint_cluster_create", "dint_cluster_populate", "dint_cluster_submit", "dint_cluster_engine", "dint_cluster_size", "dint_cluster_destroy", "dint_snapshot_create", "dint_snapshot_restore", "dint_snapshot_destroy", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod", "dint_test_host_slices",
@@ -92,6 +92,9 @@ def lib():
     L.dint_cluster_engine.restype = vp; L.dint_cluster_engine.argtypes = [vp, i32]
     L.dint_cluster_size.restype = u32; L.dint_cluster_size.argtypes = [vp]
     L.dint_cluster_destroy.restype = None; L.dint_cluster_destroy.argtypes = [vp]
+    L.dint_snapshot_create.restype = i32; L.dint_snapshot_create.argtypes = [vp, C.POINTER(vp)]
+    L.dint_snapshot_restore.restype = i32; L.dint_snapshot_restore.argtypes = [vp, vp]
+    L.dint_snapshot_destroy.restype = None; L.dint_snapshot_destroy.argtypes = [vp]
     L.dint_shard_destroy.restype = None; L.dint_shard_destroy.argtypes = [vp]
     L.dint_shard_submit_many.restype = i32; L.dint_shard_submit_many.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), u64, C.POINTER(vp), vp]
     L.dint_shard_flags.restype = i32; L.dint_shard_flags.argtypes = [vp, C.POINTER(u32)]
@@ -317,6 +320,26 @@ class Engine:
             raise DintError(rc, "dint_route_unpermute")
         return out
 
+    def snapshot(self):
+        """Device-to-device copy of the whole server state; returns a handle for restore()."""
+        h = C.c_void_p()
+        rc = lib().dint_snapshot_create(self.h, C.byref(h))
+        if rc != 0:
+            raise DintError(rc, "dint_snapshot_create")
+        return h
+
+    def restore(self, snap, stream=None):
+        """Asynchronous on the current torch stream (or `stream`): order it between submit calls."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        rc = lib().dint_snapshot_restore(snap, C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise DintError(rc, "dint_snapshot_restore")
+
+    def free_snapshot(self, snap):
+        lib().dint_snapshot_destroy(snap)
+
     def sync(self, check=True):
         rc = lib().dint_sync(self.h)
         if rc != 0 and (check or rc != DINT_EPROTO):
@@ -385,7 +408,7 @@ class GpuCluster:
 
     def __init__(self, kind, n_shards, devices=None, max_batch=0, populate=False, **cfg_over):
         self.kind, self.msg, self.G = kind, MSG_SIZE[kind], n_shards
-        cfg = default_cfg(kind, **cfg_over)
+        cfg = self.cfg = default_cfg(kind, **cfg_over)
         dv = (C.c_int * n_shards)(*devices) if devices is not None else None
         h = C.c_void_p()
         rc = lib().dint_cluster_create(kind, C.byref(cfg), n_shards, dv, max_batch, C.byref(h))
@@ -411,7 +434,7 @@ class GpuCluster:
     def engine(self, shard):
         """A non-owning Engine view of one shard (state inspection)."""
         e = Engine.__new__(Engine)
-        e.kind, e.msg, e.device, e.cfg = self.kind, self.msg, None, None
+        e.kind, e.msg, e.device, e.cfg = self.kind, self.msg, None, self.cfg
         e.h = C.c_void_p(lib().dint_cluster_engine(self.h, shard))
         e.close = lambda: None
         return e

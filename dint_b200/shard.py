@@ -103,7 +103,7 @@ class ShardedEngine:
         return (cap + 127) // 128 * 128          # whole engine tiles: a reply tile never straddles two sources' slabs
 
     def _init_p2p(self, max_n, n_sets=3):
-        """Symmetric buffer per rank: n_sets x {inbox [world][cap] | outbox [world][cap]} | signal block, mapped by
+        """Symmetric buffer per rank: n_sets x {inbox [world][cap] | return buffer [world][cap]} | signal block, mapped by
         all peers (torch symmetric memory = CUDA IPC + peer access over NVLink); the step itself is driven by the
         library (dint_shard_submit_many)."""
         import torch.distributed._symmetric_memory as symm_mem
@@ -158,9 +158,9 @@ class ShardedEngine:
         return outs
 
     def _submit_gpu_p2p(self, req, n, dst):
-        """Dispatch = ONE kernel that partitions the batch and stores every run straight into the owners' inboxes
-        (then raises their epoch flags); combine = ONE kernel that loads the replies from their outboxes.  No
-        NCCL call, no host round trip.  Every rank must pass the same n."""
+        """Dispatch partitions the batch and stores every run straight into the owners' inboxes (then raises their epoch
+        flags); the owners' apply kernel stores the replies straight into this rank's return buffer; combine reassembles
+        them locally.  No NCCL call, no host round trip."""
         return self._p2p_many([req], [dst])[0]
 
     def check_p2p(self):
@@ -233,14 +233,15 @@ class ShardedEngine:
         out = torch.empty(n * self.msg, dtype=torch.uint8, device=req.device)
         return eng.route_combine(Engine.slab_ptrs(back.data_ptr(), W, cap * self.msg), state, n, W, cap, out)
 
-    def submit_many(self, reqs):
+    def submit_many(self, reqs, dsts=None):
         """A sequence of collective batches (each rank passes equally many, equally sized tensors), software
         pipelined: batch k+1 is partitioned and exchanged on a side stream while batch k runs through the
         local engine and its replies travel back on the main stream.  The engine still sees the batches in
         order, so the result equals calling submit_tensor() on each batch in turn."""
         eng, W = self.engine, self.world
         if self.use_p2p and reqs[0].numel() // self.msg <= self.p2p_max_n:
-            return self._p2p_many(reqs)
+            return self._p2p_many(reqs, dsts)
+        assert dsts is None, "client-chosen shards: use the p2p step or submit_tensor"
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_side"):
             self._side = torch.cuda.Stream(self.device)
@@ -339,104 +340,3 @@ class ShardedEngine:
             d = None if d is None else d.to(self.device, non_blocking=True)
         out = self.submit_tensor(t, d)
         return out.cpu().numpy()
-
-
-def bench_fasst_sharded(args, torch_mod, dist_mod, rank, world, fam):
-    """bench.py at N > 1: every rank drives its own 1,048,576 logical clients; requests are routed to the
-    owning shard over NCCL.  Returns the same result dict as bench.run_fasst."""
-    import time
-    from .workloads import Workload
-    import bench as B
-    dev = torch.device("cuda", torch.cuda.current_device())
-    steps, warmup = args.steps, max(args.warmup, 3)
-    n_steps = steps + warmup
-    msg = 9
-    big = args.chunk + args.chunk // 2                   # one round + slab padding fits one engine chunk
-    # exchange: "p2p" = dispatch/combine kernels storing to / loading from peer memory over NVLink, driven by
-    # dint_shard_submit_many; "slabs" = the same kernels on local buffers + NCCL all-to-all
-    mode = os.environ.get("DINT_SHARD_MODE", "p2p")
-    if mode == "p2p":
-        # all ranks must take the same path: agree on whether peer-mapped (symmetric) memory is available here
-        try:
-            import torch.distributed._symmetric_memory as _sm          # noqa: F401
-            ok_here = 1
-        except Exception:
-            ok_here = 0
-        t = torch.tensor([ok_here], device=dev, dtype=torch.int32)
-        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MIN)
-        if int(t.item()) == 0:
-            mode = "slabs"
-    mk = lambda: ShardedEngine(wire.FASST, chunk=big, use_slabs=True, strict=False, use_p2p=(mode == "p2p"), p2p_max_n=B.CLIENTS)
-    se = mk()
-    wl = Workload(wire.FASST, n_clients=B.CLIENTS, seed=20230 + rank, **fam)
-    reqs = np.empty((n_steps, B.STEP_REQS * msg), dtype=np.uint8)
-    resps = np.empty_like(reqs)
-    committed = []
-    for s in range(n_steps):
-        before = wl.stats()["committed"]
-        for r in range(B.ROUNDS_PER_STEP):
-            q = wl.next()
-            a = se.submit(q)
-            wl.feed(a)
-            reqs[s, r * B.CLIENTS * msg:(r + 1) * B.CLIENTS * msg] = q
-            resps[s, r * B.CLIENTS * msg:(r + 1) * B.CLIENTS * msg] = a
-        committed.append(wl.stats()["committed"] - before)
-    wl_stats = wl.stats()
-    se.close()
-    # timed replay from fresh shards
-    se = mk()
-    d_req = torch.from_numpy(reqs).to(dev)
-    last = None
-    rb = B.CLIENTS * msg                                 # one collective call per client round, as recorded
-
-    def step(s_):
-        outs = se.submit_many([d_req[s_][r * rb:(r + 1) * rb] for r in range(B.ROUNDS_PER_STEP)])
-        return torch.cat(outs)
-
-    for s in range(warmup):
-        last = step(s)
-    torch.cuda.synchronize(dev)
-    se.engine.reset_stats()
-    se.engine.profile(Engine.PROF_APPLY)
-    sampler = B.ClockSampler(dev.index)
-    sampler.start()
-    dist_mod.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(warmup, n_steps):
-        last = step(s)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    dist_mod.barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    se.engine.profile(False)
-    ok = bool((last.cpu().numpy() == resps[n_steps - 1]).all()) and not se.check_overflow()
-    if se.use_p2p:
-        ok = ok and se.check_p2p() == (0, 0)
-    out = dict(ms=ms, kernel_times=se.engine.kernel_times(), stats=se.engine.stats(), clocks=clocks, parity_last_step=ok,
-               committed=sum(committed[warmup:]), requests=steps * B.STEP_REQS, wl_stats=wl_stats)
-    types = np.concatenate([resps[s].reshape(-1, msg)[:, 0] for s in range(warmup, n_steps)])
-    cnt = np.bincount(types, minlength=9)
-    out["alg_bytes"] = int(sum(B.FASST_BYTES[t] * int(cnt[t]) for t in B.FASST_BYTES))
-    # end to end: pinned host -> device -> collective step -> host
-    t_e2e = 0.0
-    se.close()
-    se = mk()
-    pin = torch.empty(B.STEP_REQS * msg, dtype=torch.uint8).pin_memory()
-    pout = torch.empty_like(pin).pin_memory()
-    for s in range(n_steps):
-        pin.numpy()[:] = reqs[s]
-        dist_mod.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        d = pin.to(dev, non_blocking=True)
-        o = torch.cat(se.submit_many([d[r * rb:(r + 1) * rb] for r in range(B.ROUNDS_PER_STEP)]))
-        pout.copy_(o, non_blocking=True)
-        torch.cuda.synchronize(dev)
-        if s >= warmup:
-            t_e2e += time.perf_counter() - t0
-    out.update(exchange=mode, e2e_s=t_e2e, e2e_parity=bool((pout.numpy() == resps[n_steps - 1]).all()))
-    se.close()
-    return out

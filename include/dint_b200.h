@@ -240,6 +240,15 @@ uint32_t dint_lock_slot(dint_engine *e, int table, uint64_t key_or_lid);
 int dint_dump_log(dint_engine *e, void *out, uint64_t *appended);
 uint32_t dint_log_entry_size(int kind);
 
+/* Checkpoint / restore of the whole server state of one engine (lock words, versions, counters, KV tables, log ring),
+ * device to device.  The reference has no such facility (its state dies with the process); a batched server can take
+ * one between two calls at HBM copy speed.  dint_snapshot_restore is asynchronous on cuda_stream and must be ordered
+ * between submit calls; it fails if a KV table was rehashed since the snapshot. */
+typedef struct dint_snapshot dint_snapshot;
+int dint_snapshot_create(dint_engine *e, dint_snapshot **out);
+int dint_snapshot_restore(dint_snapshot *s, void *cuda_stream);
+void dint_snapshot_destroy(dint_snapshot *s);
+
 int dint_get_stats(dint_engine *e, dint_stats *s);
 void dint_reset_stats(dint_engine *e);
 /* per-kernel CUDA-event timing: 0 = off, 1 = every kernel, otherwise a bit mask over

@@ -203,6 +203,37 @@ def test_txn_drivers_closed_loop_three_shards(kind, n, clients):
             e.close()
 
 
+def test_kv_tombstones_are_reclaimed_under_insert_delete_churn():
+    """The reference's chained kvs frees entries on delete (store/udp/kvs.h:124-133).  Here deletes leave tombstones;
+    a churn of ever-new call-forwarding rows through a 1024-entry table (20x its capacity in total) must neither fill
+    the table nor change a single reply, and the engine must have rehashed the table on the way (kv_rebuilds)."""
+    from dint_b200.wire import Tatp
+    n_subs = 20
+    cfg = dict(subs_populate=n_subs, kv_capacity_log2=[0, 0, 0, 0, 10])
+    ora = O.Oracle(wire.TATP, subs_populate=n_subs)
+    rng = np.random.default_rng(5)
+    with Engine(wire.TATP, populate=True, chunk=4096, **cfg) as eng:
+        next_sid = 1000
+        for call in range(40):
+            m = 512                                                # rows inserted, read and deleted again by this call
+            keys = (np.arange(next_sid, next_sid + m, dtype=np.uint64) | (np.uint64(1) << np.uint64(32)) | (np.uint64(8) << np.uint64(40)))
+            next_sid += m
+            rec = np.zeros(4 * m, dtype=wire.MSG_DTYPE[wire.TATP])
+            rec["table"] = Tatp.kCallForwarding
+            rec["key"] = np.concatenate([keys, keys, keys, keys + np.uint64(1 << 20)])
+            rec["type"] = np.concatenate([np.full(m, Tatp.kInsertBck), np.full(m, Tatp.kRead), np.full(m, Tatp.kDeleteBck),
+                                          np.full(m, Tatp.kRead)]).astype(np.uint8)       # last quarter: keys that never existed
+            rec["val"] = rng.integers(0, 256, size=(4 * m, 40))
+            req = wire.as_bytes(rec)
+            want = ora.process(req)
+            got = eng.submit(req)
+            assert first_diff(got, want, 55) is None, f"call {call}: {first_diff(got, want, 55)}"
+        st = eng.stats()
+        assert st["kv_rebuilds"] >= 1, st
+        assert st["errors"] == 0
+        assert eng.kv_count(4) == ora.kv_count(4)
+
+
 # ---------------------------------------------------------------- device path / edge cases -----------
 def test_device_path_and_empty():
     import torch
@@ -365,7 +396,6 @@ def test_route_owner_partition_unpermute(kind, world):
 
 
 # ---------------------------------------------------------------- the UDP front-end (opt-in until measured) ---
-@pytest.mark.skipif(os.environ.get("DINT_UDP_TEST") != "1", reason="opt-in: set DINT_UDP_TEST=1 (needs loopback sockets)")
 def test_udp_front_end_serves_the_wire_protocol_bit_exact():
     """dint_udp_server behind a real socket: one client socket, windows of 64 datagrams (loopback keeps their
     order), replies must equal ONE sequential reference server's."""

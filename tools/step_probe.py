@@ -5,7 +5,7 @@ back-to-back launches, no flag polling anywhere), with its buffers in plain devi
 
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/step_probe.py
 
-Written at the end of round 1 (no GPU time left to run it): DESIGN.md section 9, "open question"."""
+DESIGN.md section 9, "open question" of round 1."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -60,6 +60,9 @@ if rank == 0:
     resp_plain = torch.empty_like(plain)
     print(f"engine, plain in/out: {timed(lambda: eng.submit_tensor(plain, resp_plain)):.1f} us", flush=True)
     print(f"engine, local symmetric in/out: {timed(lambda: eng.submit_tensor(sym[:nb], sym[region:region + nb])):.1f} us", flush=True)
+    remote = hdl.get_buffer(1, (2 * region,), torch.uint8)
+    print(f"engine, plain in, replies stored into rank 1's memory (NVLink): {timed(lambda: eng.submit_tensor(plain, remote[region:region + nb])):.1f} us", flush=True)
+    print(f"engine, local symmetric in, replies stored into rank 1's memory: {timed(lambda: eng.submit_tensor(sym[:nb], remote[region:region + nb])):.1f} us", flush=True)
     print("flags", flags.tolist())
     eng.close()
 torch.cuda.synchronize()
