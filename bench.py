@@ -591,6 +591,41 @@ def run_closed_loop_extra(args, torch, rank, kind_name, rounds=16, warm=24):
     return res
 
 
+def run_gpu_clients(args, torch, fam, warm_rounds=48):
+    """the closed-loop clients themselves on the GPU (dint_clients_*): no trace, no host in the
+    loop -- committed txn/s and abort rates are produced live for as long as the timed region lasts.  The client
+    kernel shares the GPU with the server, so this is lower than the replay of a recorded trace (which times the
+    server alone, as the reference's server throughput is measured with clients on other machines)."""
+    from dint_b200 import Engine, GpuClients, wire
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    with Engine(wire.FASST, device=dev.index, chunk=args.chunk) as eng:
+        gc = GpuClients(eng, CLIENTS, seed=20230, **fam)
+        stream = torch.cuda.current_stream(dev)
+        gc.run(warm_rounds, stream.cuda_stream)
+        torch.cuda.synchronize(dev)
+        s0 = gc.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        gc.run(64, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        rounds = max(64, int(np.ceil(min(TIMED_SECONDS, 0.5) * 1e3 / (e0.elapsed_time(e1) / 64))))
+        s0 = gc.stats()
+        e0.record(stream)
+        gc.run(rounds, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        s1 = gc.stats()
+        gc.close()
+    d = {k: s1[k] - s0[k] for k in s1}
+    return {"workload": f"{CLIENTS} lock_fasst closed-loop clients RESIDENT ON THE GPU (one kernel per round absorbs the replies and emits the next "
+                        f"requests; same state machine and draws as the host clients: tests/test_gpu_clients.py), {rounds} rounds timed",
+            "txn_per_s": d["committed"] / (ms * 1e-3), "requests_per_s": d["requests"] / (ms * 1e-3), "timed_region_s": ms * 1e-3,
+            "committed_per_request": d["committed"] / max(1, d["requests"]),
+            "abort_stats": {k: d[k] for k in ("committed", "validation_aborts", "lock_rejects")}, "us_per_round": ms * 1e3 / rounds}
+
+
 def run_udp_front_end(seconds=4.0):
     """dint_udp_server (the reference's UDP server shape over the C ABI, dint_b200/csrc/udp_server.cc) with the GPU
     engine behind it, driven over loopback by the same multi-socket replayer that times the unmodified reference
@@ -975,6 +1010,7 @@ def main():
                 "abort_stats": {k: hot["wl_stats"][k] for k in ("committed", "validation_aborts", "lock_rejects")},
                 "conflicted_fraction": hot["stats"]["conflicted"] / max(1, hot["stats"]["requests"]),
                 "replies_bit_exact_vs_closed_loop_recording": bool(hot["parity_replay"]), "cpu_baseline": hot.get("cpu_baseline")}
+            extra["on_gpu_closed_loop"] = run_gpu_clients(args, torch, REF)
             extra["store_get"] = run_store_get(args, torch, rank, max(3, args.steps // 2), 3)
             extra["tatp"] = run_txn(args, torch, rank, "tatp")
             extra["smallbank"] = run_txn(args, torch, rank, "smallbank")

@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "route.cuh"
 #include "kv.cuh"
+#include "clients.cuh"
 
 using namespace dint;
 
@@ -79,12 +80,14 @@ struct dint_engine {
   uint32_t seg_tiles = 0;
   uint64_t seg_resp[kMaxShards]{};
   bool pad_ok = false;
+  const uint32_t* skip = nullptr;
   uint32_t smem_classify = 0;                // K1: max(stages, ordered-replay slices)
   uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
   uint32_t* d_route = nullptr;               // multi-GPU dispatch scratch (per-tile per-shard counts)
   uint32_t route_tiles = 0;
-  uint32_t* d_route2 = nullptr;              // dispatch scratch: [grid][8] per-CTA counts + the finished-CTA counter
-  int grid_route = 0;                        // co-resident CTAs of k_route_dispatch
+  uint32_t* d_route2 = nullptr;              // dispatch scratch: counters, totals, look-back descriptors
+  uint32_t route_desc_tiles = 0, route_seq = 0;
+  int grid_route = 148 * 4;                  // CTAs of k_route_dispatch (tiles are drawn by ticket: any grid works)
   // L2 persistence: the flag sets (+ lock_fasst lock bits) live in one arena that every launch maps
   // with a persisting access-policy window, so the streaming request/reply traffic cannot evict it
   uint8_t* hot_arena = nullptr;
@@ -258,6 +261,7 @@ static void fill_chunk_ctx(dint_engine* e, Ctx& c) {
   c.ord_tile0 = e->ord_tile0;
   c.seg_tiles = e->seg_tiles;
   c.pad_ok = e->pad_ok ? 1u : 0u;
+  c.skip = e->skip;
   for (int i = 0; i < kMaxShards; i++) c.seg_resp[i] = e->seg_resp[i];
 }
 
@@ -422,20 +426,28 @@ struct HostSlices {
 template <int KIND>
 static int route_dispatch_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) {
   using RT = RTile<Wire<KIND>::MSG>;
-  if (!e->d_route2) {
-    e->grid_route = 148 * 4;
-    const size_t words = 16 + (size_t)(e->grid_route / 32 + 2) * kMaxShards + (size_t)e->grid_route * kMaxShards;
-    CU(cudaMalloc(&e->d_route2, words * sizeof(uint32_t)));
-    CU(cudaMemsetAsync(e->d_route2, 0, words * sizeof(uint32_t), s));
+  // scratch: [0] finished-CTA counter, [1] tile tickets, [4..12] totals + valid word, then the look-back descriptors
+  if (!e->d_route2 || a.n_tiles > e->route_desc_tiles) {
+    if (e->d_route2) { CU(cudaStreamSynchronize(s)); CU(cudaFree(e->d_route2)); e->d_route2 = nullptr; }
+    e->route_desc_tiles = a.n_tiles + a.n_tiles / 2 + 64;
+    const size_t bytes = 64 + (size_t)e->route_desc_tiles * 4 * sizeof(unsigned long long);
+    CU(cudaMalloc(&e->d_route2, bytes));
+    CU(cudaMemsetAsync(e->d_route2, 0, bytes, s));
+    e->route_seq = 0;
   }
+  e->route_seq = e->route_seq % 255u + 1u;              // 1..255; when the number wraps every descriptor is cleared, so a word
+  if (e->route_seq == 1)                                 // left by an earlier launch can never carry the current number
+    CU(cudaMemsetAsync(e->d_route2, 0, 64 + (size_t)e->route_desc_tiles * 4 * sizeof(unsigned long long), s));
   RouteArgs b = a;
   b.done = e->d_route2;
-  b.grp_tot = e->d_route2 + 16;
-  b.cta_tot = e->d_route2 + 16 + (size_t)(e->grid_route / 32 + 2) * kMaxShards;
+  b.ticket = e->d_route2 + 1;
+  b.totals = e->d_route2 + 4;
+  b.desc = (unsigned long long*)(e->d_route2 + 16);
+  b.seq = e->route_seq;
+  if (CUDART_VERSION >= 11000 && RT::SMEM > 48 * 1024) CU(cudaFuncSetAttribute(k_route_dispatch<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT::SMEM));
   int grid = (int)b.n_tiles < e->grid_route ? (int)b.n_tiles : e->grid_route;
   if (grid < 1) grid = 1;
-  k_route_count<KIND><<<grid, kThreads, 0, s>>>(e->ctx, b);
-  k_route_scatter<KIND><<<grid, kThreads, RT::SMEM, s>>>(b);
+  k_route_dispatch<KIND><<<grid, kThreads, RT::SMEM, s>>>(e->ctx, b);
   CU(cudaGetLastError());
   return DINT_OK;
 }
@@ -722,7 +734,7 @@ uint32_t dint_route_tile_records(dint_engine* e) { return e ? route_tile_records
 int dint_route_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owner_in_dev, uint64_t n, uint32_t n_shards, uint32_t rank,
                         uint32_t cap, const dint_peer_ptrs* slab_ptrs, const dint_peer_ptrs* sig_ptrs, uint32_t epoch,
                         uint8_t* owner_dev, uint32_t* tilebase_dev, uint32_t* flags_dev, void* cuda_stream) {
-  if (!e || !slab_ptrs || !flags_dev || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 || n > 0xffffffffULL ||
+  if (!e || !slab_ptrs || !flags_dev || n_shards == 0 || n_shards > kMaxShards || rank >= n_shards || cap == 0 || n >= (1ULL << 27) ||
       (n && (!req_dev || !owner_dev || !tilebase_dev)))
     return set_err(DINT_EINVAL, "bad argument");
   if ((uintptr_t)req_dev & 15) return set_err(DINT_EINVAL, "device buffers must be 16-byte aligned");
@@ -742,7 +754,7 @@ int dint_route_dispatch(dint_engine* e, const void* req_dev, const uint8_t* owne
   a.epoch = epoch;
   for (uint32_t i = 0; i < kMaxShards; i++) { a.slab.p[i] = slab_ptrs->p[i]; a.sig.p[i] = sig_ptrs ? sig_ptrs->p[i] : 0; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  e->stats.kernel_launches += 2;
+  e->stats.kernel_launches += 1;
   switch (e->kind) {
     case DINT_LOCK2PL: return route_dispatch_t<K_LOCK2PL>(e, a, s);
     case DINT_FASST: return route_dispatch_t<K_FASST>(e, a, s);
@@ -785,7 +797,7 @@ int dint_p2p_wait(dint_engine* e, const uint32_t* local_sig_dev, uint32_t n_shar
   if (!e || !local_sig_dev || n_shards == 0 || n_shards > kMaxShards) return set_err(DINT_EINVAL, "bad argument");
   CU(cudaSetDevice(e->device));
   e->stats.kernel_launches++;
-  k_p2p_wait<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(local_sig_dev, n_shards, epoch, flags_dev + 1);
+  k_p2p_wait<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(local_sig_dev, n_shards, epoch, flags_dev + 1, nullptr);
   CU(cudaGetLastError());
   return DINT_OK;
 }
@@ -1194,10 +1206,10 @@ static int shard_make(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
     }
   for (uint32_t o = 0; o < n_shards; o++) {
     c->sigreq.p[o] = sig_blocks->p[o];
-    c->sigrsp.p[o] = sig_blocks->p[o] + 64;
+    c->sigrsp.p[o] = sig_blocks->p[o] + 128;          // signal block: request flags [n_sets][8] at +0, reply flags [8] at +128
   }
   c->my_req = (uint32_t*)sig_blocks->p[rank];
-  c->my_rsp = (uint32_t*)(sig_blocks->p[rank] + 64);
+  c->my_rsp = (uint32_t*)(sig_blocks->p[rank] + 128);
   if (!one_stream) {
     CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->ret, cudaStreamNonBlocking));
@@ -1215,8 +1227,8 @@ static int shard_make(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
     CU(cudaMalloc(&c->owner[s], max_n + 16));
     CU(cudaMalloc(&c->tilebase[s], tiles * kMaxShards * sizeof(uint32_t)));
   }
-  CU(cudaMalloc(&c->flags, 2 * sizeof(uint32_t)));
-  CU(cudaMemset(c->flags, 0, 2 * sizeof(uint32_t)));
+  CU(cudaMalloc(&c->flags, 4 * sizeof(uint32_t)));        // [0] records that did not fit, [1] timed-out waits, [2] first epoch left unserved
+  CU(cudaMemset(c->flags, 0, 4 * sizeof(uint32_t)));
   c->trace = getenv("DINT_SHARD_TRACE") != nullptr;
   *out = c;
   return DINT_OK;
@@ -1238,7 +1250,9 @@ static int shard_dispatch(dint_shard_ctx* c, uint32_t slot, uint32_t ep, const v
   if (ep > c->S && !c->one_stream) CU(cudaStreamWaitEvent(st, c->ev_comb[s], 0));   // my combine of batch ep - S: every owner is done with inbox set s
   shard_mark(c, slot, 0, st);
   dint_peer_ptrs in{}, sg{};
-  for (uint32_t o = 0; o < c->W; o++) { in.p[o] = c->inbox[s][o] + (uint64_t)c->me * slab; sg.p[o] = c->sigreq.p[o]; }
+  // one request-flag word per (buffer set, source): the flag of epoch ep -- which may carry the overflow bit -- is not
+  // overwritten before the owner has consumed it (the source reuses set s only after the owners' replies of ep)
+  for (uint32_t o = 0; o < c->W; o++) { in.p[o] = c->inbox[s][o] + (uint64_t)c->me * slab; sg.p[o] = c->sigreq.p[o] + (uint64_t)s * 32; }
   int rc = dint_route_dispatch(e, req_dev, dst_dev, n, c->W, c->me, c->cap, &in, &sg, ep, c->owner[s], c->tilebase[s], c->flags, st);
   if (rc) return rc;
   shard_mark(c, slot, 1, st);
@@ -1251,14 +1265,16 @@ static int shard_engine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, cudaStrea
   CU(cudaSetDevice(e->device));
   const uint32_t s = ep % c->S;
   const size_t slab = (size_t)c->cap * e->msg;
-  k_p2p_wait<<<1, 32, 0, st>>>(c->my_req, c->W, ep, c->flags + 1);                    // every source's slab has arrived
+  k_p2p_wait<<<1, 32, 0, st>>>(c->my_req + s * 8, c->W, ep, c->flags + 1, c->flags + 2);     // every source's slab has arrived (or one did not fit)
   shard_mark(c, slot, 2, st);
   e->seg_tiles = c->cap / kTile;
   e->pad_ok = true;
+  e->skip = c->flags + 2;
   for (uint32_t r = 0; r < c->W; r++) e->seg_resp[r] = c->retbox[s][r] + (uint64_t)c->me * slab;   // my slab inside source r's return buffer
   int rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)c->W * c->cap, nullptr, st);
   e->seg_tiles = 0;
   e->pad_ok = false;
+  e->skip = nullptr;
   if (rc) return rc;
   k_p2p_signal<<<1, 32, 0, st>>>(c->sigrsp, c->W, c->me, ep);
   shard_mark(c, slot, 3, st);
@@ -1272,7 +1288,7 @@ static int shard_combine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, void* ou
   const uint32_t s = ep % c->S;
   const size_t slab = (size_t)c->cap * e->msg;
   if (!c->one_stream) CU(cudaStreamWaitEvent(st, c->ev_disp[s], 0));
-  k_p2p_wait<<<1, 32, 0, st>>>(c->my_rsp, c->W, ep, c->flags + 1);
+  k_p2p_wait<<<1, 32, 0, st>>>(c->my_rsp, c->W, ep, c->flags + 1, nullptr);
   shard_mark(c, slot, 4, st);
   dint_peer_ptrs rb{};
   for (uint32_t o = 0; o < c->W; o++) rb.p[o] = c->retbox[s][c->me] + (uint64_t)o * slab;
@@ -1301,12 +1317,28 @@ static void shard_trace_collect(dint_shard_ctx* c, uint32_t k) {
 // rank's combine of j (of j-1 when the ranks share one stream) -- each phase only waits for phases enqueued
 // before it, on this or another GPU, so one host thread can drive all ranks without blocking.
 struct ShardBatch { const void* req; const uint8_t* dst; void* out; uint64_t n; };
-static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const std::vector<std::vector<ShardBatch>>& b, cudaStream_t const* mains) {
+struct HostBatch { const uint8_t* req; const uint8_t* dst; uint8_t* out; uint64_t n; };
+static int shard_staging(dint_shard_ctx* c) {
+  if (c->st_req[0]) return DINT_OK;
+  CU(cudaSetDevice(c->e->device));
+  for (uint32_t s = 0; s < c->S; s++) {
+    CU(cudaMalloc(&c->st_req[s], c->max_n * c->e->msg + 16));
+    CU(cudaMalloc(&c->st_dst[s], c->max_n + 16));
+    CU(cudaMalloc(&c->st_out[s], c->max_n * c->e->msg + 16));
+  }
+  return DINT_OK;
+}
+// `host` given: the batches come from / go to HOST memory through S staging sets -- H2D of batch j+1 (copy stream) and
+// D2H of batch j-1 (another copy stream) run next to the exchange of batch j, the same slice ring as dint_submit.
+static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, std::vector<std::vector<ShardBatch>>& b, cudaStream_t const* mains,
+                     const std::vector<std::vector<HostBatch>>* host = nullptr) {
   if (k == 0) return DINT_OK;
   const bool one = ranks[0]->one_stream;
   const uint32_t lag = one ? 1u : 0u;
+  int rc;
   for (uint32_t r = 0; r < R; r++) {
     dint_shard_ctx* c = ranks[r];
+    if (host && (rc = shard_staging(c))) return rc;
     if (one) continue;
     CU(cudaSetDevice(c->e->device));
     CU(cudaEventRecord(c->ev_fork, mains[r]));
@@ -1315,22 +1347,52 @@ static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const
   }
   auto side = [&](uint32_t r) { return one ? mains[r] : ranks[r]->side; };
   auto retS = [&](uint32_t r) { return one ? mains[r] : ranks[r]->ret; };
-  int rc;
+  auto dispatch = [&](uint32_t r, uint32_t j) -> int {
+    dint_shard_ctx* c = ranks[r];
+    if (host) {                                          // stage batch j: H2D on the copy stream, the dispatch waits for it
+      const HostBatch& h = (*host)[r][j];
+      dint_engine* e = c->e;
+      const uint32_t s = j % c->S;
+      if (h.n > c->max_n) return set_err(DINT_EINVAL, "batch size");
+      CU(cudaSetDevice(e->device));
+      CU(cudaStreamWaitEvent(c->s_in, c->ev_d2h[s], 0)); // batch j - S has left this staging set (its dispatch is long done too)
+      if (h.n) CU(cudaMemcpyAsync(c->st_req[s], h.req, h.n * e->msg, cudaMemcpyHostToDevice, c->s_in));
+      if (h.dst && h.n) CU(cudaMemcpyAsync(c->st_dst[s], h.dst, h.n, cudaMemcpyHostToDevice, c->s_in));
+      CU(cudaEventRecord(c->ev_h2d[s], c->s_in));
+      CU(cudaStreamWaitEvent(side(r), c->ev_h2d[s], 0));
+      e->stats.h2d_bytes += h.n * e->msg + (h.dst ? h.n : 0);
+      b[r][j] = ShardBatch{c->st_req[s], h.dst ? c->st_dst[s] : nullptr, c->st_out[s], h.n};
+    }
+    return shard_dispatch(c, j, c->epoch + 1 + j, b[r][j].req, b[r][j].dst, b[r][j].n, side(r));
+  };
+  auto combine = [&](uint32_t r, uint32_t j) -> int {
+    dint_shard_ctx* c = ranks[r];
+    int rc2 = shard_combine(c, j, c->epoch + 1 + j, b[r][j].out, b[r][j].n, retS(r));
+    if (rc2 || !host) return rc2;
+    const HostBatch& h = (*host)[r][j];
+    const uint32_t s = j % c->S, es = (c->epoch + 1 + j) % c->S;
+    if (one) CU(cudaEventRecord(c->ev_comb[es], retS(r)));
+    CU(cudaStreamWaitEvent(c->s_out, c->ev_comb[es], 0));
+    if (h.n) CU(cudaMemcpyAsync(h.out, c->st_out[s], h.n * c->e->msg, cudaMemcpyDeviceToHost, c->s_out));
+    CU(cudaEventRecord(c->ev_d2h[s], c->s_out));
+    c->e->stats.d2h_bytes += h.n * c->e->msg;
+    return DINT_OK;
+  };
   for (uint32_t r = 0; r < R; r++)
-    if ((rc = shard_dispatch(ranks[r], 0, ranks[r]->epoch + 1, b[r][0].req, b[r][0].dst, b[r][0].n, side(r)))) return rc;
+    if ((rc = dispatch(r, 0))) return rc;
   for (uint32_t j = 0; j < k; j++) {
     if (j + 1 < k)
       for (uint32_t r = 0; r < R; r++)
-        if ((rc = shard_dispatch(ranks[r], j + 1, ranks[r]->epoch + 2 + j, b[r][j + 1].req, b[r][j + 1].dst, b[r][j + 1].n, side(r)))) return rc;
+        if ((rc = dispatch(r, j + 1))) return rc;
     for (uint32_t r = 0; r < R; r++)
       if ((rc = shard_engine(ranks[r], j, ranks[r]->epoch + 1 + j, mains[r]))) return rc;
     if (j >= lag)
       for (uint32_t r = 0; r < R; r++)
-        if ((rc = shard_combine(ranks[r], j - lag, ranks[r]->epoch + 1 + j - lag, b[r][j - lag].out, b[r][j - lag].n, retS(r)))) return rc;
+        if ((rc = combine(r, j - lag))) return rc;
   }
   for (uint32_t j = k - (lag < k ? lag : k); j < k; j++)
     for (uint32_t r = 0; r < R; r++)
-      if ((rc = shard_combine(ranks[r], j, ranks[r]->epoch + 1 + j, b[r][j].out, b[r][j].n, retS(r)))) return rc;
+      if ((rc = combine(r, j))) return rc;
   for (uint32_t r = 0; r < R; r++) {
     dint_shard_ctx* c = ranks[r];
     const uint32_t last = c->epoch + k;
@@ -1341,8 +1403,21 @@ static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const
     CU(cudaStreamWaitEvent(mains[r], c->ev_disp[last % c->S], 0));
   }
   CU(cudaGetLastError());
+  if (host)
+    for (uint32_t r = 0; r < R; r++) {                   // returns when every reply is in host memory
+      CU(cudaSetDevice(ranks[r]->e->device));
+      CU(cudaStreamSynchronize(ranks[r]->s_out));
+      CU(cudaStreamSynchronize(mains[r]));
+    }
   for (uint32_t r = 0; r < R; r++) shard_trace_collect(ranks[r], k);
   return DINT_OK;
+}
+
+static int shard_run_host(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const std::vector<std::vector<HostBatch>>& hb) {
+  std::vector<cudaStream_t> mains(R);
+  for (uint32_t r = 0; r < R; r++) mains[r] = ranks[0]->one_stream ? ranks[0]->e->stream : ranks[r]->e->stream;   // ranks sharing a device: one stream
+  std::vector<std::vector<ShardBatch>> b(R, std::vector<ShardBatch>(k));
+  return shard_run(ranks, R, k, b, mains.data(), &hb);
 }
 
 extern "C" {
@@ -1393,6 +1468,32 @@ int dint_shard_flags(dint_shard_ctx* c, uint32_t out[2]) {
   return DINT_OK;
 }
 
+// After a slab overflow: *first_unserved = index, inside the LAST submit call (of k batches), of the first batch that
+// no shard served (it and every later batch left the state untouched; their replies are garbage), or 0xffffffff when
+// nothing was skipped.  Clears the condition and the engine's inter-chunk bookkeeping; call it on every rank before the
+// next submit, then serve the unserved batches again in pieces of at most `cap` records per rank (which cannot overflow).
+int dint_shard_recover(dint_shard_ctx* c, uint32_t k_last, uint32_t* first_unserved) {
+  if (!c || !first_unserved) return DINT_EINVAL;
+  dint_engine* e = c->e;
+  CU(cudaSetDevice(e->device));
+  CU(cudaDeviceSynchronize());
+  uint32_t bad = 0;
+  CU(cudaMemcpy(&bad, c->flags + 2, sizeof bad, cudaMemcpyDeviceToHost));
+  *first_unserved = 0xffffffffu;
+  if (!bad) return DINT_OK;
+  const uint32_t first_epoch = c->epoch - k_last + 1;
+  *first_unserved = bad >= first_epoch ? bad - first_epoch : 0;
+  CU(cudaMemset(c->flags, 0, 4 * sizeof(uint32_t)));
+  // the skipped launches changed nothing on the device, but the host-side chunk bookkeeping advanced: start clean
+  e->ord_pending = false;
+  e->prev_n = 0;
+  CU(cudaMemset(e->d_nc, 0, 8 * sizeof(uint32_t)));
+  CU(cudaMemset(e->ctx.tickets, 0, 4 * sizeof(uint32_t)));
+  CU(cudaMemset(e->d_flags[0], 0, (size_t)((char*)e->d_flags[1] - (char*)e->d_flags[0]) * 2));
+  CU(cudaDeviceSynchronize());
+  return DINT_OK;
+}
+
 int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req_dev, const uint8_t* const* dst_dev, uint64_t n,
                            void* const* out_dev, void* cuda_stream) {
   if (!c || !req_dev || !out_dev || n == 0 || n > c->max_n) return set_err(DINT_EINVAL, "bad argument");
@@ -1404,72 +1505,6 @@ int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req
 }
 
 }  // extern "C"
-
-// ---- host buffers through the sharded step: H2D | dispatch | engine | combine | D2H, S sets deep ---------------------
-// (what a transport front-end calls at N > 1: the same slice ring as dint_submit, with the exchange in the middle)
-static int shard_staging(dint_shard_ctx* c) {
-  if (c->st_req[0]) return DINT_OK;
-  CU(cudaSetDevice(c->e->device));
-  for (uint32_t s = 0; s < c->S; s++) {
-    CU(cudaMalloc(&c->st_req[s], c->max_n * c->e->msg + 16));
-    CU(cudaMalloc(&c->st_dst[s], c->max_n + 16));
-    CU(cudaMalloc(&c->st_out[s], c->max_n * c->e->msg + 16));
-  }
-  return DINT_OK;
-}
-struct HostBatch { const uint8_t* req; const uint8_t* dst; uint8_t* out; uint64_t n; };
-// k batches per rank from / to HOST memory.  Batches are processed in groups of S (one per buffer set): the copies of
-// a group overlap the exchange of the same group, the groups follow each other on the streams without a host sync.
-static int shard_run_host(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, const std::vector<std::vector<HostBatch>>& hb) {
-  int rc;
-  for (uint32_t r = 0; r < R; r++) if ((rc = shard_staging(ranks[r]))) return rc;
-  const uint32_t S = ranks[0]->S;
-  std::vector<cudaStream_t> mains(R);
-  for (uint32_t r = 0; r < R; r++) mains[r] = ranks[r]->e->stream;
-  if (ranks[0]->one_stream) for (uint32_t r = 0; r < R; r++) mains[r] = ranks[0]->e->stream;   // ranks sharing a device: one stream
-  for (uint32_t j0 = 0; j0 < k; j0 += S) {
-    const uint32_t g = (k - j0 < S) ? (k - j0) : S;
-    std::vector<std::vector<ShardBatch>> b(R, std::vector<ShardBatch>(g));
-    for (uint32_t r = 0; r < R; r++) {
-      dint_shard_ctx* c = ranks[r];
-      dint_engine* e = c->e;
-      CU(cudaSetDevice(e->device));
-      for (uint32_t j = 0; j < g; j++) {
-        const HostBatch& h = hb[r][j0 + j];
-        if (h.n > c->max_n) return set_err(DINT_EINVAL, "batch size");
-        const uint32_t s = j;                                 // staging set (any fixed mapping works: groups are serialised per set)
-        CU(cudaStreamWaitEvent(c->s_in, c->ev_d2h[s], 0));    // the previous user of this staging set has left
-        if (h.n) CU(cudaMemcpyAsync(c->st_req[s], h.req, h.n * e->msg, cudaMemcpyHostToDevice, c->s_in));
-        if (h.dst && h.n) CU(cudaMemcpyAsync(c->st_dst[s], h.dst, h.n, cudaMemcpyHostToDevice, c->s_in));
-        CU(cudaEventRecord(c->ev_h2d[s], c->s_in));
-        e->stats.h2d_bytes += h.n * e->msg + (h.dst ? h.n : 0);
-        b[r][j] = ShardBatch{c->st_req[s], h.dst ? c->st_dst[s] : nullptr, c->st_out[s], h.n};
-      }
-      for (uint32_t j = 0; j < g; j++) CU(cudaStreamWaitEvent(mains[r], c->ev_h2d[j], 0));   // (main forks side / ret)
-    }
-    if ((rc = shard_run(ranks, R, g, b, mains.data()))) return rc;
-    for (uint32_t r = 0; r < R; r++) {
-      dint_shard_ctx* c = ranks[r];
-      dint_engine* e = c->e;
-      CU(cudaSetDevice(e->device));
-      for (uint32_t j = 0; j < g; j++) {
-        const HostBatch& h = hb[r][j0 + j];
-        const uint32_t ep = c->epoch - g + 1 + j;
-        if (c->one_stream) { CU(cudaEventRecord(c->ev_comb[ep % c->S], mains[r])); }
-        CU(cudaStreamWaitEvent(c->s_out, c->ev_comb[ep % c->S], 0));
-        if (h.n) CU(cudaMemcpyAsync(h.out, c->st_out[j], h.n * e->msg, cudaMemcpyDeviceToHost, c->s_out));
-        CU(cudaEventRecord(c->ev_d2h[j], c->s_out));
-        e->stats.d2h_bytes += h.n * e->msg;
-      }
-    }
-  }
-  for (uint32_t r = 0; r < R; r++) {
-    CU(cudaSetDevice(ranks[r]->e->device));
-    CU(cudaStreamSynchronize(ranks[r]->s_out));
-    CU(cudaStreamSynchronize(mains[r]));
-  }
-  return DINT_OK;
-}
 
 extern "C" {
 
@@ -1491,6 +1526,7 @@ struct dint_cluster {
   std::vector<dint_engine*> eng;
   std::vector<dint_shard_ctx*> sh;
   std::vector<void*> bufs;                  // per rank: one allocation {inbox sets | return-buffer sets | signal block}
+  uint64_t overflow_retries = 0;            // submit calls that met a slab overflow and served the rest in small rounds
 };
 
 void dint_cluster_destroy(dint_cluster* cl) {
@@ -1590,21 +1626,16 @@ int dint_cluster_populate(dint_cluster* cl) {
 dint_engine* dint_cluster_engine(dint_cluster* cl, int shard) { return (cl && shard >= 0 && shard < (int)cl->G) ? cl->eng[shard] : nullptr; }
 uint32_t dint_cluster_size(dint_cluster* cl) { return cl ? cl->G : 0; }
 
-int dint_cluster_submit(dint_cluster* cl, const void* req, uint64_t n, const uint8_t* dst_shard, void* resp) {
-  if (!cl || (n && (!req || !resp))) return set_err(DINT_EINVAL, "null argument");
-  if (cl->by_dst && cl->G > 1 && !dst_shard) return set_err(DINT_EINVAL, "tatp / smallbank: the client names the shard of every record (dst_shard)");
-  if (n == 0) return DINT_OK;
+// rounds over [from, to): a round hands rank r the r-th of G contiguous pieces of at most `lim` records (rank-major
+// order = index order); for a client-chosen placement the pieces are cut so that no slab can overflow.
+// Returns the first record index that was NOT served (to = everything served), or a negative error.
+static int64_t cluster_run(dint_cluster* cl, const uint8_t* rq, const uint8_t* dst_shard, uint8_t* rs, uint64_t from, uint64_t to, uint64_t lim) {
   const uint32_t G = cl->G, msg = kMsgSize[cl->kind];
-  const uint8_t* rq = (const uint8_t*)req;
-  uint8_t* rs = (uint8_t*)resp;
-  unsigned long long err_before = 0;
-  for (auto* e : cl->eng) err_before += e->stats.errors;
-  // Rounds: a round hands rank r the r-th of G contiguous pieces (rank-major order = index order).
-  // For a client-chosen placement the pieces are cut so that no (source, owner) slab can overflow.
   std::vector<std::vector<HostBatch>> hb(G);
-  uint64_t off = 0;
-  while (off < n) {
-    uint64_t m = n - off < (uint64_t)G * cl->max_n ? n - off : (uint64_t)G * cl->max_n;
+  std::vector<uint64_t> round_off;
+  uint64_t off = from;
+  while (off < to) {
+    uint64_t m = to - off < (uint64_t)G * lim ? to - off : (uint64_t)G * lim;
     for (;;) {
       const uint64_t q = (m + G - 1) / G;
       bool fits = true;
@@ -1620,6 +1651,7 @@ int dint_cluster_submit(dint_cluster* cl, const void* req, uint64_t n, const uin
       m = (m + 1) / 2;
     }
     const uint64_t q = (m + G - 1) / G;
+    round_off.push_back(off);
     for (uint32_t r = 0; r < G; r++) {
       const uint64_t lo = off + (uint64_t)r * q;
       const uint64_t hi = lo + q < off + m ? lo + q : off + m;
@@ -1628,19 +1660,150 @@ int dint_cluster_submit(dint_cluster* cl, const void* req, uint64_t n, const uin
     }
     off += m;
   }
-  const uint32_t k = (uint32_t)hb[0].size();
+  const uint32_t k = (uint32_t)round_off.size();
   int rc = shard_run_host(cl->sh.data(), G, k, hb);
   if (rc) return rc;
-  unsigned long long err_after = 0;
+  uint32_t first_unserved = 0xffffffffu;
   for (uint32_t r = 0; r < G; r++) {
-    uint32_t fl[2] = {0, 0};
+    uint32_t fl[2] = {0, 0}, fu = 0xffffffffu;
     if ((rc = dint_shard_flags(cl->sh[r], fl))) return rc;
-    if (fl[0] || fl[1]) return set_err(DINT_EIO, fl[0] ? "slab overflow in the exchange (adversarially skewed keys): server state has advanced" : "exchange timed out");
+    if (fl[1]) return set_err(DINT_EIO, "exchange timed out");
+    if ((rc = dint_shard_recover(cl->sh[r], k, &fu))) return rc;
+    if (fu < first_unserved) first_unserved = fu;
+  }
+  return first_unserved == 0xffffffffu ? (int64_t)to : (int64_t)round_off[first_unserved];
+}
+
+int dint_cluster_submit(dint_cluster* cl, const void* req, uint64_t n, const uint8_t* dst_shard, void* resp) {
+  if (!cl || (n && (!req || !resp))) return set_err(DINT_EINVAL, "null argument");
+  if (cl->by_dst && cl->G > 1 && !dst_shard) return set_err(DINT_EINVAL, "tatp / smallbank: the client names the shard of every record (dst_shard)");
+  if (n == 0) return DINT_OK;
+  unsigned long long err_before = 0;
+  for (auto* e : cl->eng) err_before += e->stats.errors;
+  // Normal rounds; if a slab overflowed (keys skewed beyond the slack of the slabs) every shard stopped serving AT that
+  // round, nothing behind it touched the state: serve the rest in rounds of at most `cap` records per rank, which fit
+  // any slab whatever the keys are.
+  int64_t done = cluster_run(cl, (const uint8_t*)req, dst_shard, (uint8_t*)resp, 0, n, cl->max_n);
+  if (done < 0) return (int)done;
+  if ((uint64_t)done < n) {
+    cl->overflow_retries++;
+    done = cluster_run(cl, (const uint8_t*)req, dst_shard, (uint8_t*)resp, (uint64_t)done, n, cl->cap < cl->max_n ? cl->cap : cl->max_n);
+    if (done < 0) return (int)done;
+    if ((uint64_t)done < n) return set_err(DINT_EIO, "internal: a round of at most cap records per rank overflowed");
+  }
+  unsigned long long err_after = 0;
+  for (uint32_t r = 0; r < cl->G; r++) {
     dint_engine* e = cl->eng[r];
-    if ((rc = pull_counters(e))) return rc;
+    int rc = pull_counters(e);
+    if (rc) return rc;
     err_after += e->stats.errors;
   }
   return err_after != err_before ? DINT_EPROTO : DINT_OK;
+}
+uint64_t dint_cluster_overflow_retries(dint_cluster* cl) { return cl ? cl->overflow_retries : 0; }
+
+}  // extern "C"
+
+extern "C" {
+// ---- lock_fasst closed-loop clients on the GPU (clients.cuh) ------------------------------------------------
+struct dint_clients {
+  dint_engine* e = nullptr;
+  ClientCtx cc{};
+  uint8_t *req = nullptr, *resp = nullptr;
+  double* cdf = nullptr;
+  uint64_t seed = 0;
+  bool started = false;
+};
+
+void dint_clients_destroy(dint_clients* c) {
+  if (!c) return;
+  cudaSetDevice(c->e->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->req); cudaFree(c->resp); cudaFree(c->cdf);
+  cudaFree(c->cc.hdr); cudaFree(c->cc.rng); cudaFree(c->cc.rk); cudaFree(c->cc.rv); cudaFree(c->cc.stats);
+  delete c;
+}
+
+int dint_clients_create(dint_engine* e, uint32_t n_clients, uint64_t seed, uint32_t n_keys, double zipf_theta, uint32_t read_pct,
+                        dint_clients** out) {
+  if (!e || !out || e->kind != DINT_FASST || n_clients == 0 || n_keys == 0) return set_err(DINT_EINVAL, "lock_fasst engine, n_clients > 0, n_keys > 0");
+  CU(cudaSetDevice(e->device));
+  dint_clients* c = new dint_clients();
+  c->e = e;
+  c->seed = seed;
+  ClientCtx& cc = c->cc;
+  cc.n_clients = n_clients; cc.n_keys = n_keys; cc.read_pct = read_pct;
+  const size_t n = n_clients;
+  if (cudaMalloc(&c->req, n * 9 + 16) != cudaSuccess || cudaMalloc(&c->resp, n * 9 + 16) != cudaSuccess ||
+      cudaMalloc(&cc.hdr, n * 8) != cudaSuccess || cudaMalloc(&cc.rng, n * 8) != cudaSuccess || cudaMalloc(&cc.rk, n * 40) != cudaSuccess ||
+      cudaMalloc(&cc.rv, n * 40) != cudaSuccess || cudaMalloc(&cc.stats, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaError_t ce = cudaGetLastError();
+    dint_clients_destroy(c);
+    return set_err(DINT_ENOMEM, "client state", ce);
+  }
+  CU(cudaMemset(cc.stats, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaMemset(cc.rv, 0, n * 40));
+  if (zipf_theta > 0) {                                  // workloads.cc Zipf::init
+    std::vector<double> cdf(n_keys);
+    double acc = 0;
+    for (uint32_t k = 0; k < n_keys; k++) { acc += 1.0 / std::pow((double)(k + 1), zipf_theta); cdf[k] = acc; }
+    for (auto& v : cdf) v /= acc;
+    CU(cudaMalloc(&c->cdf, (size_t)n_keys * sizeof(double)));
+    CU(cudaMemcpy(c->cdf, cdf.data(), (size_t)n_keys * sizeof(double), cudaMemcpyHostToDevice));
+    cc.cdf = c->cdf;
+    cc.zipf_n = n_keys;
+  }
+  *out = c;
+  return DINT_OK;
+}
+
+// `rounds` closed-loop rounds, asynchronous on cuda_stream: every round = the engine on the clients' request buffer
+// (dint_submit_device) + ONE kernel that absorbs the replies and emits the next round's requests
+int dint_clients_run(dint_clients* c, uint32_t rounds, void* cuda_stream) {
+  if (!c) return set_err(DINT_EINVAL, "null argument");
+  dint_engine* e = c->e;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const uint32_t blocks = (c->cc.n_clients + 255) / 256;
+  if (!c->started) {
+    k_clients_init<<<blocks, 256, 0, s>>>(c->cc, c->seed, c->req);
+    c->started = true;
+    e->stats.kernel_launches++;
+  }
+  for (uint32_t r = 0; r < rounds; r++) {
+    int rc = run_device(e, c->req, c->cc.n_clients, c->resp, s);
+    if (rc) return rc;
+    k_clients_step<<<blocks, 256, 0, s>>>(c->cc, c->resp, c->req);
+    e->stats.kernel_launches++;
+  }
+  CU(cudaGetLastError());
+  return DINT_OK;
+}
+
+// out: requests served, committed transactions, validation aborts, lock rejects, rounds (synchronises)
+int dint_clients_stats(dint_clients* c, uint64_t out[5]) {
+  if (!c || !out) return set_err(DINT_EINVAL, "null argument");
+  CU(cudaSetDevice(c->e->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long h[5];
+  CU(cudaMemcpy(h, c->cc.stats, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 5; i++) out[i] = h[i];
+  return DINT_OK;
+}
+
+// test hook: the requests the clients will send next and the replies they absorbed last (host buffers of n_clients * 9 bytes)
+int dint_clients_peek(dint_clients* c, void* next_req_host, void* last_resp_host) {
+  if (!c) return set_err(DINT_EINVAL, "null argument");
+  CU(cudaSetDevice(c->e->device));
+  CU(cudaDeviceSynchronize());
+  if (!c->started) {
+    k_clients_init<<<(c->cc.n_clients + 255) / 256, 256>>>(c->cc, c->seed, c->req);
+    c->started = true;
+    CU(cudaDeviceSynchronize());
+  }
+  if (next_req_host) CU(cudaMemcpy(next_req_host, c->req, (size_t)c->cc.n_clients * 9, cudaMemcpyDeviceToHost));
+  if (last_resp_host) CU(cudaMemcpy(last_resp_host, c->resp, (size_t)c->cc.n_clients * 9, cudaMemcpyDeviceToHost));
+  return DINT_OK;
 }
 
 }  // extern "C"

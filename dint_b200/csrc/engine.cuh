@@ -145,6 +145,7 @@ struct Ctx {
   uint32_t tile0, ord_tile0;      // index, inside the batch, of the first tile of this chunk / of the replayed chunk
   uint32_t pad_ok;                // 1 inside the multi-GPU step: type 0xFE records are slab padding (else: invalid)
   uint64_t seg_resp[8];           // reply slab of source s (device address, possibly peer memory)
+  const uint32_t* skip;           // multi-GPU step: non-zero = a slab overflowed, serve nothing more (see k_p2p_wait)
 };
 
 // address of tile T's replies (T counted from the start of the batch) when the replies are segmented by source

@@ -232,15 +232,21 @@ __global__ void k_p2p_signal(PeerPtrs sig, uint32_t world, uint32_t me, uint32_t
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
   }
 }
-// before consuming: wait until every peer has signalled epoch `e` (bounded spin: ~4 s, then *timeout = 1)
-__global__ void k_p2p_wait(const uint32_t* my_sig, uint32_t world, uint32_t epoch, uint32_t* timeout) {
+// before consuming: wait until every peer has signalled epoch `e` (bounded spin: ~4 s, then *timeout = 1).
+// Bit 31 of a request flag = "this source could not fit one of its slabs": the first epoch for which any source says so
+// is recorded in *bad (0 = none), and from then on every engine launch of the step returns at once (Ctx::skip): the
+// batch and everything behind it is left unserved on EVERY shard -- all owners see all sources' flags -- so the server
+// state stays consistent and the host can serve those records again in smaller rounds.
+constexpr uint32_t kSigOverflow = 0x80000000u;
+__global__ void k_p2p_wait(const uint32_t* my_sig, uint32_t world, uint32_t epoch, uint32_t* timeout, uint32_t* bad) {
   if (threadIdx.x < world) {
     const long long t0 = clock64();
     uint32_t v;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_sig + threadIdx.x) : "memory");
       if (clock64() - t0 > 8000000000LL) { atomicExch(timeout, 1u); break; }
-    } while ((int32_t)(v - epoch) < 0);
+    } while ((int32_t)((v & ~kSigOverflow) - epoch) < 0);
+    if (bad && (v & kSigOverflow) && (v & ~kSigOverflow) == epoch) atomicCAS(bad, 0u, epoch);
   }
   __syncthreads();
   __threadfence_system();
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   __shared__ uint64_t full[kStages];
   __shared__ uint32_t scratch[kTile / 32];
   __shared__ uint32_t s_ring[kStages];
+  if (c.skip && __ldcg(c.skip)) return;                  // the multi-GPU step is draining after a slab overflow (k_p2p_wait)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     // [2] (a writer exists) is OR-ed by any CTA of this launch, so it is cleared one launch early: each K1
@@ -368,6 +375,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
 
 // K1b: absolute append ordinal of every tile's first log append (single CTA).
 __global__ void __launch_bounds__(kThreads) k_log_scan(const Ctx c) {
+  if (c.skip && __ldcg(c.skip)) return;
   __shared__ unsigned long long carry;
   __shared__ uint32_t wsum[kThreads / 32];
   if (threadIdx.x == 0) carry = c.log_total[0];
@@ -416,6 +424,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
   // the TMA stage) instead of re-hashing; KV servers need the hash itself to find the table entry
   constexpr bool kGrpFromK1 = (KIND == K_LOCK2PL || KIND == K_FASST);
   __shared__ uint32_t s_ring[kStages];
+  if (c.skip && __ldcg(c.skip)) return;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     if (blockIdx.x == 0) c.tickets[0] = 0;               // K1 is not running: its ticket counter is reset here
@@ -716,6 +725,7 @@ struct GridBar {
 
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) k_ordered(const Ctx c) {
+  if (c.skip && __ldcg(c.skip)) return;
   const uint32_t nc = c.nc_ord[0];
   const uint32_t overflow = c.nc_ord[1];
   if (nc == 0 || overflow == 0) return;               // the bucket path (inside the next K1) handles this chunk

@@ -1,16 +1,16 @@
 // Multi-GPU dispatch / combine: stable partition of a batch of wire records by owner shard, written straight
-// into fixed-capacity slabs (local memory for an NCCL exchange, or the owners' receive buffers over NVLink),
-// and its inverse.  Two plain launches over the same grid (no cooperative launch: inside the multi-GPU step
-// other streams hold flag-polling kernels, see GridBar in kernels.cuh); the batch comes from HBM once:
+// into fixed-capacity slabs (local memory, or the owners' receive buffers over NVLink), and its inverse.
 //
-//   k_route_count    every CTA owns a contiguous range of tiles: owner shard of every record (hash of the key,
-//            the slot ONE server would compute, modulo the shard count -- or the client-chosen shard), one byte
-//            per record, and the CTA's per-shard record counts
-//   k_route_scatter  exclusive prefix over the CTAs' counts = first slot of this CTA's records in every slab; the
-//            tiles are read again (L2 hits), partitioned in shared memory into one run per shard, and every run
-//            leaves with 16-byte stores: runs sit in shared memory at the alignment of their destination.
-//            Slots past a slab's total become padding records; the last CTA to finish raises the epoch flags
-//            of the peers (release, system scope) when the slabs live in peer memory.
+//   k_route_dispatch  ONE launch, ONE pass over the batch.  Tiles (1024 records; 256 for the 53/55-byte kinds) are
+//            handed out in index order by a ticket counter.  Per tile: owner shard of every record (hash of the key,
+//            the slot ONE server would compute, modulo the shard count -- or the client-chosen shard), the tile's
+//            per-shard counts, and the first slot of the tile's run in every slab from a DECOUPLED LOOK-BACK over
+//            the preceding tiles' published counts (single-pass prefix sum: a tile publishes its aggregate at once,
+//            then walks back until it meets a tile whose inclusive prefix is known).  The tile is partitioned in
+//            shared memory into one run per shard, each run placed at the alignment of its destination so that it
+//            leaves with 16-byte stores.  Slots past a slab's total become padding records; the last CTA to finish
+//            raises the epoch flags of the peers (release, system scope) when the slabs live in peer memory.
+//            (Round 1 used two launches -- count, then scatter: 28 us per 2^20 records against about half that here.)
 //
 // The combine reads, per tile, one contiguous run per shard from the reply slabs and reassembles the tile in
 // request order; its only per-record state is the owner byte and, per tile, the first slot of each run.
@@ -34,9 +34,11 @@ struct RouteArgs {
   const uint8_t* owner_in;   // dispatch: client-chosen shard per record, or nullptr = computed from the keys
   uint8_t* owner;            // [n] owner byte per record (dispatch writes, combine reads); 0xff = undeliverable
   uint32_t* tilebase;        // [n_tiles][kMaxShards] first slot of each tile's run in each slab
-  uint32_t* cta_tot;         // dispatch scratch [grid][kMaxShards]: per-CTA per-shard counts
-  uint32_t* grp_tot;         // dispatch scratch [grid / 32 + 1][kMaxShards]: the same per 32 CTAs; zero between launches
-  uint32_t* done;            // dispatch scratch, zero between launches
+  unsigned long long* desc;  // dispatch scratch [n_tiles][4]: look-back descriptors, self-validating words tagged with `seq`
+  uint32_t* totals;          // dispatch scratch [kMaxShards + 1]: per-shard totals of this launch, [8] = seq once they are valid
+  uint32_t* ticket;          // dispatch scratch: tile ticket counter, zero between launches
+  uint32_t* done;            // dispatch scratch: finished-CTA counter, zero between launches
+  uint32_t seq;              // launch sequence number (1..255): stale descriptors of earlier launches read as "not yet"
   uint32_t* flags;           // [0] += records that did not fit their slab
   uint8_t* out;              // combine: [n * MSG] replies in request order, 16-byte aligned
   uint32_t n, n_tiles, world, me, cap, epoch;
@@ -131,53 +133,24 @@ DINT_D Cnt8 load_owners(const RouteArgs& a, uint32_t t, uint32_t (&own)[PER]) {
   return mine;
 }
 
-// dispatch, launch 1 of 2: owner byte per record, per-CTA per-shard counts (CTA b owns a contiguous range of tiles)
-template <int KIND>
-__global__ void __launch_bounds__(kThreads) k_route_count(const Ctx c, const RouteArgs a) {
-  using W = Wire<KIND>;
-  using RT = RTile<W::MSG>;
-  constexpr int MSG = W::MSG, PER = RT::PER;
-  __shared__ uint32_t s_cnt[kMaxShards];
-  const uint32_t G = gridDim.x, b = blockIdx.x;
-  const uint32_t t0 = (uint32_t)((uint64_t)a.n_tiles * b / G), t1 = (uint32_t)((uint64_t)a.n_tiles * (b + 1) / G);
-  if (threadIdx.x < kMaxShards) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  for (uint32_t t = t0; t < t1; t++) {
-    const uint32_t i0 = (t * kThreads + threadIdx.x) * PER;
-    uint32_t own[PER];
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-      const uint32_t i = i0 + j;
-      uint32_t o = 0xffu;
-      if (i < a.n) {
-        o = a.owner_in ? a.owner_in[i] : route_owner_of<KIND>(c, a.req + (size_t)i * MSG);
-        if (o >= a.world) o = 0xffu;
-      }
-      own[j] = o;
-    }
-    if (PER == 4 && i0 + 3 < a.n) {
-      *(uint32_t*)(a.owner + i0) = own[0] | (own[1 % PER] << 8) | (own[2 % PER] << 16) | (own[3 % PER] << 24);
-    } else {
-#pragma unroll
-      for (int j = 0; j < PER; j++)
-        if (i0 + j < a.n) a.owner[i0 + j] = (uint8_t)own[j];
-    }
-    for (uint32_t o = 0; o < a.world; o++) {
-      uint32_t k = 0;
-#pragma unroll
-      for (int j = 0; j < PER; j++) k += __popc(__ballot_sync(0xffffffffu, own[j] == o));
-      if (lane_id() == 0 && k) atomicAdd(&s_cnt[o], k);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < kMaxShards) a.cta_tot[b * kMaxShards + threadIdx.x] = threadIdx.x < a.world ? s_cnt[threadIdx.x] : 0u;
-  // group totals (32 consecutive CTAs) keep the scatter kernel's prefix short: G/32 + 32 loads instead of G
-  if (threadIdx.x < a.world && s_cnt[threadIdx.x]) atomicAdd(&a.grp_tot[(b / 32) * kMaxShards + threadIdx.x], s_cnt[threadIdx.x]);
+// look-back descriptor word: bits 63..56 seq, 55..54 status (1 = the tile's own counts, 2 = inclusive prefix), then two
+// 27-bit counters (shards 2k and 2k+1 in word k).  Every word validates itself, so the four words of a descriptor need
+// no common publication point.
+DINT_D unsigned long long lb_pack(uint32_t seq, uint32_t status, uint32_t lo, uint32_t hi) {
+  return ((unsigned long long)seq << 56) | ((unsigned long long)status << 54) | ((unsigned long long)hi << 27) | lo;
+}
+DINT_D unsigned long long lb_load(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+DINT_D void lb_store(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// dispatch, launch 2 of 2 (same grid): partition the tiles into the slabs, pad the slabs, raise the epoch flags
+// dispatch: owner bytes, stable partition into the slabs, padding, epoch flags -- one launch, one pass
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
+__global__ void __launch_bounds__(kThreads) k_route_dispatch(const Ctx c, const RouteArgs a) {
   using W = Wire<KIND>;
   using RT = RTile<W::MSG>;
   constexpr int MSG = W::MSG, PER = RT::PER;
@@ -186,55 +159,78 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
   uint8_t* s_out = smem + RT::BYTES + 16;                // the tile partitioned into runs
   __shared__ Cnt8 s_w[kThreads / 32];
   __shared__ uint32_t s_base[kMaxShards], s_total[kMaxShards], s_off[kMaxShards], s_len[kMaxShards];
-  __shared__ uint32_t s_last;
+  __shared__ uint32_t s_tile, s_last;
   const uint32_t G = gridDim.x, b = blockIdx.x;
-  const uint32_t t0 = (uint32_t)((uint64_t)a.n_tiles * b / G), t1 = (uint32_t)((uint64_t)a.n_tiles * (b + 1) / G);
 
-  // ---- first slot of this CTA's records in every slab, and the slab totals (warp o handles shard o) ----
-  {
-    const uint32_t o = warp_id(), ng = (G + 31) / 32, myg = b / 32;
-    uint32_t before = 0, all = 0;
-    if (o < a.world) {
-      for (uint32_t g = lane_id(); g < ng; g += 32) {
-        const uint32_t v = __ldcg(&a.grp_tot[g * kMaxShards + o]);
-        all += v;
-        if (g < myg) before += v;
-      }
-      const uint32_t q = myg * 32 + lane_id();
-      if (q < b) before += __ldcg(&a.cta_tot[q * kMaxShards + o]);
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      before += __shfl_xor_sync(0xffffffffu, before, d);
-      all += __shfl_xor_sync(0xffffffffu, all, d);
-    }
-    if (lane_id() == 0) { s_base[o] = before; s_total[o] = all; }
-  }
-  __syncthreads();
-  if (b == 0 && threadIdx.x < a.world && s_total[threadIdx.x] > a.cap) atomicAdd(&a.flags[0], s_total[threadIdx.x] - a.cap);
-
-  // ---- padding: slots [total, cap) of every slab, shared out over the CTAs ----
-  for (uint32_t o = 0; o < a.world; o++) {
-    const uint32_t tot = s_total[o] < a.cap ? s_total[o] : a.cap;
-    const uint64_t len = (uint64_t)(a.cap - tot) * MSG;
-    const uint64_t lo = len * b / G, hi = len * (b + 1) / G;
-    if (hi > lo) coop_fill_pad((uint8_t*)a.slab.p[o] + (uint64_t)tot * MSG + lo, hi - lo);
-  }
-
-  // ---- phase 2: partition every tile in shared memory, one contiguous run per shard leaves ----
-  for (uint32_t t = t0; t < t1; t++) {
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);          // tiles in index order: a tile only ever waits for
+    __syncthreads();                                                  // tiles drawn before it, i.e. by CTAs that are running
+    const uint32_t t = s_tile;
+    if (t >= a.n_tiles) break;
     const uint32_t first = t * RT::RECS;
-    const uint32_t valid = (a.n - first < (uint32_t)RT::RECS ? a.n - first : (uint32_t)RT::RECS) * MSG;
+    const uint32_t nrec = a.n - first < (uint32_t)RT::RECS ? a.n - first : (uint32_t)RT::RECS;
+    const uint32_t valid = nrec * MSG;
     {
       const uint8_t* src = a.req + (size_t)t * RT::BYTES;
       const uint32_t body = valid >> 4;
       for (uint32_t i = threadIdx.x; i < body; i += kThreads) ((uint4*)s_in)[i] = __ldcg((const uint4*)src + i);
       if (threadIdx.x < valid - (body << 4)) s_in[(body << 4) + threadIdx.x] = src[(body << 4) + threadIdx.x];
     }
+    __syncthreads();
+    // ---- owners of this thread's records ----
     uint32_t own[PER];
-    const Cnt8 mine = load_owners<PER>(a, t, own);
+    Cnt8 mine{0, 0};
+    const uint32_t r0 = threadIdx.x * PER;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      uint32_t o = 0xffu;
+      if (r0 + j < nrec) {
+        o = a.owner_in ? a.owner_in[first + r0 + j] : route_owner_of<KIND>(c, s_in + (size_t)(r0 + j) * MSG);
+        if (o >= a.world) o = 0xffu;
+      }
+      own[j] = o;
+      if (o < a.world) cnt8_inc(mine, o);
+    }
+    if (PER == 4 && r0 + 3 < nrec) {
+      *(uint32_t*)(a.owner + first + r0) = own[0] | (own[1 % PER] << 8) | (own[2 % PER] << 16) | (own[3 % PER] << 24);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (r0 + j < nrec) a.owner[first + r0 + j] = (uint8_t)own[j];
+    }
     Cnt8 excl, total;
-    block_scan_cnt8(mine, excl, total, s_w);              // (its barriers also publish s_in)
+    block_scan_cnt8(mine, excl, total, s_w);
+    // ---- decoupled look-back: lanes 0..3 of warp 0 own one descriptor word each (two shards per word) ----
+    if (threadIdx.x < 4) {
+      const uint32_t k = threadIdx.x;
+      const uint32_t c0 = cnt8_get(total, 2 * k), c1 = cnt8_get(total, 2 * k + 1);
+      unsigned long long* mydesc = a.desc + (size_t)t * 4 + k;
+      uint32_t e0 = 0, e1 = 0;
+      if (t == 0) {
+        lb_store(mydesc, lb_pack(a.seq, 2, c0, c1));
+      } else {
+        lb_store(mydesc, lb_pack(a.seq, 1, c0, c1));
+        for (uint32_t p = t; p-- > 0;) {
+          unsigned long long v;
+          do { v = lb_load(a.desc + (size_t)p * 4 + k); } while ((uint32_t)(v >> 56) != a.seq || ((v >> 54) & 3u) == 0);
+          e0 += (uint32_t)v & 0x7ffffffu;
+          e1 += (uint32_t)(v >> 27) & 0x7ffffffu;
+          if (((v >> 54) & 3u) == 2) break;
+        }
+        lb_store(mydesc, lb_pack(a.seq, 2, e0 + c0, e1 + c1));
+      }
+      s_base[2 * k] = e0;
+      s_base[2 * k + 1] = e1;
+      if (t == a.n_tiles - 1) {                          // the slabs' totals, for the padding and the overflow count
+        a.totals[2 * k] = e0 + c0;
+        a.totals[2 * k + 1] = e1 + c1;
+      }
+    }
+    __syncthreads();
+    if (t == a.n_tiles - 1 && threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.totals + kMaxShards), "r"(a.seq) : "memory");
+    }
     if (threadIdx.x == 0) {
       uint32_t off = 0;
       for (uint32_t o = 0; o < a.world; o++) {
@@ -270,26 +266,44 @@ __global__ void __launch_bounds__(kThreads) k_route_scatter(const RouteArgs a) {
       for (uint32_t o = warp_id(); o < a.world; o += kThreads / 32)
         if (s_len[o]) warp_copy16((uint8_t*)a.slab.p[o] + (uint64_t)s_base[o] * MSG, s_out + s_off[o], s_len[o]);
     }
-    __syncthreads();
-    if (threadIdx.x < a.world) s_base[threadIdx.x] += cnt8_get(total, threadIdx.x);
-    __syncthreads();
+    __syncthreads();                                     // (s_in / s_out / s_tile are reused by the next tile)
   }
 
+  // ---- the slabs' totals: published by whoever handled the last tile ----
+  if (a.n_tiles == 0) {
+    if (threadIdx.x < kMaxShards) s_total[threadIdx.x] = 0;
+  } else {
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.totals + kMaxShards) : "memory"); } while (v != a.seq);
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxShards) s_total[threadIdx.x] = __ldcg(&a.totals[threadIdx.x]);
+  }
+  __syncthreads();
+  if (b == 0 && threadIdx.x < a.world && s_total[threadIdx.x] > a.cap) atomicAdd(&a.flags[0], s_total[threadIdx.x] - a.cap);
+  // ---- padding: slots [total, cap) of every slab, shared out over the CTAs ----
+  for (uint32_t o = 0; o < a.world; o++) {
+    const uint32_t tot = s_total[o] < a.cap ? s_total[o] : a.cap;
+    const uint64_t len = (uint64_t)(a.cap - tot) * MSG;
+    const uint64_t lo = len * b / G, hi = len * (b + 1) / G;
+    if (hi > lo) coop_fill_pad((uint8_t*)a.slab.p[o] + (uint64_t)tot * MSG + lo, hi - lo);
+  }
   // ---- the last CTA to finish tells the peers that this source's slabs of epoch `epoch` are complete ----
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t prev = atomicAdd(a.done, 1u);
     s_last = prev == G - 1;
-    if (s_last) *a.done = 0;
+    if (s_last) { *a.done = 0; *a.ticket = 0; }          // for the next launch (stream-ordered behind this one)
   }
   __syncthreads();
-  if (s_last)
-    for (uint32_t i = threadIdx.x; i < ((G + 31) / 32) * kMaxShards; i += kThreads) a.grp_tot[i] = 0;   // for the next launch
   if (s_last && threadIdx.x < a.world && a.sig.p[threadIdx.x]) {
+    bool over = false;                                   // any slab of this source too small: every owner is told (bit 31)
+    for (uint32_t o = 0; o < a.world; o++) over |= s_total[o] > a.cap;
     __threadfence_system();
     uint32_t* flag = (uint32_t*)a.sig.p[threadIdx.x] + a.me;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.epoch) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.epoch | (over ? kSigOverflow : 0u)) : "memory");
   }
 }
 

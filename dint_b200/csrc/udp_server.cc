@@ -7,21 +7,33 @@
 // clients (`client_udp*`) talk to it unchanged.
 //
 // Shape: R socket threads (SO_REUSEPORT, like the reference's N threads) each alternate
-//     recvmmsg (a batch) -> hand the batch to the engine thread -> sendmmsg (the replies),
-// and ONE engine thread gathers whatever batches are ready, in socket order, into one pinned array, makes ONE
-// dint_submit() call for all of them (H2D, kernels, D2H inside) and hands every socket thread its slice of the
-// replies.  While the GPU serves one gathering, the other sockets keep receiving: that is the pipeline.
+//     recvmmsg (a batch) -> hand the batch to an engine thread -> sendmmsg (the replies),
+// and TWO engine threads take turns: each gathers whatever batches are ready, in socket order, into its own pinned
+// array, makes ONE submit call for all of them (H2D, kernels, D2H inside) and hands every socket thread its slice of
+// the replies -- while one gathering is on the GPU the other thread collects and copies the next one.
 // Order: datagrams of one socket (one client 4-tuple always hashes to the same socket) keep their arrival
 // order inside the array, and request i of a submit sees the effects of every earlier one -- what ONE reference
 // thread would have produced for that arrival order.  (Across sockets the reference has no order either.)
+//
+// --gpus N: the key space is served by N GPUs of this box through the C-level cluster API (dint_cluster_*): lock
+// servers and store route every request to the GPU that owns its slot; tatp / smallbank keep the reference's
+// deployment of one `server_shard` per address -- here shard i listens on port P + i and the port a datagram arrives
+// on is the shard the client chose (tatp/caladan/client_udp_shard.cc:187: `key % kNumServers` picks the address).
+//
+// Caladan clients (lock_2pl/caladan/client_caladan.cc:248-271) first ask the server for data ports: a 4-byte
+// `net_req{int nports}` datagram on the well-known port is answered with `net_resp{int nports; uint16_t ports[]}` after
+// the server has opened that many fresh sockets (lock_2pl/caladan/proto.h:32-39, server.cc:107-146).  No wire message
+// is 4 bytes long, so the same port serves both: a 4-byte datagram is a control request, everything else is data.
 //
 // Host C++ above the C ABI only (include/dint_b200.h): no CUDA here, no oracle, no CPU fallback -- without a
 // GPU dint_create() fails and the server exits.
 //
 // usage: dint_udp_server <lock_2pl|lock_fasst|log_server|store|tatp|smallbank> [--port P] [--bind A.B.C.D]
-//                        [--sockets R] [--batch N] [--device D] [--shard-id I --shards G] [--linger-us U]
+//                        [--sockets R] [--batch N] [--device D] [--gpus G [--devices a,b,..]] [--shard-id I --shards G]
+//                        [--linger-us U] [--populate N]
 #include <arpa/inet.h>
 #include <netinet/in.h>
+#include <poll.h>
 #include <signal.h>
 #include <sys/socket.h>
 #include <unistd.h>
@@ -33,6 +45,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -49,14 +63,18 @@ void on_signal(int) { g_stop.store(true); }
 
 // one socket thread's batch: filled by recvmmsg, answered in place, sent back with sendmmsg
 struct Worker {
-  int fd = -1;
+  std::vector<int> fds;                 // 1 socket (a listener) or the data sockets opened for one control request
+  int group = 0;                        // --gpus with tatp / smallbank: the shard whose port these sockets serve
+  bool control = false;                 // listens on a well-known port: 4-byte datagrams are control requests
   std::vector<uint8_t> buf;             // n * msg: requests in, replies out
   std::vector<mmsghdr> hdr;
   std::vector<iovec> iov;
   std::vector<sockaddr_in> peer;
+  std::vector<int> from;                // fd index of every datagram
   int n = 0;
   enum State { FILLING, READY, IN_FLIGHT, DONE } state = FILLING;   // guarded by the shared mutex
-  uint64_t datagrams = 0, dropped = 0;
+  uint64_t datagrams = 0, dropped = 0, controls = 0;
+  std::thread th;
 };
 
 int kind_of(const std::string& s) {
@@ -66,22 +84,34 @@ int kind_of(const std::string& s) {
   return -1;
 }
 
+int open_socket(const sockaddr_in& addr, bool reuseport) {
+  int fd = socket(AF_INET, SOCK_DGRAM, 0);
+  if (fd < 0) return -1;
+  int one = 1, buf = 32 << 20;
+  if (reuseport) setsockopt(fd, SOL_SOCKET, SO_REUSEPORT, &one, sizeof one);
+  setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof buf);
+  setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &buf, sizeof buf);
+  if (bind(fd, (const sockaddr*)&addr, sizeof addr) < 0) { close(fd); return -1; }
+  return fd;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
   if (argc < 2) {
     fprintf(stderr, "usage: %s <lock_2pl|lock_fasst|log_server|store|tatp|smallbank> [--port P] [--bind ADDR] [--sockets R] "
-                    "[--batch N] [--device D] [--shards G --shard-id I] [--linger-us U]\n", argv[0]);
+                    "[--batch N] [--device D] [--gpus G [--devices a,b,..]] [--shards G --shard-id I] [--linger-us U] [--populate N]\n", argv[0]);
     return 2;
   }
   const int kind = kind_of(argv[1]);
   if (kind < 0) { fprintf(stderr, "unknown server kind '%s'\n", argv[1]); return 2; }
-  int port = 20230, device = 0, linger_us = 50;
+  int port = 20230, device = 0, linger_us = 50, gpus = 1, populate = -1;
   unsigned batch_max = 16384, shards = 1, shard_id = 0;
   unsigned n_sock = std::thread::hardware_concurrency() / 2;
   if (n_sock < 1) n_sock = 1;
   if (n_sock > 8) n_sock = 8;                         // the reference runs `server 8` (exp/run_lock_fasst.sh)
   std::string bind_addr = "0.0.0.0";
+  std::vector<int> devices;
   for (int i = 2; i + 1 < argc; i += 2) {
     const std::string a = argv[i];
     const char* v = argv[i + 1];
@@ -90,95 +120,140 @@ int main(int argc, char** argv) {
     else if (a == "--batch") batch_max = (unsigned)atoi(v);
     else if (a == "--sockets") n_sock = (unsigned)atoi(v);
     else if (a == "--device") device = atoi(v);
+    else if (a == "--gpus") gpus = atoi(v);
+    else if (a == "--devices") { for (const char* p = v; *p;) { devices.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p) p++; } }
     else if (a == "--shards") shards = (unsigned)atoi(v);
     else if (a == "--shard-id") shard_id = (unsigned)atoi(v);
     else if (a == "--linger-us") linger_us = atoi(v);
+    else if (a == "--populate") populate = atoi(v);
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
   if (batch_max < 1) batch_max = 1;
   if (n_sock < 1) n_sock = 1;
   if (n_sock > 64) n_sock = 64;
+  if (gpus < 1 || gpus > 8 || (!devices.empty() && (int)devices.size() != gpus)) { fprintf(stderr, "bad --gpus / --devices\n"); return 2; }
   sockaddr_in srv{};
   srv.sin_family = AF_INET;
-  srv.sin_port = htons((uint16_t)port);
   if (inet_pton(AF_INET, bind_addr.c_str(), &srv.sin_addr) != 1) { fprintf(stderr, "bad --bind address\n"); return 2; }
   const uint32_t msg = dint_msg_size(kind);
+  const bool by_dst = kind == DINT_TATP || kind == DINT_SMALLBANK;
+  const int n_groups = (gpus > 1 && by_dst) ? gpus : 1;        // one well-known port per shard server
 
-  // ---- engine: the state the reference keeps in its global arrays lives on the GPU ----
+  // ---- engine: the state the reference keeps in its global arrays lives on the GPU(s) ----
   dint_cfg cfg;
   dint_default_cfg(kind, &cfg);                       // kLockHashSize, table sizes, ring length of the reference
-  if (kind == DINT_TATP || kind == DINT_SMALLBANK) {  // server_shard <id>: the CLIENT picks the shard; each holds its replicas
-    cfg.txn_shards = shards;
-    cfg.txn_shard_id = shard_id;
-  }
+  if (populate >= 0) { cfg.subs_populate = (uint32_t)populate; cfg.accts_populate = (uint32_t)populate; }   // a prefix of the reference's population
   dint_engine* eng = nullptr;
-  if (dint_create(kind, &cfg, device, &eng) != DINT_OK) {
-    fprintf(stderr, "dint_udp_server: dint_create failed: %s\n", dint_last_error());
-    return 1;
+  dint_cluster* cluster = nullptr;
+  if (gpus > 1) {
+    if (dint_cluster_create(kind, &cfg, gpus, devices.empty() ? nullptr : devices.data(), 0, &cluster) != DINT_OK ||
+        dint_cluster_populate(cluster) != DINT_OK) {
+      fprintf(stderr, "dint_udp_server: dint_cluster_create/populate failed: %s\n", dint_last_error());
+      return 1;
+    }
+  } else {
+    if (by_dst) {                                     // server_shard <id>: the CLIENT picks the shard; each holds its replicas
+      cfg.txn_shards = shards;
+      cfg.txn_shard_id = shard_id;
+    }
+    if (dint_create(kind, &cfg, device, &eng) != DINT_OK) {
+      fprintf(stderr, "dint_udp_server: dint_create failed: %s\n", dint_last_error());
+      return 1;
+    }
+    if (dint_populate(eng) != DINT_OK) {              // kvs_init + populate_* of the reference (no-op for lock / log)
+      fprintf(stderr, "dint_udp_server: dint_populate failed: %s\n", dint_last_error());
+      return 1;
+    }
   }
-  if (dint_populate(eng) != DINT_OK) {                // kvs_init + populate_* of the reference (no-op for lock / log)
-    fprintf(stderr, "dint_udp_server: dint_populate failed: %s\n", dint_last_error());
-    return 1;
-  }
-
-  // ---- sockets: as the reference sets them up, one per thread, all bound to the same port ----
-  std::vector<Worker> w(n_sock);
-  for (Worker& x : w) {
-    x.fd = socket(AF_INET, SOCK_DGRAM, 0);
-    if (x.fd < 0) { perror("socket"); return 1; }
-    int one = 1, buf = 32 << 20;
-    setsockopt(x.fd, SOL_SOCKET, SO_REUSEPORT, &one, sizeof one);
-    setsockopt(x.fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof buf);
-    setsockopt(x.fd, SOL_SOCKET, SO_SNDBUF, &buf, sizeof buf);
-    timeval tv{0, 200000};                            // wake up 5x a second to notice a stop request
-    setsockopt(x.fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
-    if (bind(x.fd, (sockaddr*)&srv, sizeof srv) < 0) { perror("bind"); return 1; }
-    x.buf.resize((size_t)batch_max * msg);
-    x.hdr.resize(batch_max);
-    x.iov.resize(batch_max);
-    x.peer.resize(batch_max);
-  }
-  // the array one dint_submit() sees: every ready batch, back to back (pinned: the engine copies from / to it)
-  const size_t arr_cap = (size_t)batch_max * n_sock;
-  uint8_t* req = (uint8_t*)dint_host_alloc(arr_cap * msg);
-  uint8_t* resp = (uint8_t*)dint_host_alloc(arr_cap * msg);
-  if (!req || !resp) { fprintf(stderr, "pinned allocation failed\n"); return 1; }
 
   std::mutex mu;
   std::condition_variable cv_engine, cv_workers;
+  std::vector<std::unique_ptr<Worker>> w;            // grows when control requests open data sockets (under mu)
   std::atomic<uint64_t> submits{0}, bad_batches{0};
-  signal(SIGINT, on_signal);
-  signal(SIGTERM, on_signal);
-  fprintf(stderr, "dint_udp_server: %s on %s:%d, device %d, %u sockets, batches of <= %u datagrams of %u bytes\n", argv[1],
-          bind_addr.c_str(), port, device, n_sock, batch_max, msg);
 
-  auto socket_thread = [&](Worker& x) {
+  auto make_worker = [&](std::vector<int> fds, int group, bool control) {
+    std::unique_ptr<Worker> x(new Worker());
+    x->fds = std::move(fds);
+    x->group = group;
+    x->control = control;
+    x->buf.resize((size_t)batch_max * msg);
+    x->hdr.resize(batch_max);
+    x->iov.resize(batch_max);
+    x->peer.resize(batch_max);
+    x->from.resize(batch_max);
+    return x;
+  };
+
+  std::function<void(Worker&)> socket_thread;
+  // control handshake (lock_2pl/caladan/server.cc:107-146): open `nports` fresh sockets, serve them, tell the client
+  auto handle_control = [&](Worker& x, int fd, const sockaddr_in& who, int nports) {
+    if (nports < 1 || nports > 1024) return;
+    std::vector<int> fds;
+    std::vector<uint8_t> resp(sizeof(int) + sizeof(uint16_t) * (size_t)nports);
+    memcpy(resp.data(), &nports, sizeof(int));
+    sockaddr_in any = srv;
+    any.sin_port = 0;
+    for (int i = 0; i < nports; i++) {
+      int dfd = open_socket(any, false);
+      if (dfd < 0) { for (int q : fds) close(q); return; }
+      sockaddr_in got{};
+      socklen_t gl = sizeof got;
+      getsockname(dfd, (sockaddr*)&got, &gl);
+      const uint16_t p = ntohs(got.sin_port);          // rt::UdpConn::LocalAddr().port is host order
+      memcpy(resp.data() + sizeof(int) + sizeof(uint16_t) * (size_t)i, &p, sizeof p);
+      fds.push_back(dfd);
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      w.push_back(make_worker(std::move(fds), x.group, false));
+      Worker* nw = w.back().get();
+      nw->th = std::thread(socket_thread, std::ref(*nw));
+    }
+    sendto(fd, resp.data(), resp.size(), 0, (const sockaddr*)&who, sizeof who);
+    x.controls++;
+  };
+
+  socket_thread = [&](Worker& x) {
+    std::vector<pollfd> pfd(x.fds.size());
     while (!g_stop.load()) {
-      // ---- receive (replaces net_recv): block for the first datagram, then drain what has queued up ----
-      for (unsigned i = 0; i < batch_max; i++) {
-        x.iov[i] = {x.buf.data() + (size_t)i * msg, msg};
-        x.hdr[i].msg_hdr = {&x.peer[i], sizeof(sockaddr_in), &x.iov[i], 1, nullptr, 0, 0};
-        x.hdr[i].msg_len = 0;
-      }
-      int n = recvmmsg(x.fd, x.hdr.data(), batch_max, MSG_WAITFORONE, nullptr);
-      if (n <= 0) continue;                           // timeout: look at the stop flag again
+      // ---- receive (replaces net_recv): wait for the first datagram, then drain what has queued up ----
+      for (size_t i = 0; i < x.fds.size(); i++) pfd[i] = {x.fds[i], POLLIN, 0};
+      if (poll(pfd.data(), (nfds_t)pfd.size(), 200) <= 0) continue;     // timeout: look at the stop flag again
+      int n = 0;
       const auto t0 = std::chrono::steady_clock::now();
-      while ((unsigned)n < batch_max) {               // keep draining for a short linger so that load builds batches
-        const int m = recvmmsg(x.fd, x.hdr.data() + n, batch_max - (unsigned)n, MSG_DONTWAIT, nullptr);
-        if (m > 0) { n += m; continue; }
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(linger_us)) break;
+      for (;;) {
+        bool any = false;
+        for (size_t i = 0; i < x.fds.size() && (unsigned)n < batch_max; i++) {
+          for (unsigned q = (unsigned)n; q < batch_max; q++) {
+            x.iov[q] = {x.buf.data() + (size_t)q * msg, msg};
+            x.hdr[q].msg_hdr = {&x.peer[q], sizeof(sockaddr_in), &x.iov[q], 1, nullptr, 0, 0};
+            x.hdr[q].msg_len = 0;
+          }
+          const int m = recvmmsg(x.fds[i], x.hdr.data() + n, batch_max - (unsigned)n, MSG_DONTWAIT, nullptr);
+          if (m > 0) { for (int q = 0; q < m; q++) x.from[n + q] = (int)i; n += m; any = true; }
+        }
+        if ((unsigned)n >= batch_max) break;
+        if (!any && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(linger_us)) break;   // a short linger so that load builds batches
       }
       int keep = 0;                                   // a datagram of the wrong size cannot be a request of this server
       for (int i = 0; i < n; i++) {
-        if (x.hdr[i].msg_len != msg) { x.dropped++; continue; }
+        if (x.hdr[i].msg_len != msg) {
+          int nports = 0;
+          if (x.control && x.hdr[i].msg_len == sizeof(int)) {          // net_req{int nports}
+            memcpy(&nports, x.buf.data() + (size_t)i * msg, sizeof(int));
+            handle_control(x, x.fds[x.from[i]], x.peer[i], nports);
+          } else x.dropped++;
+          continue;
+        }
         if (keep != i) {
           memcpy(x.buf.data() + (size_t)keep * msg, x.buf.data() + (size_t)i * msg, msg);
           x.peer[keep] = x.peer[i];
+          x.from[keep] = x.from[i];
         }
         keep++;
       }
       if (keep == 0) continue;
-      // ---- hand the batch to the engine thread and wait for the replies (they come back in x.buf) ----
+      // ---- hand the batch to an engine thread and wait for the replies (they come back in x.buf) ----
       {
         std::unique_lock<std::mutex> lk(mu);
         x.n = keep;
@@ -189,76 +264,123 @@ int main(int argc, char** argv) {
         if (x.state != Worker::DONE) return;
         x.state = Worker::FILLING;
       }
-      // ---- send (replaces net_send): every reply goes back to the address its request came from ----
+      // ---- send (replaces net_send): every reply goes back to the address, and from the socket, its request came to ----
       for (int i = 0; i < keep; i++) {
-        x.iov[i].iov_base = x.buf.data() + (size_t)i * msg;
-        x.hdr[i].msg_hdr.msg_name = &x.peer[i];
-        x.hdr[i].msg_hdr.msg_namelen = sizeof(sockaddr_in);
+        x.iov[i] = {x.buf.data() + (size_t)i * msg, msg};
+        x.hdr[i].msg_hdr = {&x.peer[i], sizeof(sockaddr_in), &x.iov[i], 1, nullptr, 0, 0};
       }
       for (int sent = 0; sent < keep;) {
-        const int r = sendmmsg(x.fd, x.hdr.data() + sent, (unsigned)(keep - sent), 0);
-        if (r <= 0) { x.dropped += (uint64_t)(keep - sent); break; }
-        sent += r;
+        int run = 1;
+        while (sent + run < keep && x.from[sent + run] == x.from[sent]) run++;
+        for (int done = 0; done < run;) {
+          const int r = sendmmsg(x.fds[x.from[sent]], x.hdr.data() + sent + done, (unsigned)(run - done), 0);
+          if (r <= 0) { x.dropped += (uint64_t)(run - done); break; }
+          done += r;
+        }
+        sent += run;
       }
       x.datagrams += (uint64_t)keep;
     }
   };
 
-  std::vector<std::thread> threads;
-  for (Worker& x : w) threads.emplace_back(socket_thread, std::ref(x));
-
-  // ---- engine thread (this one): gather the ready batches, one dint_submit, scatter the replies ----
-  std::vector<int> taken;
-  while (!g_stop.load()) {
-    taken.clear();
-    size_t n = 0;
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      cv_engine.wait_for(lk, std::chrono::milliseconds(200), [&] {
-        for (const Worker& x : w)
-          if (x.state == Worker::READY) return true;
-        return g_stop.load();
-      });
-      for (unsigned i = 0; i < n_sock; i++)           // socket order: deterministic for a given set of ready batches
-        if (w[i].state == Worker::READY) { w[i].state = Worker::IN_FLIGHT; taken.push_back((int)i); }
+  // ---- sockets: as the reference sets them up, one per thread, all bound to the same port (one port per shard group) ----
+  for (int g = 0; g < n_groups; g++) {
+    sockaddr_in a = srv;
+    a.sin_port = htons((uint16_t)(port + g));
+    for (unsigned i = 0; i < n_sock; i++) {
+      const int fd = open_socket(a, true);
+      if (fd < 0) { perror("socket/bind"); return 1; }
+      w.push_back(make_worker({fd}, g, true));
     }
-    if (taken.empty()) continue;
-    for (int i : taken) {                             // the batches back to back: ONE array for the engine
-      memcpy(req + n * msg, w[i].buf.data(), (size_t)w[i].n * msg);
-      n += (size_t)w[i].n;
-    }
-    // replaces the switch(type) of the reference's server_loop for every gathered datagram, in array order
-    const int rc = dint_submit(eng, req, (uint64_t)n, resp);
-    if (rc != DINT_OK && rc != DINT_EPROTO) {         // DINT_EPROTO: malformed records were answered with type 0xFF
-      fprintf(stderr, "dint_udp_server: dint_submit failed: %s\n", dint_last_error());
-      g_stop.store(true);
-    }
-    if (rc == DINT_EPROTO) bad_batches++;
-    submits++;
-    size_t off = 0;
-    for (int i : taken) {
-      memcpy(w[i].buf.data(), resp + off * msg, (size_t)w[i].n * msg);
-      off += (size_t)w[i].n;
-    }
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      for (int i : taken) w[i].state = Worker::DONE;
-    }
-    cv_workers.notify_all();
   }
+  signal(SIGINT, on_signal);
+  signal(SIGTERM, on_signal);
+  fprintf(stderr, "dint_udp_server: %s on %s:%d%s, %d GPU(s), %u sockets, batches of <= %u datagrams of %u bytes\n", argv[1],
+          bind_addr.c_str(), port, n_groups > 1 ? " (+shard)" : "", gpus, n_sock * (unsigned)n_groups, batch_max, msg);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& x : w) x->th = std::thread(socket_thread, std::ref(*x));
+  }
+
+  // ---- engine threads: gather the ready batches, one submit, scatter the replies; two of them take turns ----
+  std::mutex submit_mu;                               // the engine has ONE submitter at a time (include/dint_b200.h)
+  auto engine_thread = [&]() {
+    size_t arr_cap = (size_t)batch_max * 8;           // the array one submit sees: every ready batch, back to back (pinned)
+    uint8_t* req = (uint8_t*)dint_host_alloc(arr_cap * msg);
+    uint8_t* resp = (uint8_t*)dint_host_alloc(arr_cap * msg);
+    std::vector<uint8_t> dst(arr_cap);
+    std::vector<Worker*> taken;
+    if (!req || !resp) { fprintf(stderr, "pinned allocation failed\n"); g_stop.store(true); return; }
+    while (!g_stop.load()) {
+      taken.clear();
+      size_t n = 0;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_engine.wait_for(lk, std::chrono::milliseconds(200), [&] {
+          for (const auto& x : w)
+            if (x->state == Worker::READY) return true;
+          return g_stop.load();
+        });
+        for (auto& x : w)                             // socket order: deterministic for a given set of ready batches
+          if (x->state == Worker::READY && n + (size_t)x->n <= arr_cap) { x->state = Worker::IN_FLIGHT; taken.push_back(x.get()); n += (size_t)x->n; }
+      }
+      if (taken.empty()) continue;
+      n = 0;
+      for (Worker* x : taken) {                       // the batches back to back: ONE array for the engine
+        memcpy(req + n * msg, x->buf.data(), (size_t)x->n * msg);
+        memset(dst.data() + n, x->group, (size_t)x->n);
+        n += (size_t)x->n;
+      }
+      int rc;
+      {
+        // replaces the switch(type) of the reference's server_loop for every gathered datagram, in array order
+        std::lock_guard<std::mutex> sl(submit_mu);
+        rc = cluster ? dint_cluster_submit(cluster, req, (uint64_t)n, by_dst ? dst.data() : nullptr, resp) : dint_submit(eng, req, (uint64_t)n, resp);
+      }
+      if (rc != DINT_OK && rc != DINT_EPROTO) {       // DINT_EPROTO: malformed records were answered with type 0xFF
+        fprintf(stderr, "dint_udp_server: submit failed: %s\n", dint_last_error());
+        g_stop.store(true);
+      }
+      if (rc == DINT_EPROTO) bad_batches++;
+      submits++;
+      size_t off = 0;
+      for (Worker* x : taken) {
+        memcpy(x->buf.data(), resp + off * msg, (size_t)x->n * msg);
+        off += (size_t)x->n;
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        for (Worker* x : taken) x->state = Worker::DONE;
+      }
+      cv_workers.notify_all();
+    }
+    dint_host_free(req);
+    dint_host_free(resp);
+  };
+  std::thread second(engine_thread);
+  engine_thread();
+  second.join();
   {
     std::lock_guard<std::mutex> lk(mu);               // under the mutex: no worker sits between its predicate and its wait
     g_stop.store(true);
   }
   cv_workers.notify_all();
-  for (std::thread& t : threads) t.join();
-  uint64_t total = 0, dropped = 0;
-  for (Worker& x : w) { total += x.datagrams; dropped += x.dropped; close(x.fd); }
-  fprintf(stderr, "dint_udp_server: %llu datagrams in %llu submits (%.1f per submit), %llu dropped, %llu submits with malformed records\n",
+  uint64_t total = 0, dropped = 0, controls = 0;
+  for (size_t i = 0;; i++) {                          // (control requests may still have been adding workers)
+    Worker* x;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (i >= w.size()) break;
+      x = w[i].get();
+    }
+    if (x->th.joinable()) x->th.join();
+    total += x->datagrams; dropped += x->dropped; controls += x->controls;
+    for (int fd : x->fds) close(fd);
+  }
+  fprintf(stderr, "dint_udp_server: %llu datagrams in %llu submits (%.1f per submit), %llu dropped, %llu control requests, %llu submits with malformed records\n",
           (unsigned long long)total, (unsigned long long)submits.load(), submits.load() ? (double)total / (double)submits.load() : 0.0,
-          (unsigned long long)dropped, (unsigned long long)bad_batches.load());
-  dint_host_free(req);
-  dint_host_free(resp);
-  dint_destroy(eng);
+          (unsigned long long)dropped, (unsigned long long)controls, (unsigned long long)bad_batches.load());
+  if (cluster) dint_cluster_destroy(cluster);
+  if (eng) dint_destroy(eng);
   return 0;
 }

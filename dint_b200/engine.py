@@ -49,7 +49,7 @@ _lib = None
 # every symbol include/dint_b200.h declares
 ABI_SYMBOLS = [
     "dint_msg_size", "dint_default_cfg", "dint_create", "dint_destroy", "dint_populate", "dint_load",
-    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_submit_host", "dint_shard_flags", "dint_cluster_create", "dint_cluster_populate", "dint_cluster_submit", "dint_cluster_engine", "dint_cluster_size", "dint_cluster_destroy", "dint_snapshot_create", "dint_snapshot_restore", "dint_snapshot_destroy", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
+    "dint_submit", "dint_submit_device", "dint_route_owner", "dint_route_partition", "dint_route_unpermute", "dint_route_tile_records", "dint_route_dispatch", "dint_route_combine", "dint_p2p_wait", "dint_p2p_signal", "dint_shard_create", "dint_shard_destroy", "dint_shard_submit_many", "dint_shard_submit_host", "dint_shard_flags", "dint_cluster_create", "dint_cluster_populate", "dint_cluster_submit", "dint_cluster_engine", "dint_cluster_size", "dint_cluster_overflow_retries", "dint_shard_recover", "dint_cluster_destroy", "dint_clients_create", "dint_clients_run", "dint_clients_stats", "dint_clients_peek", "dint_clients_destroy", "dint_snapshot_create", "dint_snapshot_restore", "dint_snapshot_destroy", "dint_sync", "dint_kv_get", "dint_kv_count", "dint_lock_state",
     "dint_lock_slot", "dint_dump_log", "dint_log_entry_size", "dint_get_stats", "dint_reset_stats",
     "dint_profile", "dint_kernel_times", "dint_last_error", "dint_host_alloc", "dint_host_free",
     "dint_test_fasthash64", "dint_test_fastmod", "dint_test_host_slices",
@@ -91,7 +91,14 @@ def lib():
     L.dint_cluster_submit.restype = i32; L.dint_cluster_submit.argtypes = [vp, vp, u64, vp, vp]
     L.dint_cluster_engine.restype = vp; L.dint_cluster_engine.argtypes = [vp, i32]
     L.dint_cluster_size.restype = u32; L.dint_cluster_size.argtypes = [vp]
+    L.dint_cluster_overflow_retries.restype = u64; L.dint_cluster_overflow_retries.argtypes = [vp]
+    L.dint_shard_recover.restype = i32; L.dint_shard_recover.argtypes = [vp, u32, C.POINTER(u32)]
     L.dint_cluster_destroy.restype = None; L.dint_cluster_destroy.argtypes = [vp]
+    L.dint_clients_create.restype = i32; L.dint_clients_create.argtypes = [vp, u32, u64, u32, C.c_double, u32, C.POINTER(vp)]
+    L.dint_clients_run.restype = i32; L.dint_clients_run.argtypes = [vp, u32, vp]
+    L.dint_clients_stats.restype = i32; L.dint_clients_stats.argtypes = [vp, C.POINTER(u64)]
+    L.dint_clients_peek.restype = i32; L.dint_clients_peek.argtypes = [vp, vp, vp]
+    L.dint_clients_destroy.restype = None; L.dint_clients_destroy.argtypes = [vp]
     L.dint_snapshot_create.restype = i32; L.dint_snapshot_create.argtypes = [vp, C.POINTER(vp)]
     L.dint_snapshot_restore.restype = i32; L.dint_snapshot_restore.argtypes = [vp, vp]
     L.dint_snapshot_destroy.restype = None; L.dint_snapshot_destroy.argtypes = [vp]
@@ -402,6 +409,52 @@ class Engine:
         return {arr[i].name.decode(): (arr[i].launches, arr[i].total_ms) for i in range(max(k, 0))}
 
 
+class GpuClients:
+    """lock_fasst closed-loop clients resident on the GPU next to `engine` (dint_clients_*)."""
+
+    def __init__(self, engine, n_clients, seed=20230, n_keys=24_000_000, zipf_theta=0.0, read_pct=80):
+        self.engine, self.n = engine, n_clients
+        h = C.c_void_p()
+        rc = lib().dint_clients_create(engine.h, n_clients, seed, n_keys, zipf_theta, read_pct, C.byref(h))
+        if rc != 0:
+            raise DintError(rc, "dint_clients_create")
+        self.h = h
+
+    def run(self, rounds, stream=None):
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        rc = lib().dint_clients_run(self.h, rounds, C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise DintError(rc, "dint_clients_run")
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        rc = lib().dint_clients_stats(self.h, out)
+        if rc != 0:
+            raise DintError(rc, "dint_clients_stats")
+        return dict(zip(["requests", "committed", "validation_aborts", "lock_rejects", "rounds"], [int(x) for x in out]))
+
+    def peek(self):
+        rq = np.empty(self.n * 9, dtype=np.uint8)
+        rs = np.empty(self.n * 9, dtype=np.uint8)
+        rc = lib().dint_clients_peek(self.h, rq.ctypes.data, rs.ctypes.data)
+        if rc != 0:
+            raise DintError(rc, "dint_clients_peek")
+        return rq, rs
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().dint_clients_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class GpuCluster:
     """G shard engines driven by ONE process (dint_cluster_*): the C-level multi-GPU server.  devices: CUDA ordinals,
     all distinct (NVLink peer access) or all the same (several shards resident on one GPU)."""
@@ -430,6 +483,9 @@ class GpuCluster:
         if rc != 0 and (check or rc != DINT_EPROTO):
             raise DintError(rc, "dint_cluster_submit")
         return out
+
+    def overflow_retries(self):
+        return int(lib().dint_cluster_overflow_retries(self.h))
 
     def engine(self, shard):
         """A non-owning Engine view of one shard (state inspection)."""

@@ -146,7 +146,8 @@ int dint_route_partition(dint_engine *e, const void *req_dev, const uint8_t *own
 /* Fixed-capacity dispatch / combine (no host round trip for the split sizes), local or over NVLink peer memory.
  * Every source rank sends every shard o one SLAB of `cap` records: its records for o first, in request order,
  * then padding records (every byte 0xFE: a padding record is answered unchanged and touches nothing).
- *   dint_route_dispatch: ONE cooperative kernel.  owner_in_dev = client-chosen shard per record (tatp / smallbank
+ *   dint_route_dispatch: ONE kernel, one pass over the batch (single-pass prefix sums by decoupled look-back; n < 2^27).
+ *     owner_in_dev = client-chosen shard per record (tatp / smallbank
  *     placement) or NULL = computed as dint_route_owner would (needs n_shards == cfg.n_shards).  slab_ptrs->p[o] =
  *     device address of THIS source's slab for shard o: inside a local send buffer (then exchange the slabs with
  *     an all-to-all) or inside rank o's receive buffer mapped over NVLink (then no collective is needed: with
@@ -176,8 +177,8 @@ int dint_p2p_signal(dint_engine *e, const dint_peer_ptrs *sig_ptrs, uint32_t n_s
                     void *cuda_stream);
 /* The whole sharded step over NVLink peer memory, driven from ONE host call per sequence of batches (what
  * dint_b200/shard.py uses at N > 1, one process per GPU).  Every rank owns n_sets (2..4) buffer sets {inbox, return
- * buffer}, each n_shards * cap records (cap a multiple of 128), plus one 256-byte signal block (two arrays of 8 epoch
- * words: requests written / replies written), all in memory its peers map (CUDA IPC / torch symmetric memory), zeroed once.
+ * buffer}, each n_shards * cap records (cap a multiple of 128), plus one 256-byte signal block (epoch words: requests
+ * written [n_sets][8] at +0, replies written [8] at +128), all in memory its peers map (CUDA IPC / torch symmetric memory), zeroed once.
  *   inbox_sets[s].p[o], retbox_sets[s].p[o]: device address of rank o's set s; sig_blocks->p[o]: rank o's block.
  * dint_shard_submit_many: k batches of n (<= max_n) records each, the same k on every rank; batch j+1 is partitioned
  * into the OWNERS' inboxes (dint_route_dispatch) while batch j runs through the local engine on cuda_stream -- its
@@ -199,6 +200,12 @@ int dint_shard_submit_many(dint_shard_ctx *c, uint32_t k, const void *const *req
 int dint_shard_submit_host(dint_shard_ctx *c, uint32_t k, const void *const *req_host, const uint8_t *const *dst_host, uint64_t n,
                            void *const *out_host);
 int dint_shard_flags(dint_shard_ctx *c, uint32_t out[2]);
+/* Slab overflow (more records of one source for one owner than `cap`): the source flags it to EVERY owner with the
+ * batch, and from that batch on no shard serves anything -- the state stays exactly what it was after the last complete
+ * batch.  dint_shard_recover (call on every rank, synchronises): *first_unserved = index, inside the last submit call of
+ * k_last batches, of the first batch left unserved (0xffffffff: none); clears the condition.  Serve the unserved
+ * batches again in pieces of at most `cap` records per rank -- those cannot overflow.  (dint_cluster_submit does this.) */
+int dint_shard_recover(dint_shard_ctx *c, uint32_t k_last, uint32_t *first_unserved);
 
 /*
  * Multi-GPU server in ONE process: SURVEY.md section 8(b)'s `dint_create(kind, cfg, n_gpus)` / `dint_submit(e, req, n,
@@ -214,7 +221,9 @@ int dint_shard_flags(dint_shard_ctx *c, uint32_t out[2]);
  *     >= 3) and holds only the keys it is a replica of.
  *   dint_cluster_submit: req/resp are HOST arrays of n wire structs; dst_shard[i] (tatp / smallbank: required, the
  *     shard the client would have sent record i to; other kinds: NULL) -- resp[i] answers req[i]; semantics: every
- *     shard sees its records in index order.  Returns 0, DINT_EPROTO, or an error; never blocks on the network.
+ *     shard sees its records in index order.  Keys skewed beyond the slack of the exchange slabs (all records of
+ *     a round hashing to one shard) are handled: the round that does not fit is served again in smaller pieces.
+ *     Returns 0, DINT_EPROTO, or an error; never blocks on the network.
  */
 typedef struct dint_cluster dint_cluster;
 int dint_cluster_create(int kind, const dint_cfg *cfg, int n_gpus, const int *devices, uint64_t max_batch, dint_cluster **out);
@@ -222,6 +231,7 @@ int dint_cluster_populate(dint_cluster *c);
 int dint_cluster_submit(dint_cluster *c, const void *req, uint64_t n, const uint8_t *dst_shard, void *resp);
 dint_engine *dint_cluster_engine(dint_cluster *c, int shard);   /* state inspection of one shard */
 uint32_t dint_cluster_size(dint_cluster *c);
+uint64_t dint_cluster_overflow_retries(dint_cluster *c);   /* submit calls that met a slab overflow (recovered, see dint_shard_recover) */
 void dint_cluster_destroy(dint_cluster *c);
 int dint_route_unpermute(dint_engine *e, const void *sorted_dev, const uint32_t *perm_dev, uint64_t n, void *out_dev,
                          void *cuda_stream);
@@ -248,6 +258,25 @@ typedef struct dint_snapshot dint_snapshot;
 int dint_snapshot_create(dint_engine *e, dint_snapshot **out);
 int dint_snapshot_restore(dint_snapshot *s, void *cuda_stream);
 void dint_snapshot_destroy(dint_snapshot *s);
+
+/*
+ * lock_fasst closed-loop clients ON the GPU.  The reference's clients are Caladan
+ * uthreads on other machines (lock_fasst/caladan/client.cc:183-280, trace shape lock_fasst/caladan/trace_init.sh:9-27);
+ * here n_clients of those state machines live next to the engine, one request outstanding each per round, so committed
+ * txn/s and the abort rate are produced live instead of replayed.  n_keys / zipf_theta / read_pct: the workload family
+ * (reference: 24,000,000 ids, uniform (theta 0), read_pct 80).  Same decisions, draw for draw, as the host-side
+ * clients of dint_b200/csrc/workloads.cc (seed, client id).
+ *   dint_clients_run: `rounds` rounds, asynchronous on cuda_stream.
+ *   dint_clients_stats (synchronises): requests served, committed transactions, validation aborts, lock rejects, rounds.
+ *   dint_clients_peek (test hook, synchronises): the next round's requests / the last round's replies, n_clients * 9 bytes.
+ */
+typedef struct dint_clients dint_clients;
+int dint_clients_create(dint_engine *e, uint32_t n_clients, uint64_t seed, uint32_t n_keys, double zipf_theta, uint32_t read_pct,
+                        dint_clients **out);
+int dint_clients_run(dint_clients *c, uint32_t rounds, void *cuda_stream);
+int dint_clients_stats(dint_clients *c, uint64_t out[5]);
+int dint_clients_peek(dint_clients *c, void *next_req_host, void *last_resp_host);
+void dint_clients_destroy(dint_clients *c);
 
 int dint_get_stats(dint_engine *e, dint_stats *s);
 void dint_reset_stats(dint_engine *e);

@@ -49,3 +49,42 @@ int dint_submit(dint_engine *e, const void *req, uint64_t n, void *resp) {
 }
 void *dint_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void dint_host_free(void *p) { free(p); }
+
+/* ---- dint_cluster_*: lock kinds / store = ONE sequential oracle (what the cluster must equal); tatp / smallbank =
+ * n_gpus oracle shard servers, each fed its records in index order ---- */
+struct dint_cluster { int kind, G; dint_oracle *o[8]; };
+int dint_cluster_create(int kind, const dint_cfg *cfg, int n_gpus, const int *devices, uint64_t max_batch, dint_cluster **out) {
+  (void)devices; (void)max_batch;
+  if (n_gpus < 1 || n_gpus > 8) return DINT_EINVAL;
+  dint_cluster *c = (dint_cluster *)calloc(1, sizeof *c);
+  c->kind = kind;
+  c->G = n_gpus;
+  const int by_dst = kind == DINT_TATP || kind == DINT_SMALLBANK;
+  for (int s = 0; s < (by_dst ? n_gpus : 1); s++) {
+    dint_engine *e = NULL;
+    if (dint_create(kind, cfg, 0, &e) != DINT_OK) return DINT_ENOMEM;
+    c->o[s] = e->o;
+    free(e);
+  }
+  *out = c;
+  return DINT_OK;
+}
+int dint_cluster_populate(dint_cluster *c) {
+  for (int s = 0; s < 8; s++) if (c->o[s]) dint_oracle_populate(c->o[s]);
+  return DINT_OK;
+}
+int dint_cluster_submit(dint_cluster *c, const void *req, uint64_t n, const uint8_t *dst, void *resp) {
+  const uint32_t msg = dint_oracle_msg_size(c->kind);
+  if (!c->o[1]) return dint_oracle_process(c->o[0], req, n, resp) == 0 ? DINT_OK : DINT_EPROTO;
+  int rc = DINT_OK;
+  for (uint64_t i = 0; i < n; i++) {              /* one record at a time keeps every shard's order = index order */
+    const uint8_t s = dst ? dst[i] : 0;
+    if (s >= c->G || dint_oracle_process(c->o[s], (const uint8_t *)req + i * msg, 1, (uint8_t *)resp + i * msg) != 0) rc = DINT_EPROTO;
+  }
+  return rc;
+}
+void dint_cluster_destroy(dint_cluster *c) {
+  if (!c) return;
+  for (int s = 0; s < 8; s++) if (c->o[s]) dint_oracle_destroy(c->o[s]);
+  free(c);
+}

@@ -67,6 +67,27 @@ def test_cluster_answers_like_one_server(kind, G):
                 assert tot == ora.kv_count(0)
 
 
+@pytest.mark.parametrize("G", [2, 8])
+def test_cluster_survives_keys_that_all_hash_to_one_shard(G):
+    """The exchange slabs hold mean + 25 % + 8 sigma records per (source, owner).  A batch whose keys all belong to ONE
+    shard does not fit: the sources flag it, no shard serves that round (nor anything behind it), and the cluster serves
+    it again in rounds that cannot overflow -- the replies must still be ONE sequential server's."""
+    max_batch = 4096
+    rng = np.random.default_rng(3)
+    ora = O.Oracle(wire.FASST)
+    with GpuCluster(wire.FASST, G, devices=[0] * G, max_batch=max_batch) as cl:
+        calls = [T.fasst_random(2 * G * max_batch, 50000, seed=1),          # ordinary traffic
+                 T.fasst_random(3 * G * max_batch + 77, 1, seed=2),         # every record on lock id 0
+                 T.fasst_random(G * max_batch, 2, seed=3),                  # two ids
+                 T.fasst_random(2 * G * max_batch, 50000, seed=4)]          # ordinary traffic again
+        for i, req in enumerate(calls):
+            want = ora.process(req)
+            got = cl.submit(req)
+            d = first_diff(got, want, 9)
+            assert d is None, f"call {i}: {d}"
+        assert cl.overflow_retries() >= 1
+
+
 @pytest.mark.parametrize("kind,n,clients,G", [(wire.TATP, 3000, 1500, 3), (wire.TATP, 2500, 1200, 5),
                                               (wire.SMALLBANK, 5000, 1500, 3), (wire.SMALLBANK, 4000, 1000, 8)])
 def test_cluster_serves_client_chosen_shards(kind, n, clients, G):

@@ -277,6 +277,28 @@ def test_engine_reproduces_reference_golden(name):
     assert G.mismatch(kind, ours, resp) is None, G.mismatch(kind, ours, resp)
 
 
+def test_state_cloned_from_a_reference_server_answers_strictly_bit_exact():
+    """sweep a live reference server with kRead, dint_load what it answered (instead of
+    dint_populate) -- then even the value bytes the reference's populate_* leaves indeterminate are the reference's, and
+    the comparison with the reference binary's replies needs NO tolerance.  The sweep and the replies are the golden
+    fixture recorded from the unmodified tatp server (tools/make_golden.py)."""
+    from dint_b200.wire import Tatp
+    kind, req, resp, cfg = G.load("tatp_sweep_random")
+    assert kind == wire.TATP
+    rq = wire.as_records(kind, req)
+    rs = wire.as_records(kind, resp)
+    n_sweep = len(T.tatp_key_universe(cfg["subs_populate"]))
+    hit = rs["type"][:n_sweep] == Tatp.kGrantRead
+    with Engine(wire.TATP, subs_populate=cfg["subs_populate"], chunk=2048) as eng:      # tables sized as usual, NOT populated
+        for tb in range(5):
+            sel = hit & (rq["table"][:n_sweep] == tb)
+            if sel.any():
+                eng.load(tb, rq["key"][:n_sweep][sel], np.ascontiguousarray(rs["val"][:n_sweep][sel]))
+        got = eng.submit(req)
+        d = first_diff(got, resp, 55)
+        assert d is None, d                                                              # strict: no indeterminate-byte mask
+
+
 # ---------------------------------------------------------------- multi-GPU dispatch kernels (1 GPU) -----
 def _route_case(kind, n, seed=3):
     cfg = {}
@@ -395,35 +417,54 @@ def test_route_owner_partition_unpermute(kind, world):
         assert np.array_equal(back.cpu().numpy(), req)
 
 
-# ---------------------------------------------------------------- the UDP front-end (opt-in until measured) ---
-def test_udp_front_end_serves_the_wire_protocol_bit_exact():
-    """dint_udp_server behind a real socket: one client socket, windows of 64 datagrams (loopback keeps their
-    order), replies must equal ONE sequential reference server's."""
+# ---------------------------------------------------------------- the UDP front-end ---------------------
+def _udp_cases():
+    return [
+        ("lock_2pl", wire.LOCK2PL, lambda: T.lock2pl_random(12000, 2000, seed=22), {}, ()),
+        ("lock_fasst", wire.FASST, lambda: T.fasst_random(20000, 3000, seed=21), {}, ()),
+        ("log_server", wire.LOG, lambda: T.log_random(6000, seed=23), {}, ()),
+        ("store", wire.STORE, lambda: T.store_random(8000, 400, seed=24), dict(subs_populate=400), ("--populate", "400")),
+        ("tatp", wire.TATP, lambda: T.tatp_random(8000, 30, seed=25), dict(subs_populate=30), ("--populate", "30")),
+        ("smallbank", wire.SMALLBANK, lambda: T.smallbank_random(12000, 500, seed=26), dict(accts_populate=500), ("--populate", "500")),
+        # the same server with the key space on several shards (here all resident on GPU 0): owner = slot % 2
+        ("lock_fasst", wire.FASST, lambda: T.fasst_random(20000, 3000, seed=27), {}, ("--gpus", "2", "--devices", "0,0")),
+    ]
+
+
+@pytest.mark.parametrize("name,kind,make,cfg,extra", _udp_cases(), ids=[c[0] + ("+gpus" if "--gpus" in c[4] else "") for c in _udp_cases()])
+def test_udp_front_end_serves_the_wire_protocol_bit_exact(name, kind, make, cfg, extra):
+    """dint_udp_server behind a real socket, every server kind: one client socket, windows of 64 datagrams (loopback
+    keeps their order), replies must equal ONE sequential reference server's."""
     import socket
     import subprocess
     import time
     from dint_b200 import _build
-    req = T.fasst_random(20000, 3000, seed=21)
-    want = O.Oracle(wire.FASST).process(req).reshape(-1, 9)
+    msg = wire.MSG_SIZE[kind]
+    req = make()
+    want = O.Oracle(kind, **cfg).process(req).reshape(-1, msg)
     with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s0:
         s0.bind(("127.0.0.1", 0))
         port = s0.getsockname()[1]
-    srv = subprocess.Popen([_build.UDP_SERVER, "lock_fasst", "--port", str(port), "--bind", "127.0.0.1"], stderr=subprocess.PIPE)
+    srv = subprocess.Popen([_build.UDP_SERVER, name, "--port", str(port), "--bind", "127.0.0.1", *extra], stderr=subprocess.PIPE)
     try:
-        time.sleep(8.0)                                   # CUDA context + tables
-        assert srv.poll() is None, srv.stderr.read()
+        os.set_blocking(srv.stderr.fileno(), False)
+        banner, t0 = b"", time.time()
+        while b"sockets, batches" not in banner:           # printed once the engine exists and the sockets are bound
+            assert srv.poll() is None and time.time() - t0 < 120, banner
+            time.sleep(0.1)
+            banner += srv.stderr.read() or b""
         c = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
         c.settimeout(5.0)
         c.connect(("127.0.0.1", port))
-        rec = np.ascontiguousarray(req).view(np.uint8).reshape(-1, 9)
+        rec = np.ascontiguousarray(req).view(np.uint8).reshape(-1, msg)
         got = np.empty_like(rec)
         for lo in range(0, len(rec), 64):
             hi = min(lo + 64, len(rec))
             for i in range(lo, hi):
                 c.send(rec[i].tobytes())
             for i in range(lo, hi):
-                got[i] = np.frombuffer(c.recv(64), dtype=np.uint8)
-        assert np.array_equal(got, want)
+                got[i] = np.frombuffer(c.recv(256), dtype=np.uint8)
+        assert first_diff(got, want, msg) is None, first_diff(got, want, msg)
     finally:
         srv.terminate()
         srv.wait(timeout=20)

@@ -88,3 +88,65 @@ def test_front_end_refuses_bad_arguments(stub_dir):
     env = dict(os.environ, LD_LIBRARY_PATH=stub_dir)
     assert subprocess.run([_build.UDP_SERVER, "lock_fasst", "--bind", "not.an.address"], env=env, capture_output=True).returncode == 2
     assert subprocess.run([_build.UDP_SERVER, "lock_fasst", "--frobnicate", "1"], env=env, capture_output=True).returncode == 2
+
+
+def test_front_end_answers_the_caladan_control_handshake(stub_dir):
+    """lock_2pl/caladan/client_caladan.cc:248-271: `net_req{int nports}` on the well-known port -> `net_resp{int nports;
+    uint16_t ports[]}`; the data then flows on the fresh ports and is served exactly like the well-known one."""
+    import struct
+    req = T.fasst_random(3000, 40, seed=41)
+    rec = np.ascontiguousarray(req).view(np.uint8).reshape(-1, 9)
+    want = O.Oracle(wire.FASST).process(req).reshape(-1, 9)
+    srv, port = _serve(stub_dir, "lock_fasst", ("--batch", "64", "--sockets", "2"))
+    try:
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as ctl:
+            ctl.settimeout(5.0)
+            ctl.sendto(struct.pack("<i", 3), ("127.0.0.1", port))
+            resp = ctl.recv(256)
+        nports, = struct.unpack_from("<i", resp)
+        ports = struct.unpack_from("<3H", resp, 4)
+        assert nports == 3 and len(resp) == 4 + 2 * 3 and all(p not in (0, port) for p in ports) and len(set(ports)) == 3
+        socks = [socket.socket(socket.AF_INET, socket.SOCK_DGRAM) for _ in ports]
+        got = np.zeros_like(rec)
+        for s, p in zip(socks, ports):
+            s.settimeout(5.0)
+            s.connect(("127.0.0.1", p))
+        for lo in range(0, len(rec), 32):                  # one window at a time, data ports in turn: a fixed global order
+            s = socks[(lo // 32) % 3]
+            for i in range(lo, min(lo + 32, len(rec))):
+                s.send(rec[i].tobytes())
+            for i in range(lo, min(lo + 32, len(rec))):
+                got[i] = np.frombuffer(s.recv(256), dtype=np.uint8)
+        assert np.array_equal(got, want)
+    finally:
+        log = _stop(srv)
+    assert " 1 control requests" in log, log
+
+
+def test_front_end_serves_one_port_per_shard_with_gpus(stub_dir):
+    """--gpus 3, smallbank: shard i listens on port + i; the port a datagram arrives on is the shard the client chose
+    (smallbank/caladan/client_udp_shard.cc: primary / backups / log have their own addresses)."""
+    n, accts = 3000, 300
+    req = T.smallbank_random(n, accts, seed=43)
+    rec = np.ascontiguousarray(req).view(np.uint8).reshape(-1, 23)
+    rng = np.random.default_rng(5)
+    dst = rng.integers(0, 3, size=n)
+    oras = [O.Oracle(wire.SMALLBANK, accts_populate=accts) for _ in range(3)]
+    want = np.zeros_like(rec)
+    for i in range(n):
+        want[i] = oras[dst[i]].process(rec[i].copy()).reshape(-1)
+    srv, port = _serve(stub_dir, "smallbank", ("--gpus", "3", "--sockets", "1", "--batch", "50"))
+    try:
+        socks = []
+        for g in range(3):
+            s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+            s.settimeout(5.0)
+            s.connect(("127.0.0.1", port + g))
+            socks.append(s)
+        got = np.zeros_like(rec)
+        for i in range(n):                                  # strictly one at a time: the global order is the index order
+            socks[dst[i]].send(rec[i].tobytes())
+            got[i] = np.frombuffer(socks[dst[i]].recv(256), dtype=np.uint8)
+        assert np.array_equal(got, want)
+    finally:
+        _stop(srv)

@@ -16,7 +16,7 @@ if "--store" in sys.argv:
 if "--hot" in sys.argv:
     probe(wire.FASST, T.fasst_random(n, 4800, seed=1), chunk=1 << 20)
     probe(wire.LOCK2PL, T.lock2pl_random(n, 4800, seed=2), chunk=1 << 20)
-if "--route" in sys.argv:
+if "--route" in sys.argv:   # dispatch / combine kernels alone
     # dispatch / combine kernels alone, local slabs (no NVLink): 2^20 lock_fasst records
     from dint_b200.engine import Engine as E_
     m = 1 << 20
