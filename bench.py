@@ -646,7 +646,7 @@ def run_udp_front_end(seconds=4.0):
         s0.bind(("127.0.0.1", 0))
         port = s0.getsockname()[1]
     cores = os.cpu_count() or 8
-    n_sock = max(8, min(32, cores // 4))
+    n_sock = 8                                    # the reference's own thread count (exp/run_lock_fasst.sh: `server 8`)
     with tempfile.TemporaryDirectory() as td:
         tp = os.path.join(td, "trace.bin")
         wire.as_bytes(rec).tofile(tp)

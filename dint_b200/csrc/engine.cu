@@ -87,7 +87,8 @@ struct dint_engine {
   uint32_t route_tiles = 0;
   uint32_t* d_route2 = nullptr;              // dispatch scratch: counters, totals, look-back descriptors
   uint32_t route_desc_tiles = 0, route_seq = 0;
-  int grid_route = 148 * 4;                  // CTAs of k_route_dispatch (tiles are drawn by ticket: any grid works)
+  int grid_route = 148 * 4;                  // CTAs of k_route_dispatch: 4 per SM are resident (64 registers x 256 threads); 2^20 small
+                                             // records = 512 tiles = ONE wave (tiles are drawn by ticket, so any grid is correct)
   // L2 persistence: the flag sets (+ lock_fasst lock bits) live in one arena that every launch maps
   // with a persisting access-policy window, so the streaming request/reply traffic cannot evict it
   uint8_t* hot_arena = nullptr;
@@ -346,8 +347,7 @@ static int kv_maintain(dint_engine* e, cudaStream_t s) {
 }
 static int kv_publish_counts(dint_engine* e, cudaStream_t s) {
   if (e->ctx.n_tables == 0 || !e->h_kvcnt) return DINT_OK;
-  for (uint32_t t = 0; t < e->ctx.n_tables; t++)
-    CU(cudaMemcpyAsync(e->h_kvcnt + 2 * t, e->ctx.tbl[t].live, 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(e->h_kvcnt, e->ctx.tbl[0].live, 16 * e->ctx.n_tables, cudaMemcpyDeviceToHost, s));   // (the tables' counters are contiguous)
   CU(cudaEventRecord(e->ev_kvcnt, s));
   return DINT_OK;
 }
@@ -430,19 +430,20 @@ static int route_dispatch_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) 
   if (!e->d_route2 || a.n_tiles > e->route_desc_tiles) {
     if (e->d_route2) { CU(cudaStreamSynchronize(s)); CU(cudaFree(e->d_route2)); e->d_route2 = nullptr; }
     e->route_desc_tiles = a.n_tiles + a.n_tiles / 2 + 64;
-    const size_t bytes = 64 + (size_t)e->route_desc_tiles * 4 * sizeof(unsigned long long);
+    const size_t bytes = 64 + (size_t)(e->route_desc_tiles + e->route_desc_tiles / 32 + 1) * 4 * sizeof(unsigned long long);
     CU(cudaMalloc(&e->d_route2, bytes));
     CU(cudaMemsetAsync(e->d_route2, 0, bytes, s));
     e->route_seq = 0;
   }
   e->route_seq = e->route_seq % 255u + 1u;              // 1..255; when the number wraps every descriptor is cleared, so a word
   if (e->route_seq == 1)                                 // left by an earlier launch can never carry the current number
-    CU(cudaMemsetAsync(e->d_route2, 0, 64 + (size_t)e->route_desc_tiles * 4 * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(e->d_route2, 0, 64 + (size_t)(e->route_desc_tiles + e->route_desc_tiles / 32 + 1) * 4 * sizeof(unsigned long long), s));
   RouteArgs b = a;
   b.done = e->d_route2;
   b.ticket = e->d_route2 + 1;
   b.totals = e->d_route2 + 4;
   b.desc = (unsigned long long*)(e->d_route2 + 16);
+  b.gdesc = b.desc + (size_t)e->route_desc_tiles * 4;
   b.seq = e->route_seq;
   if (CUDART_VERSION >= 11000 && RT::SMEM > 48 * 1024) CU(cudaFuncSetAttribute(k_route_dispatch<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT::SMEM));
   int grid = (int)b.n_tiles < e->grid_route ? (int)b.n_tiles : e->grid_route;
@@ -455,12 +456,12 @@ template <int MSG>
 static int route_combine_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) {
   using RT = RTile<MSG>;
   int grid = (int)a.n_tiles;
-  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid > 148 * 4) grid = 148 * 4;
   k_route_combine<MSG><<<grid, kThreads, RT::SMEM, s>>>(a);
   CU(cudaGetLastError());
   return DINT_OK;
 }
-static uint32_t route_tile_records(const dint_engine* e) { return e->msg <= 12 ? kThreads * 4u : (uint32_t)kThreads; }
+static uint32_t route_tile_records(const dint_engine* e) { return e->msg <= 12 ? kThreads * 8u : (uint32_t)kThreads; }
 
 // ======================================================================================================
 extern "C" {
@@ -626,7 +627,6 @@ static int create_impl(dint_engine* e) {
   if ((rc = dalloc(e, &c.log_total, 2))) return rc;
   if ((rc = dalloc(e, &c.counters, 4))) return rc;
   if ((rc = dalloc(e, &c.gbar, 4))) return rc;
-  if ((rc = dalloc(e, &c.tickets, 4))) return rc;
 
   switch (e->kind) {
     case DINT_LOCK2PL: rc = grids_for<K_LOCK2PL, false>(e); break;
@@ -1199,6 +1199,7 @@ static int shard_make(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
   dint_shard_ctx* c = new dint_shard_ctx();
   e->plain_launches = true;
   c->e = e; c->W = n_shards; c->me = rank; c->cap = cap; c->S = n_sets; c->max_n = max_n; c->one_stream = one_stream;
+  { const char* os = getenv("DINT_SHARD_ONE_STREAM"); if (os && atoi(os) != 0) c->one_stream = true; }   // development A/B only
   for (uint32_t s = 0; s < n_sets; s++)
     for (uint32_t o = 0; o < n_shards; o++) {
       c->inbox[s][o] = inbox_sets[s].p[o];
@@ -1210,7 +1211,7 @@ static int shard_make(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
   }
   c->my_req = (uint32_t*)sig_blocks->p[rank];
   c->my_rsp = (uint32_t*)(sig_blocks->p[rank] + 128);
-  if (!one_stream) {
+  if (!c->one_stream) {
     CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->ret, cudaStreamNonBlocking));
   }
@@ -1488,7 +1489,6 @@ int dint_shard_recover(dint_shard_ctx* c, uint32_t k_last, uint32_t* first_unser
   e->ord_pending = false;
   e->prev_n = 0;
   CU(cudaMemset(e->d_nc, 0, 8 * sizeof(uint32_t)));
-  CU(cudaMemset(e->ctx.tickets, 0, 4 * sizeof(uint32_t)));
   CU(cudaMemset(e->d_flags[0], 0, (size_t)((char*)e->d_flags[1] - (char*)e->d_flags[0]) * 2));
   CU(cudaDeviceSynchronize());
   return DINT_OK;

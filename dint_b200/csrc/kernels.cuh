@@ -57,31 +57,24 @@ template <int MSG> struct Stage {
   static constexpr uint32_t N = (BYTES > 8192) ? 2 : kStages;
 };
 
-// Persistent-CTA tile pipeline with DYNAMIC tile assignment.  Tiles are handed out by a global ticket counter: a
-// statically striped persistent grid loses a whole wave whenever some of its CTAs cannot be resident next to another
-// stream's kernel (the multi-GPU step: dispatch / combine of the neighbouring batches; the host path: nothing, but
-// the copies' completion kernels), with tickets the CTAs that ARE resident simply take more tiles.  Thread 0 draws:
-// the first kStages tickets with one atomic at kernel start, afterwards one ticket per tile ONE ITERATION AHEAD of
-// its use (the atomic's round trip, ~0.7 us, hides behind a tile's work: drawing at the point of use measured
-// +17 % on K1 + K2).  The tile id of every pipeline stage is published in a shared-memory ring; the CTA barriers of
-// the tile loop make it visible one iteration before it is used.
-constexpr uint32_t kNoTile = 0xffffffffu;
+// Persistent-CTA tile pipeline: CTA b owns tiles b, b + gridDim.x, ...; thread 0 keeps kStages - 1 TMA bulk loads in
+// flight ahead of the tile being processed.  (Dynamic assignment by a ticket counter was built and measured in round 2,
+// profiles/r02_variants.md: +17 % with the ticket drawn at the point of use, +5-7 % with the draw one iteration ahead,
+// and NO gain inside the multi-GPU step it was meant for -- 145.7 vs 144.5 us per batch at N = 2 -- because the kernels
+// of the step compete for the memory system, not for SM slots.  Dropped.)
 struct TileIter {
-  uint32_t n_tiles, ns;
-  uint32_t* ctr;        // global ticket counter of this kernel (reset by the OTHER kernel of the K1 / K2 pair)
-  uint32_t* ring;       // shared memory, [ns]: tile id held by each pipeline stage, kNoTile = no more tiles
-  uint32_t pending;     // thread 0: the next ticket, already drawn
-  DINT_D uint32_t tile(uint32_t i) const { return ring[i % ns]; }
-  DINT_D bool has(uint32_t i) const { return ring[i % ns] != kNoTile; }
+  uint32_t n_my;        // tiles owned by this CTA
+  DINT_D uint32_t tile(uint32_t i) const { return blockIdx.x + i * gridDim.x; }
+  DINT_D bool has(uint32_t i) const { return i < n_my; }
 };
-// thread 0: stage i takes the pending ticket (and the next one is drawn, to be used one iteration later)
+DINT_D TileIter tile_iter(uint32_t n_tiles) {
+  TileIter it;
+  it.n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  return it;
+}
 template <int MSG>
-DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, TileIter& it, uint32_t i) {
-  const uint32_t t = it.pending < it.n_tiles ? it.pending : kNoTile;
-  it.ring[i % it.ns] = t;
-  if (t == kNoTile) return;                              // (the counter only grows: no need to draw again)
-  it.pending = atomicAdd(it.ctr, 1u);
-  const uint32_t first = t * kTile;
+DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, const TileIter& it, uint32_t i) {
+  const uint32_t t = it.tile(i), first = t * kTile;
   const uint32_t cnt = min((uint32_t)kTile, c.n - first);
   const uint32_t body = (cnt * MSG) & ~15u;
   const uint32_t buf = i % Stage<MSG>::N;
@@ -89,25 +82,6 @@ DINT_D void issue_tile_load(const Ctx& c, uint8_t* smem, uint64_t* full, TileIte
     mbar_expect_tx(&full[buf], body);
     tma_load_1d(smem + buf * Stage<MSG>::BYTES, c.req + (size_t)first * MSG, body, &full[buf]);
   }
-}
-// thread 0, once per kernel: the first NS stages with ONE atomic (NS + 1 consecutive tickets: NS used now, one pending)
-template <int MSG>
-DINT_D void issue_first_tiles(const Ctx& c, uint8_t* smem, uint64_t* full, TileIter& it, uint32_t NS) {
-  uint32_t t0 = kNoTile;
-  if (it.n_tiles) t0 = atomicAdd(it.ctr, NS + 1);        // (a flush launch has no tiles and must not touch the counter)
-  for (uint32_t i = 0; i < NS; i++) {
-    const uint32_t t = (t0 != kNoTile && t0 + i < it.n_tiles) ? t0 + i : kNoTile;
-    it.ring[i % it.ns] = t;
-    if (t == kNoTile) continue;
-    const uint32_t first = t * kTile;
-    const uint32_t cnt = min((uint32_t)kTile, c.n - first);
-    const uint32_t body = (cnt * MSG) & ~15u;
-    if (body) {
-      mbar_expect_tx(&full[i], body);
-      tma_load_1d(smem + i * Stage<MSG>::BYTES, c.req + (size_t)first * MSG, body, &full[i]);
-    }
-  }
-  it.pending = (t0 != kNoTile) ? t0 + NS : kNoTile;
 }
 // all threads: wait for tile i's bulk load, fetch the (<16-byte) tail of the very last tile by hand
 template <int MSG>
@@ -278,13 +252,12 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[kStages];
   __shared__ uint32_t scratch[kTile / 32];
-  __shared__ uint32_t s_ring[kStages];
   if (c.skip && __ldcg(c.skip)) return;                  // the multi-GPU step is draining after a slab overflow (k_p2p_wait)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
     // [2] (a writer exists) is OR-ed by any CTA of this launch, so it is cleared one launch early: each K1
     // clears the slot of the chunk it replays, which is the slot the NEXT chunk will use
-    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; c.nc_ord[2] = 0; c.tickets[1] = 0; }   // (K2 is not running: its ticket counter is reset here)
+    if (blockIdx.x == 0) { c.nc_cur[0] = 0; c.nc_cur[1] = 0; c.nc_ord[2] = 0; }
   }
   __syncthreads();
   // The previous chunk's listed requests are replayed by this launch too (their buckets were filled by its
@@ -296,9 +269,9 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
     ordered_buckets<KIND>(c, smem);
     __syncthreads();
   }
-  TileIter it{c.n_tiles, NS, &c.tickets[0], s_ring, kNoTile};
-  if (threadIdx.x == 0) issue_first_tiles<W::MSG>(c, smem, full, it, NS);
-  __syncthreads();
+  const TileIter it = tile_iter(c.n_tiles);
+  if (threadIdx.x == 0)
+    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
 
   // retire the previous chunk's flags: every word it touched is zeroed (all of that set's nibbles
   // were written by that chunk, so whole-word stores are exact).  Loads are batched four deep so that
@@ -323,7 +296,7 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   bool saw_writer = false;          // any request of this CTA's tiles that writes A or L
   for (uint32_t i = 0; it.has(i); i++) {
     // the stage that held tile i-1 is free (barrier at the end of iteration i-1): refill it now
-    if (threadIdx.x == 0 && i) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
+    if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);
     uint32_t first, cnt;
     const uint8_t* tile = acquire_tile<W::MSG>(c, smem, full, it, i, first, cnt);
     const bool valid = threadIdx.x < cnt;
@@ -423,16 +396,13 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
   // lock servers: the group id K1 stored is all K2 needs of the key -- fetch it (coalesced, independent of
   // the TMA stage) instead of re-hashing; KV servers need the hash itself to find the table entry
   constexpr bool kGrpFromK1 = (KIND == K_LOCK2PL || KIND == K_FASST);
-  __shared__ uint32_t s_ring[kStages];
   if (c.skip && __ldcg(c.skip)) return;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0)
     for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
-    if (blockIdx.x == 0) c.tickets[0] = 0;               // K1 is not running: its ticket counter is reset here
-  }
   __syncthreads();
-  TileIter it{c.n_tiles, NS, &c.tickets[1], s_ring, kNoTile};
-  if (threadIdx.x == 0) issue_first_tiles<W::MSG>(c, smem, full, it, NS);
-  __syncthreads();
+  const TileIter it = tile_iter(c.n_tiles);
+  if (threadIdx.x == 0)
+    for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
   const bool chunk_has_writer = c.nc_cur[2] != 0;      // set by K1; false = nothing in this chunk can conflict
 
   for (uint32_t i = 0; it.has(i); i++) {
@@ -442,7 +412,7 @@ __global__ void __launch_bounds__(kTile) k_apply(const Ctx c) {
       const uint32_t idx = it.tile(i) * kTile + threadIdx.x;
       if (idx < c.n) g_k1 = __ldcg(&c.grp[idx]);
     }
-    if (threadIdx.x == 0 && i) {
+    if (threadIdx.x == 0 && i && i + NS - 1 < it.n_my) {
       // the stage that held tile i-1 is refilled as soon as its bulk store has finished READING it
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       issue_tile_load<W::MSG>(c, smem, full, it, i + NS - 1);

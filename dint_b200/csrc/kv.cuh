@@ -497,9 +497,12 @@ int kv_create_tables(int kind, const dint_cfg& cf, Ctx& c, KvHost* kv, uint64_t*
     int rc = alloc(&p, (size_t)(1ULL << lg) << T.ent_shift);
     if (rc) return rc;
     T.entries = (uint8_t*)p;
-    rc = alloc(&p, 16);
-    if (rc) return rc;
-    T.live = (unsigned long long*)p;
+    if (t == 0) {                                    // {live, used} of every table side by side: one copy publishes them all
+      rc = alloc(&p, 16 * kMaxTables);
+      if (rc) return rc;
+      c.tbl[0].live = (unsigned long long*)p;
+    }
+    T.live = c.tbl[0].live + 2 * t;
     kv[t].capacity = 1ULL << lg;
     kv[t].hash_size = hs[t];
   }

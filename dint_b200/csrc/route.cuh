@@ -1,12 +1,13 @@
 // Multi-GPU dispatch / combine: stable partition of a batch of wire records by owner shard, written straight
 // into fixed-capacity slabs (local memory, or the owners' receive buffers over NVLink), and its inverse.
 //
-//   k_route_dispatch  ONE launch, ONE pass over the batch.  Tiles (1024 records; 256 for the 53/55-byte kinds) are
+//   k_route_dispatch  ONE launch, ONE pass over the batch.  Tiles (2048 records; 256 for the 23/53/55-byte kinds) are
 //            handed out in index order by a ticket counter.  Per tile: owner shard of every record (hash of the key,
 //            the slot ONE server would compute, modulo the shard count -- or the client-chosen shard), the tile's
-//            per-shard counts, and the first slot of the tile's run in every slab from a DECOUPLED LOOK-BACK over
-//            the preceding tiles' published counts (single-pass prefix sum: a tile publishes its aggregate at once,
-//            then walks back until it meets a tile whose inclusive prefix is known).  The tile is partitioned in
+//            per-shard counts, and the first slot of the tile's run in every slab from a two-level LOOK-BACK over
+//            the preceding tiles' published counts (single-pass prefix sum: a tile publishes its counts at once, sums
+//            those of the tiles before it in its group of 32 and those of the groups before its own -- two windows of
+//            32 loads, never a wait for somebody else's prefix).  The tile is partitioned in
 //            shared memory into one run per shard, each run placed at the alignment of its destination so that it
 //            leaves with 16-byte stores.  Slots past a slab's total become padding records; the last CTA to finish
 //            raises the epoch flags of the peers (release, system scope) when the slabs live in peer memory.
@@ -22,7 +23,10 @@
 
 namespace dint {
 template <int MSG> struct RTile {
-  static constexpr int PER = MSG <= 12 ? 4 : 1;                  // records per thread
+  // records per thread.  Small records: 8, i.e. 2048-record tiles, so that a batch of 2^20 records is 512 tiles = ONE wave
+  // of the 4 CTAs per SM the kernels' 64 registers allow (with 1024-record tiles half of the CTAs had to take a second
+  // tile after the first: the dispatch is a chain of latencies per tile, and its time was two chains)
+  static constexpr int PER = MSG <= 12 ? 8 : 1;
   static constexpr int RECS = kThreads * PER;                    // records per tile
   static constexpr int BYTES = RECS * MSG;                       // a multiple of 16
   static constexpr int RUNS = BYTES + 16 * kMaxShards + 16;      // the partitioned copy: alignment gaps between runs
@@ -34,7 +38,8 @@ struct RouteArgs {
   const uint8_t* owner_in;   // dispatch: client-chosen shard per record, or nullptr = computed from the keys
   uint8_t* owner;            // [n] owner byte per record (dispatch writes, combine reads); 0xff = undeliverable
   uint32_t* tilebase;        // [n_tiles][kMaxShards] first slot of each tile's run in each slab
-  unsigned long long* desc;  // dispatch scratch [n_tiles][4]: look-back descriptors, self-validating words tagged with `seq`
+  unsigned long long* desc;  // dispatch scratch [n_tiles][4]: per-tile counts, self-validating words tagged with `seq`
+  unsigned long long* gdesc; // dispatch scratch [n_tiles / 32][4]: the same per group of 32 tiles
   uint32_t* totals;          // dispatch scratch [kMaxShards + 1]: per-shard totals of this launch, [8] = seq once they are valid
   uint32_t* ticket;          // dispatch scratch: tile ticket counter, zero between launches
   uint32_t* done;            // dispatch scratch: finished-CTA counter, zero between launches
@@ -46,7 +51,7 @@ struct RouteArgs {
   PeerPtrs sig;              // dispatch: epoch word array of shard o (word `me` is written); 0 = no signalling
 };
 
-// eight 16-bit counters (one per shard); a tile holds at most 1024 records, so fields never carry
+// eight 16-bit counters (one per shard); a tile holds at most 2048 records, so fields never carry
 struct Cnt8 { uint64_t lo, hi; };
 DINT_D Cnt8 operator+(Cnt8 a, Cnt8 b) { return Cnt8{a.lo + b.lo, a.hi + b.hi}; }
 DINT_D Cnt8 operator-(Cnt8 a, Cnt8 b) { return Cnt8{a.lo - b.lo, a.hi - b.hi}; }
@@ -119,10 +124,10 @@ template <int PER>
 DINT_D Cnt8 load_owners(const RouteArgs& a, uint32_t t, uint32_t (&own)[PER]) {
   const uint32_t i0 = (t * kThreads + threadIdx.x) * PER;
   Cnt8 mine{0, 0};
-  if (PER == 4 && i0 + 3 < a.n) {
-    const uint32_t w = *(const uint32_t*)(a.owner + i0);
+  if (PER == 8 && i0 + 7 < a.n) {
+    const uint2 w = *(const uint2*)(a.owner + i0);
 #pragma unroll
-    for (int j = 0; j < PER; j++) own[j] = (w >> (8 * j)) & 0xffu;
+    for (int j = 0; j < PER; j++) own[j] = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xffu;
   } else {
 #pragma unroll
     for (int j = 0; j < PER; j++) own[j] = i0 + j < a.n ? a.owner[i0 + j] : 0xffu;
@@ -150,7 +155,7 @@ DINT_D void lb_store(unsigned long long* p, unsigned long long v) {
 
 // dispatch: owner bytes, stable partition into the slabs, padding, epoch flags -- one launch, one pass
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) k_route_dispatch(const Ctx c, const RouteArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_route_dispatch(const Ctx c, const RouteArgs a) {
   using W = Wire<KIND>;
   using RT = RTile<W::MSG>;
   constexpr int MSG = W::MSG, PER = RT::PER;
@@ -191,8 +196,9 @@ __global__ void __launch_bounds__(kThreads) k_route_dispatch(const Ctx c, const 
       own[j] = o;
       if (o < a.world) cnt8_inc(mine, o);
     }
-    if (PER == 4 && r0 + 3 < nrec) {
-      *(uint32_t*)(a.owner + first + r0) = own[0] | (own[1 % PER] << 8) | (own[2 % PER] << 16) | (own[3 % PER] << 24);
+    if (PER == 8 && r0 + 7 < nrec) {
+      *(uint2*)(a.owner + first + r0) = make_uint2(own[0] | (own[1 % PER] << 8) | (own[2 % PER] << 16) | (own[3 % PER] << 24),
+                                                   own[4 % PER] | (own[5 % PER] << 8) | (own[6 % PER] << 16) | (own[7 % PER] << 24));
     } else {
 #pragma unroll
       for (int j = 0; j < PER; j++)
@@ -200,30 +206,48 @@ __global__ void __launch_bounds__(kThreads) k_route_dispatch(const Ctx c, const 
     }
     Cnt8 excl, total;
     block_scan_cnt8(mine, excl, total, s_w);
-    // ---- decoupled look-back: lanes 0..3 of warp 0 own one descriptor word each (two shards per word) ----
-    if (threadIdx.x < 4) {
-      const uint32_t k = threadIdx.x;
+    // ---- two-level look-back over published COUNTS (nothing ever waits for a prefix, so all tiles of a wave finish
+    //      together): warp k (< 4) owns descriptor word k (two shards per word).  (1) the tiles before t inside its group of
+    //      32 -- one window; (2) the last tile of a group publishes the group's counts; (3) the groups before t's -- one
+    //      window per 32 groups.  Every word validates itself (launch number + "present" bit). ----
+    if (warp_id() < 4) {
+      const uint32_t k = warp_id(), lane = lane_id();
       const uint32_t c0 = cnt8_get(total, 2 * k), c1 = cnt8_get(total, 2 * k + 1);
-      unsigned long long* mydesc = a.desc + (size_t)t * 4 + k;
-      uint32_t e0 = 0, e1 = 0;
-      if (t == 0) {
-        lb_store(mydesc, lb_pack(a.seq, 2, c0, c1));
-      } else {
-        lb_store(mydesc, lb_pack(a.seq, 1, c0, c1));
-        for (uint32_t p = t; p-- > 0;) {
-          unsigned long long v;
-          do { v = lb_load(a.desc + (size_t)p * 4 + k); } while ((uint32_t)(v >> 56) != a.seq || ((v >> 54) & 3u) == 0);
-          e0 += (uint32_t)v & 0x7ffffffu;
-          e1 += (uint32_t)(v >> 27) & 0x7ffffffu;
-          if (((v >> 54) & 3u) == 2) break;
-        }
-        lb_store(mydesc, lb_pack(a.seq, 2, e0 + c0, e1 + c1));
+      const uint32_t g = t >> 5, j = t & 31u;
+      if (lane == 0) lb_store(a.desc + (size_t)t * 4 + k, lb_pack(a.seq, 1, c0, c1));
+      uint32_t x0 = 0, x1 = 0;
+      if (lane < j) {                                    // (1) tiles g*32 .. t-1
+        const unsigned long long* p = a.desc + (size_t)(g * 32 + lane) * 4 + k;
+        unsigned long long v;
+        do { v = lb_load(p); } while ((uint32_t)(v >> 56) != a.seq || ((v >> 54) & 3u) == 0);
+        x0 = (uint32_t)v & 0x7ffffffu;
+        x1 = (uint32_t)(v >> 27) & 0x7ffffffu;
       }
-      s_base[2 * k] = e0;
-      s_base[2 * k + 1] = e1;
-      if (t == a.n_tiles - 1) {                          // the slabs' totals, for the padding and the overflow count
-        a.totals[2 * k] = e0 + c0;
-        a.totals[2 * k + 1] = e1 + c1;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) { x0 += __shfl_xor_sync(0xffffffffu, x0, d); x1 += __shfl_xor_sync(0xffffffffu, x1, d); }
+      if (j == 31 && lane == 0) lb_store(a.gdesc + (size_t)g * 4 + k, lb_pack(a.seq, 1, x0 + c0, x1 + c1));   // (2)
+      uint32_t e0 = x0, e1 = x1;
+      for (uint32_t base = 0; base < g; base += 32) {    // (3) groups 0 .. g-1
+        uint32_t y0 = 0, y1 = 0;
+        if (base + lane < g) {
+          const unsigned long long* p = a.gdesc + (size_t)(base + lane) * 4 + k;
+          unsigned long long v;
+          do { v = lb_load(p); } while ((uint32_t)(v >> 56) != a.seq || ((v >> 54) & 3u) == 0);
+          y0 = (uint32_t)v & 0x7ffffffu;
+          y1 = (uint32_t)(v >> 27) & 0x7ffffffu;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { y0 += __shfl_xor_sync(0xffffffffu, y0, d); y1 += __shfl_xor_sync(0xffffffffu, y1, d); }
+        e0 += y0;
+        e1 += y1;
+      }
+      if (lane == 0) {
+        s_base[2 * k] = e0;
+        s_base[2 * k + 1] = e1;
+        if (t == a.n_tiles - 1) {                        // the slabs' totals, for the padding and the overflow count
+          a.totals[2 * k] = e0 + c0;
+          a.totals[2 * k + 1] = e1 + c1;
+        }
       }
     }
     __syncthreads();
@@ -309,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) k_route_dispatch(const Ctx c, const 
 
 // combine: the replies of tile t are one contiguous run per shard in the reply slabs; put them back in order
 template <int MSG>
-__global__ void __launch_bounds__(kThreads) k_route_combine(const RouteArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_route_combine(const RouteArgs a) {
   using RT = RTile<MSG>;
   constexpr int PER = RT::PER;
   extern __shared__ __align__(128) uint8_t smem[];
