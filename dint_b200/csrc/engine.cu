@@ -178,6 +178,7 @@ static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
     int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kTile - 1) / (4 * kTile));
     if (clr > want) want = clr;
     int grid = (want < e->grid_classify && !c.ord_pending) ? want : e->grid_classify;
+    if (c.n == 0 && e->sms > 0 && grid > 8 * e->sms) grid = 8 * e->sms;     // a flush launch only replays: 32 warps per SM are plenty
     CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, kTile, e->smem_classify, s, false, c));
   }
   if (c.n == 0) { CU(cudaGetLastError()); return DINT_OK; }
@@ -297,10 +298,11 @@ static int flush_ordered(dint_engine* e, cudaStream_t s) {
   c.req = nullptr;
   c.resp = nullptr;
   fill_chunk_ctx(e, c);
+  c.prev_n = 0;                  // replay only: that chunk's flags are retired by the NEXT chunk's K1 as usual (next to its tile
+                                 // loads), not by this launch, which a caller is waiting for
   int rc = launch_chunk(e, c, s);
   if (rc) return rc;
   e->ord_pending = false;
-  e->prev_n = 0;                 // the flush also cleared that chunk's flags
   return DINT_OK;
 }
 
@@ -1199,7 +1201,6 @@ static int shard_make(dint_engine* e, uint32_t n_shards, uint32_t rank, uint32_t
   dint_shard_ctx* c = new dint_shard_ctx();
   e->plain_launches = true;
   c->e = e; c->W = n_shards; c->me = rank; c->cap = cap; c->S = n_sets; c->max_n = max_n; c->one_stream = one_stream;
-  { const char* os = getenv("DINT_SHARD_ONE_STREAM"); if (os && atoi(os) != 0) c->one_stream = true; }   // development A/B only
   for (uint32_t s = 0; s < n_sets; s++)
     for (uint32_t o = 0; o < n_shards; o++) {
       c->inbox[s][o] = inbox_sets[s].p[o];

@@ -30,11 +30,17 @@
 //
 // usage: dint_udp_server <lock_2pl|lock_fasst|log_server|store|tatp|smallbank> [--port P] [--bind A.B.C.D]
 //                        [--sockets R] [--batch N] [--device D] [--gpus G [--devices a,b,..]] [--shard-id I --shards G]
-//                        [--linger-us U] [--populate N]
+//                        [--linger-us U] [--populate N] [--mon-port 20231]
+//
+// --mon-port P: the reference servers' utilisation channel (tatp/udp/server_shard.cc:213-274: a thread samples the CPU
+// time of the server's cores once a second, another answers any datagram on UDP :20231 with `struct {double ucores;
+// double kcores;}`).  Here the two doubles are the user / kernel CPU cores this process used over the last second
+// (getrusage) -- with the handler on the GPU that is what the host still spends on the sockets.
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <poll.h>
 #include <signal.h>
+#include <sys/resource.h>
 #include <sys/socket.h>
 #include <unistd.h>
 
@@ -105,7 +111,7 @@ int main(int argc, char** argv) {
   }
   const int kind = kind_of(argv[1]);
   if (kind < 0) { fprintf(stderr, "unknown server kind '%s'\n", argv[1]); return 2; }
-  int port = 20230, device = 0, linger_us = 50, gpus = 1, populate = -1;
+  int port = 20230, device = 0, linger_us = 50, gpus = 1, populate = -1, mon_port = 0;
   unsigned batch_max = 16384, shards = 1, shard_id = 0;
   unsigned n_sock = std::thread::hardware_concurrency() / 2;
   if (n_sock < 1) n_sock = 1;
@@ -126,6 +132,7 @@ int main(int argc, char** argv) {
     else if (a == "--shard-id") shard_id = (unsigned)atoi(v);
     else if (a == "--linger-us") linger_us = atoi(v);
     else if (a == "--populate") populate = atoi(v);
+    else if (a == "--mon-port") mon_port = atoi(v);
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
   if (batch_max < 1) batch_max = 1;
@@ -302,6 +309,47 @@ int main(int argc, char** argv) {
     for (auto& x : w) x->th = std::thread(socket_thread, std::ref(*x));
   }
 
+  // ---- utilisation channel (cpu_mon_func + cpu_mon_handler of the reference) ----
+  std::atomic<double> ucores{0.0}, kcores{0.0};
+  std::thread mon_sampler, mon_server;
+  int mon_fd = -1;
+  if (mon_port > 0) {
+    sockaddr_in ma = srv;
+    ma.sin_port = htons((uint16_t)mon_port);
+    mon_fd = open_socket(ma, false);
+    if (mon_fd < 0) { perror("mon socket/bind"); return 1; }
+    timeval tv{0, 200000};
+    setsockopt(mon_fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+    mon_sampler = std::thread([&] {
+      rusage last{};
+      getrusage(RUSAGE_SELF, &last);
+      auto t_last = std::chrono::steady_clock::now();
+      while (!g_stop.load()) {
+        for (int i = 0; i < 10 && !g_stop.load(); i++) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        rusage cur{};
+        getrusage(RUSAGE_SELF, &cur);
+        const auto t_now = std::chrono::steady_clock::now();
+        const double dt = std::chrono::duration<double>(t_now - t_last).count();
+        auto secs = [](const timeval& a, const timeval& b) { return (double)(a.tv_sec - b.tv_sec) + 1e-6 * (double)(a.tv_usec - b.tv_usec); };
+        ucores.store(secs(cur.ru_utime, last.ru_utime) / dt);
+        kcores.store(secs(cur.ru_stime, last.ru_stime) / dt);
+        last = cur;
+        t_last = t_now;
+      }
+    });
+    mon_server = std::thread([&] {
+      struct { double ucores, kcores; } m;
+      while (!g_stop.load()) {
+        sockaddr_in who{};
+        socklen_t wl = sizeof who;
+        if (recvfrom(mon_fd, &m, sizeof m, 0, (sockaddr*)&who, &wl) < 0) continue;      // timeout: look at the stop flag
+        m.ucores = ucores.load();
+        m.kcores = kcores.load();
+        sendto(mon_fd, &m, sizeof m, 0, (const sockaddr*)&who, sizeof who);
+      }
+    });
+  }
+
   // ---- engine threads: gather the ready batches, one submit, scatter the replies; two of them take turns ----
   std::mutex submit_mu;                               // the engine has ONE submitter at a time (include/dint_b200.h)
   auto engine_thread = [&]() {
@@ -380,6 +428,9 @@ int main(int argc, char** argv) {
   fprintf(stderr, "dint_udp_server: %llu datagrams in %llu submits (%.1f per submit), %llu dropped, %llu control requests, %llu submits with malformed records\n",
           (unsigned long long)total, (unsigned long long)submits.load(), submits.load() ? (double)total / (double)submits.load() : 0.0,
           (unsigned long long)dropped, (unsigned long long)controls, (unsigned long long)bad_batches.load());
+  if (mon_sampler.joinable()) mon_sampler.join();
+  if (mon_server.joinable()) mon_server.join();
+  if (mon_fd >= 0) close(mon_fd);
   if (cluster) dint_cluster_destroy(cluster);
   if (eng) dint_destroy(eng);
   return 0;

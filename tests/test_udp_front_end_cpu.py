@@ -123,6 +123,23 @@ def test_front_end_answers_the_caladan_control_handshake(stub_dir):
     assert " 1 control requests" in log, log
 
 
+def test_front_end_answers_the_utilisation_channel(stub_dir):
+    """tatp/udp/server_shard.cc:241-274: any datagram on the monitor port is answered with {double ucores; double kcores}."""
+    import struct
+    with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s0:
+        s0.bind(("127.0.0.1", 0))
+        mon = s0.getsockname()[1]
+    srv, port = _serve(stub_dir, "lock_fasst", ("--mon-port", str(mon)))
+    try:
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as c:
+            c.settimeout(5.0)
+            c.sendto(struct.pack("<dd", 0.0, 0.0), ("127.0.0.1", mon))
+            u, k = struct.unpack("<dd", c.recv(64))
+        assert 0.0 <= u < 256.0 and 0.0 <= k < 256.0
+    finally:
+        _stop(srv)
+
+
 def test_front_end_serves_one_port_per_shard_with_gpus(stub_dir):
     """--gpus 3, smallbank: shard i listens on port + i; the port a datagram arrives on is the shard the client chose
     (smallbank/caladan/client_udp_shard.cc: primary / backups / log have their own addresses)."""
