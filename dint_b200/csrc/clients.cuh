@@ -119,6 +119,10 @@ __global__ void __launch_bounds__(256) k_clients_init(const ClientCtx c, unsigne
 __global__ void __launch_bounds__(256) k_clients_step(const ClientCtx c, const uint8_t* resp, uint8_t* req) {
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t committed = 0, vaborts = 0, rejects = 0;
+  __shared__ uint32_t s_list[256];
+  __shared__ uint32_t s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   if (id < c.n_clients) {
     CHdr h = chdr_unpack(c.hdr[id]);
     const uint8_t* a = resp + (size_t)id * 9;
@@ -155,22 +159,37 @@ __global__ void __launch_bounds__(256) k_clients_step(const ClientCtx c, const u
         if (++h.pos == h.nw) { committed = 1; fresh = true; }
         break;
     }
-    if (fresh) {
-      CRng r{c.rng[id]};
-      client_new_txn(c, id, r, h);
-      c.rng[id] = r.s;
+    if (fresh) {                                          // (new transactions are drawn below, by converged warps)
+      s_list[atomicAdd(&s_cnt, 1u)] = id;
+    } else {
+      c.hdr[id] = chdr_pack(h);
+      // ---- emit (workloads.cc emit()) ----
+      uint32_t t, lid;
+      if (h.phase == CPH_READ || h.phase == CPH_VALIDATE) { t = 0; lid = c.rk[(size_t)h.pos * c.n_clients + id]; }
+      else {
+        t = h.phase == CPH_ACQ ? 1u : h.phase == CPH_ABORT ? 2u : 3u;
+        lid = c.rk[(size_t)nth_set_bit(h.wmask, h.pos) * c.n_clients + id];
+      }
+      uint8_t* m = req + (size_t)id * 9;
+      m[0] = (uint8_t)t;
+      st_u32_unaligned(m + 1, lid);
+      st_u32_unaligned(m + 5, 0u);
     }
-    c.hdr[id] = chdr_pack(h);
-    // ---- emit (workloads.cc emit()) ----
-    uint32_t t, lid;
-    if (h.phase == CPH_READ || h.phase == CPH_VALIDATE) { t = 0; lid = c.rk[(size_t)h.pos * c.n_clients + id]; }
-    else {
-      t = h.phase == CPH_ACQ ? 1u : h.phase == CPH_ABORT ? 2u : 3u;
-      lid = c.rk[(size_t)nth_set_bit(h.wmask, h.pos) * c.n_clients + id];
-    }
-    uint8_t* m = req + (size_t)id * 9;
-    m[0] = (uint8_t)t;
-    st_u32_unaligned(m + 1, lid);
+  }
+  // ---- clients that finished a transaction (about 1 in 25 per round) start the next one: drawing 5-10 distinct keys,
+  //      sorting them and choosing the write set is ~600 instructions, so the few clients of a CTA that need it are
+  //      compacted into its first warps instead of dragging every warp through the divergent path ----
+  __syncthreads();
+  if (threadIdx.x < s_cnt) {
+    const uint32_t id2 = s_list[threadIdx.x];
+    CRng r{c.rng[id2]};
+    CHdr h2{};
+    client_new_txn(c, id2, r, h2);
+    c.rng[id2] = r.s;
+    c.hdr[id2] = chdr_pack(h2);
+    uint8_t* m = req + (size_t)id2 * 9;
+    m[0] = 0;                                              // kRead of the first key
+    st_u32_unaligned(m + 1, c.rk[id2]);
     st_u32_unaligned(m + 5, 0u);
   }
   // counters: one atomic per warp and counter

@@ -1244,36 +1244,38 @@ static void shard_mark(dint_shard_ctx* c, uint32_t slot, int which, cudaStream_t
   cudaEventRecord(c->tev[(size_t)6 * slot + which], st);
 }
 // dispatch: partition n records of this rank into the owners' inbox set (epoch ep)
-static int shard_dispatch(dint_shard_ctx* c, uint32_t slot, uint32_t ep, const void* req_dev, const uint8_t* dst_dev, uint64_t n, cudaStream_t st) {
+// (cap: the slab capacity THIS batch uses, <= the capacity the buffers were laid out for and the same on every rank: a
+//  batch much smaller than max_n then does not make the owners wade through padding)
+static int shard_dispatch(dint_shard_ctx* c, uint32_t slot, uint32_t ep, const void* req_dev, const uint8_t* dst_dev, uint64_t n, uint32_t cap, cudaStream_t st) {
   dint_engine* e = c->e;
   CU(cudaSetDevice(e->device));
   const uint32_t s = ep % c->S;
-  const size_t slab = (size_t)c->cap * e->msg;
+  const size_t slab = (size_t)cap * e->msg;
   if (ep > c->S && !c->one_stream) CU(cudaStreamWaitEvent(st, c->ev_comb[s], 0));   // my combine of batch ep - S: every owner is done with inbox set s
   shard_mark(c, slot, 0, st);
   dint_peer_ptrs in{}, sg{};
   // one request-flag word per (buffer set, source): the flag of epoch ep -- which may carry the overflow bit -- is not
   // overwritten before the owner has consumed it (the source reuses set s only after the owners' replies of ep)
   for (uint32_t o = 0; o < c->W; o++) { in.p[o] = c->inbox[s][o] + (uint64_t)c->me * slab; sg.p[o] = c->sigreq.p[o] + (uint64_t)s * 32; }
-  int rc = dint_route_dispatch(e, req_dev, dst_dev, n, c->W, c->me, c->cap, &in, &sg, ep, c->owner[s], c->tilebase[s], c->flags, st);
+  int rc = dint_route_dispatch(e, req_dev, dst_dev, n, c->W, c->me, cap, &in, &sg, ep, c->owner[s], c->tilebase[s], c->flags, st);
   if (rc) return rc;
   shard_mark(c, slot, 1, st);
   if (!c->one_stream) CU(cudaEventRecord(c->ev_disp[s], st));
   return DINT_OK;
 }
 // engine: this rank's shard serves inbox set (epoch ep); every reply tile goes to its source's return buffer
-static int shard_engine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, cudaStream_t st) {
+static int shard_engine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, uint32_t cap, cudaStream_t st) {
   dint_engine* e = c->e;
   CU(cudaSetDevice(e->device));
   const uint32_t s = ep % c->S;
-  const size_t slab = (size_t)c->cap * e->msg;
+  const size_t slab = (size_t)cap * e->msg;
   k_p2p_wait<<<1, 32, 0, st>>>(c->my_req + s * 8, c->W, ep, c->flags + 1, c->flags + 2);     // every source's slab has arrived (or one did not fit)
   shard_mark(c, slot, 2, st);
-  e->seg_tiles = c->cap / kTile;
+  e->seg_tiles = cap / kTile;
   e->pad_ok = true;
   e->skip = c->flags + 2;
   for (uint32_t r = 0; r < c->W; r++) e->seg_resp[r] = c->retbox[s][r] + (uint64_t)c->me * slab;   // my slab inside source r's return buffer
-  int rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)c->W * c->cap, nullptr, st);
+  int rc = run_device(e, (const uint8_t*)c->inbox[s][c->me], (uint64_t)c->W * cap, nullptr, st);
   e->seg_tiles = 0;
   e->pad_ok = false;
   e->skip = nullptr;
@@ -1284,17 +1286,17 @@ static int shard_engine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, cudaStrea
   return DINT_OK;
 }
 // combine: the replies of batch ep are in my return-buffer set; put them back in request order
-static int shard_combine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, void* out_dev, uint64_t n, cudaStream_t st) {
+static int shard_combine(dint_shard_ctx* c, uint32_t slot, uint32_t ep, void* out_dev, uint64_t n, uint32_t cap, cudaStream_t st) {
   dint_engine* e = c->e;
   CU(cudaSetDevice(e->device));
   const uint32_t s = ep % c->S;
-  const size_t slab = (size_t)c->cap * e->msg;
+  const size_t slab = (size_t)cap * e->msg;
   if (!c->one_stream) CU(cudaStreamWaitEvent(st, c->ev_disp[s], 0));
   k_p2p_wait<<<1, 32, 0, st>>>(c->my_rsp, c->W, ep, c->flags + 1, nullptr);
   shard_mark(c, slot, 4, st);
   dint_peer_ptrs rb{};
   for (uint32_t o = 0; o < c->W; o++) rb.p[o] = c->retbox[s][c->me] + (uint64_t)o * slab;
-  int rc = dint_route_combine(e, &rb, c->owner[s], c->tilebase[s], n, c->W, c->cap, out_dev, st);
+  int rc = dint_route_combine(e, &rb, c->owner[s], c->tilebase[s], n, c->W, cap, out_dev, st);
   if (rc) return rc;
   shard_mark(c, slot, 5, st);
   if (!c->one_stream) CU(cudaEventRecord(c->ev_comb[s], st));
@@ -1318,7 +1320,7 @@ static void shard_trace_collect(dint_shard_ctx* c, uint32_t k) {
 // G in a cluster).  Host enqueue order per batch: every rank's dispatch of j+1, every rank's engine of j, every
 // rank's combine of j (of j-1 when the ranks share one stream) -- each phase only waits for phases enqueued
 // before it, on this or another GPU, so one host thread can drive all ranks without blocking.
-struct ShardBatch { const void* req; const uint8_t* dst; void* out; uint64_t n; };
+struct ShardBatch { const void* req; const uint8_t* dst; void* out; uint64_t n; uint32_t cap = 0; };   // cap: slab records of this batch (0 = the full capacity)
 struct HostBatch { const uint8_t* req; const uint8_t* dst; uint8_t* out; uint64_t n; };
 static int shard_staging(dint_shard_ctx* c) {
   if (c->st_req[0]) return DINT_OK;
@@ -1363,13 +1365,13 @@ static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, std::
       CU(cudaEventRecord(c->ev_h2d[s], c->s_in));
       CU(cudaStreamWaitEvent(side(r), c->ev_h2d[s], 0));
       e->stats.h2d_bytes += h.n * e->msg + (h.dst ? h.n : 0);
-      b[r][j] = ShardBatch{c->st_req[s], h.dst ? c->st_dst[s] : nullptr, c->st_out[s], h.n};
+      b[r][j] = ShardBatch{c->st_req[s], h.dst ? c->st_dst[s] : nullptr, c->st_out[s], h.n, 0};
     }
-    return shard_dispatch(c, j, c->epoch + 1 + j, b[r][j].req, b[r][j].dst, b[r][j].n, side(r));
+    return shard_dispatch(c, j, c->epoch + 1 + j, b[r][j].req, b[r][j].dst, b[r][j].n, b[r][j].cap ? b[r][j].cap : c->cap, side(r));
   };
   auto combine = [&](uint32_t r, uint32_t j) -> int {
     dint_shard_ctx* c = ranks[r];
-    int rc2 = shard_combine(c, j, c->epoch + 1 + j, b[r][j].out, b[r][j].n, retS(r));
+    int rc2 = shard_combine(c, j, c->epoch + 1 + j, b[r][j].out, b[r][j].n, b[r][j].cap ? b[r][j].cap : c->cap, retS(r));
     if (rc2 || !host) return rc2;
     const HostBatch& h = (*host)[r][j];
     const uint32_t s = j % c->S, es = (c->epoch + 1 + j) % c->S;
@@ -1387,7 +1389,7 @@ static int shard_run(dint_shard_ctx* const* ranks, uint32_t R, uint32_t k, std::
       for (uint32_t r = 0; r < R; r++)
         if ((rc = dispatch(r, j + 1))) return rc;
     for (uint32_t r = 0; r < R; r++)
-      if ((rc = shard_engine(ranks[r], j, ranks[r]->epoch + 1 + j, mains[r]))) return rc;
+      if ((rc = shard_engine(ranks[r], j, ranks[r]->epoch + 1 + j, b[r][j].cap ? b[r][j].cap : ranks[r]->cap, mains[r]))) return rc;
     if (j >= lag)
       for (uint32_t r = 0; r < R; r++)
         if ((rc = combine(r, j - lag))) return rc;
@@ -1508,6 +1510,20 @@ int dint_shard_submit_many(dint_shard_ctx* c, uint32_t k, const void* const* req
 }  // extern "C"
 
 extern "C" {
+
+int dint_shard_submit_many_v(dint_shard_ctx* c, uint32_t k, const void* const* req_dev, const uint8_t* const* dst_dev, const uint64_t* n,
+                             const uint32_t* cap, void* const* out_dev, void* cuda_stream) {
+  if (!c || !req_dev || !out_dev || !n) return set_err(DINT_EINVAL, "bad argument");
+  if (k == 0) return DINT_OK;
+  std::vector<std::vector<ShardBatch>> b(1, std::vector<ShardBatch>(k));
+  for (uint32_t j = 0; j < k; j++) {
+    const uint32_t cj = cap ? cap[j] : 0;
+    if (n[j] > c->max_n || cj > c->cap || cj % kTile != 0) return set_err(DINT_EINVAL, "batch size / slab capacity (a multiple of 128, <= the capacity of dint_shard_create)");
+    b[0][j] = ShardBatch{req_dev[j], dst_dev ? dst_dev[j] : nullptr, out_dev[j], n[j], cj};
+  }
+  cudaStream_t main = (cudaStream_t)cuda_stream;
+  return shard_run(&c, 1, k, b, &main);
+}
 
 int dint_shard_submit_host(dint_shard_ctx* c, uint32_t k, const void* const* req_host, const uint8_t* const* dst_host, uint64_t n,
                            void* const* out_host) {

@@ -129,20 +129,27 @@ class ShardedEngine:
         self.p2p_ctx = ctx
         self.use_p2p = True
 
-    def _p2p_many(self, reqs, dsts=None):
-        """k equally sized batches through dint_shard_submit_many (same k and n on every rank)."""
+    def _p2p_many(self, reqs, dsts=None, caps=None):
+        """k batches through dint_shard_submit_many_v (the same k on every rank; sizes may differ).  caps: per batch the
+        slab capacity to use (the same on every rank; see cap_for) -- None = the full capacity."""
         k = len(reqs)
-        n = reqs[0].numel() // self.msg
-        assert all(r.numel() == n * self.msg and r.is_contiguous() for r in reqs) and 0 < n <= self.p2p_max_n
-        outs = [torch.empty(n * self.msg, dtype=torch.uint8, device=self.device) for _ in range(k)]
+        ns = [r.numel() // self.msg for r in reqs]
+        assert all(r.is_contiguous() for r in reqs) and all(0 < n <= self.p2p_max_n for n in ns)
+        outs = [torch.empty(n * self.msg, dtype=torch.uint8, device=self.device) for n in ns]
         a_req = (C.c_void_p * k)(*[r.data_ptr() for r in reqs])
         a_out = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
         a_dst = None if dsts is None or dsts[0] is None else (C.c_void_p * k)(*[d.data_ptr() for d in dsts])
+        a_n = (C.c_uint64 * k)(*ns)
+        a_cap = None if caps is None else (C.c_uint32 * k)(*caps)
         s = torch.cuda.current_stream(self.device).cuda_stream
-        rc = lib().dint_shard_submit_many(self.p2p_ctx, k, a_req, a_dst, n, a_out, C.c_void_p(s) if s else None)
+        rc = lib().dint_shard_submit_many_v(self.p2p_ctx, k, a_req, a_dst, a_n, a_cap, a_out, C.c_void_p(s) if s else None)
         if rc != 0:
-            raise DintError(rc, "dint_shard_submit_many")
+            raise DintError(rc, "dint_shard_submit_many_v")
         return outs
+
+    def cap_for(self, n_max):
+        """Slab capacity for a batch whose LARGEST per-rank size is n_max (every rank must pass the same value)."""
+        return min(self._cap(n_max), self._cap(self.p2p_max_n))
 
     def submit_many_host(self, reqs, outs, dsts=None):
         """k equally sized batches from / to pinned HOST tensors through dint_shard_submit_host (H2D | dispatch | engine |
@@ -233,14 +240,14 @@ class ShardedEngine:
         out = torch.empty(n * self.msg, dtype=torch.uint8, device=req.device)
         return eng.route_combine(Engine.slab_ptrs(back.data_ptr(), W, cap * self.msg), state, n, W, cap, out)
 
-    def submit_many(self, reqs, dsts=None):
+    def submit_many(self, reqs, dsts=None, caps=None):
         """A sequence of collective batches (each rank passes equally many, equally sized tensors), software
         pipelined: batch k+1 is partitioned and exchanged on a side stream while batch k runs through the
         local engine and its replies travel back on the main stream.  The engine still sees the batches in
         order, so the result equals calling submit_tensor() on each batch in turn."""
         eng, W = self.engine, self.world
         if self.use_p2p and reqs[0].numel() // self.msg <= self.p2p_max_n:
-            return self._p2p_many(reqs, dsts)
+            return self._p2p_many(reqs, dsts, caps)
         assert dsts is None, "client-chosen shards: use the p2p step or submit_tensor"
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_side"):

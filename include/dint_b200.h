@@ -197,6 +197,11 @@ int dint_shard_create(dint_engine *e, uint32_t n_shards, uint32_t rank, uint32_t
 void dint_shard_destroy(dint_shard_ctx *c);
 int dint_shard_submit_many(dint_shard_ctx *c, uint32_t k, const void *const *req_dev, const uint8_t *const *dst_dev, uint64_t n,
                            void *const *out_dev, void *cuda_stream);
+/* Batches of different sizes in one pipelined sequence (tatp / smallbank rounds): n[j] records in batch j (may differ
+ * between ranks) and cap[j] = the slab capacity batch j uses (a multiple of 128, <= the cap of dint_shard_create, THE SAME
+ * ON EVERY RANK; NULL or 0 = the full capacity): sized to the batch, the owners do not wade through padding. */
+int dint_shard_submit_many_v(dint_shard_ctx *c, uint32_t k, const void *const *req_dev, const uint8_t *const *dst_dev,
+                             const uint64_t *n, const uint32_t *cap, void *const *out_dev, void *cuda_stream);
 int dint_shard_submit_host(dint_shard_ctx *c, uint32_t k, const void *const *req_host, const uint8_t *const *dst_host, uint64_t n,
                            void *const *out_host);
 int dint_shard_flags(dint_shard_ctx *c, uint32_t out[2]);

@@ -60,6 +60,17 @@ def _worker(rank, world, port, kind, n_per_rank, mode, ret):
             want = seq.process(np.concatenate([mk(r + 100 + 10 * i) for r in range(world)]))
             ok = ok and bool(np.array_equal(outs[i].cpu().numpy(), want[lo:hi]))
         if mode.startswith('p2p'):
+            # batches of different sizes (per rank too) in one pipelined call, every batch's slabs sized to the batch
+            sizes = [n_per_rank - 1000 * i - 7 * r for i in range(5) for r in [rank]]
+            varied = [np.ascontiguousarray(mk(rank + 300 + 10 * i)).view(np.uint8).reshape(-1, msg)[:sizes[i]].reshape(-1) for i in range(5)]
+            caps = [se.cap_for(n_per_rank - 1000 * i) for i in range(5)]
+            outs = se.submit_many([torch.from_numpy(v).cuda() for v in varied], caps=caps)
+            torch.cuda.synchronize()
+            for i in range(5):
+                parts = [np.ascontiguousarray(mk(r + 300 + 10 * i)).view(np.uint8).reshape(-1, msg)[:n_per_rank - 1000 * i - 7 * r].reshape(-1) for r in range(world)]
+                want = seq.process(np.concatenate(parts))
+                lo2 = sum(p.size for p in parts[:rank])
+                ok = ok and bool(np.array_equal(outs[i].cpu().numpy(), want[lo2:lo2 + parts[rank].size]))
             ok = ok and se.check_p2p() == (0, 0)
         else:
             ok = ok and not se.check_overflow()
