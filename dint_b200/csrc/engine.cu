@@ -81,6 +81,10 @@ struct dint_engine {
   uint64_t seg_resp[kMaxShards]{};
   bool pad_ok = false;
   const uint32_t* skip = nullptr;
+  bool flag_memset = false;                  // development A/B (DINT_FLAG_MEMSET=1)
+  cudaStream_t s_clear = nullptr;
+  cudaEvent_t ev_k2[2]{}, ev_clr[2]{};
+  size_t flag_set_bytes = 0;
   uint32_t smem_classify = 0;                // K1: max(stages, ordered-replay slices)
   uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
   uint32_t* d_route = nullptr;               // multi-GPU dispatch scratch (per-tile per-shard counts)
@@ -254,7 +258,7 @@ static void fill_chunk_ctx(dint_engine* e, Ctx& c) {
   c.grp_prev = e->d_grp[cur ^ 1];
   c.flags = e->d_flags[cur];
   c.flags_prev = e->d_flags[cur ^ 1];
-  c.prev_n = e->prev_n;
+  c.prev_n = e->flag_memset ? 0u : e->prev_n;
   c.nc_cur = e->d_nc + 4 * cur;          // {listed, overflow, a writer exists, -}
   c.nc_ord = e->d_nc + 4 * (cur ^ 1);
   c.ord_pending = e->ord_pending ? 1u : 0u;
@@ -276,8 +280,18 @@ static int submit_chunk(dint_engine* e, const uint8_t* req, uint32_t n, uint8_t*
   c.resp = resp;
   c.tile0 = tile0;
   fill_chunk_ctx(e, c);
+  const int cur = (int)(e->chunk_seq & 1);
+  if (e->flag_memset) CU(cudaStreamWaitEvent(s, e->ev_clr[cur], 0));      // this flag set was zeroed after its last reader (K2, two chunks ago)
   int rc = launch_chunk(e, c, s);
   if (rc) return rc;
+  if (e->flag_memset) {
+    // K2 was the last reader of this chunk's flag set: zero the whole set on a side stream, off the critical path (it is
+    // needed again two chunks from now), instead of K1 chasing the words one by one through the previous chunk's group ids
+    CU(cudaEventRecord(e->ev_k2[cur], s));
+    CU(cudaStreamWaitEvent(e->s_clear, e->ev_k2[cur], 0));
+    CU(cudaMemsetAsync(e->d_flags[cur], 0, e->flag_set_bytes, e->s_clear));
+    CU(cudaEventRecord(e->ev_clr[cur], e->s_clear));
+  }
   e->chunk_seq++;
   e->prev_n = n;
   e->ord_pending = e->kind != DINT_LOG;
@@ -517,6 +531,8 @@ void dint_destroy(dint_engine* e) {
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
   }
+  if (e->s_clear) cudaStreamDestroy(e->s_clear);
+  for (int i = 0; i < 2; i++) { if (e->ev_k2[i]) cudaEventDestroy(e->ev_k2[i]); if (e->ev_clr[i]) cudaEventDestroy(e->ev_clr[i]); }
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -575,6 +591,13 @@ static int create_impl(dint_engine* e) {
     while (fl > 10 && (1ULL << (fl - 1)) >= groups * 2 + 2048) fl--;   // tiny group spaces need less
     c.flags_mask = (1u << fl) - 1;
     const size_t set_bytes = (size_t)4 << (fl - 3);
+    e->flag_set_bytes = set_bytes;
+    { const char* fm = getenv("DINT_FLAG_MEMSET"); e->flag_memset = fm && atoi(fm) == 1; }
+    CU(cudaStreamCreateWithFlags(&e->s_clear, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&e->ev_k2[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ev_clr[i], cudaEventDisableTiming));
+    }
     const size_t lock_bytes = (e->kind == DINT_FASST) ? (((groups + 31) / 32) * 4 + 255) / 256 * 256 : 0;
     e->hot_bytes = 2 * set_bytes + lock_bytes;
     if ((rc = dalloc(e, &e->hot_arena, e->hot_bytes))) return rc;

@@ -37,7 +37,7 @@ def num(cell):
 traffic = {}
 md = [f"# profiles/ -- capture `{R}` (B200, `--clock-control none --cache-control none`)", "",
       "Produced by `tools/round_capture.sh` under `gpurun`, summarised by `tools/prof_summary.py`:", "```"]
-md += [l.rstrip() for l in open(os.path.join(ROOT, "tools", "round_capture.sh")) if l.startswith("ncu") or l.startswith("python bench")]
+md += [l.rstrip() for l in open(os.path.join(ROOT, "tools", "round_capture.sh")) if "ncu --" in l or l.startswith("python bench")]
 md += ["```", ""]
 lp = os.path.join(G, f"launches_{R}.csv")
 if os.path.exists(lp):
