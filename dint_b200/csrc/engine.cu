@@ -71,6 +71,7 @@ struct dint_engine {
   uint32_t* d_flags[2] = {nullptr, nullptr}; // flag-nibble sets, alternating per chunk
   uint32_t* d_grp[2] = {nullptr, nullptr};   // group ids of the current / previous chunk
   uint64_t chunk_seq = 0;
+  uint32_t prev_n = 0;                       // requests of the previous chunk whose flags are still set
   bool ord_pending = false;                  // the previous chunk's listed requests await their replay
   uint8_t* ord_resp = nullptr;               //   ... and live in this reply array
   const uint8_t* ord_req = nullptr;          //   ... their request bytes in this one
@@ -80,9 +81,6 @@ struct dint_engine {
   uint64_t seg_resp[kMaxShards]{};
   bool pad_ok = false;
   const uint32_t* skip = nullptr;
-  cudaStream_t s_clear = nullptr;            // zeroes a flag set after its chunk's K2
-  cudaEvent_t ev_k2[2]{}, ev_clr[2]{};
-  size_t flag_set_bytes = 0;
   uint32_t smem_classify = 0;                // K1: max(stages, ordered-replay slices)
   uint32_t* d_nc = nullptr;                  // [2 chunks][2]: listed / overflow counters
   uint32_t* d_route = nullptr;               // multi-GPU dispatch scratch (per-tile per-shard counts)
@@ -177,7 +175,8 @@ template <int KIND, bool HAS_LOG>
 static int launch_chunk_t(dint_engine* e, const Ctx& c, cudaStream_t s) {
   {
     ProfScope ps(e, s, KT_CLASSIFY);
-    int want = (int)c.n_tiles;
+    int want = (int)c.n_tiles, clr = (int)((c.prev_n + 4 * kTile - 1) / (4 * kTile));
+    if (clr > want) want = clr;
     int grid = (want < e->grid_classify && !c.ord_pending) ? want : e->grid_classify;
     if (c.n == 0 && e->sms > 0 && grid > 8 * e->sms) grid = 8 * e->sms;     // a flush launch only replays: 32 warps per SM are plenty
     CU(launch_ex(e, k_classify<KIND, HAS_LOG>, grid, kTile, e->smem_classify, s, false, c));
@@ -252,7 +251,10 @@ static int grids_for(dint_engine* e) {
 static void fill_chunk_ctx(dint_engine* e, Ctx& c) {
   const int cur = (int)(e->chunk_seq & 1);
   c.grp = e->d_grp[cur];
+  c.grp_prev = e->d_grp[cur ^ 1];
   c.flags = e->d_flags[cur];
+  c.flags_prev = e->d_flags[cur ^ 1];
+  c.prev_n = e->prev_n;
   c.nc_cur = e->d_nc + 4 * cur;          // {listed, overflow, a writer exists, -}
   c.nc_ord = e->d_nc + 4 * (cur ^ 1);
   c.ord_pending = e->ord_pending ? 1u : 0u;
@@ -274,18 +276,10 @@ static int submit_chunk(dint_engine* e, const uint8_t* req, uint32_t n, uint8_t*
   c.resp = resp;
   c.tile0 = tile0;
   fill_chunk_ctx(e, c);
-  const int cur = (int)(e->chunk_seq & 1);
-  CU(cudaStreamWaitEvent(s, e->ev_clr[cur], 0));      // this flag set was zeroed after its last reader (K2, two chunks ago)
   int rc = launch_chunk(e, c, s);
   if (rc) return rc;
-  // K2 was the last reader of this chunk's flag set: zero the whole set on a side stream (it is needed again two chunks
-  // from now).  Round 1 had K1 chase the words one by one through the previous chunk's group ids: K1 29.5 -> 25.7 us,
-  // store GET +3 %, lock_fasst unchanged end to end (profiles/r02_variants.md)
-  CU(cudaEventRecord(e->ev_k2[cur], s));
-  CU(cudaStreamWaitEvent(e->s_clear, e->ev_k2[cur], 0));
-  CU(cudaMemsetAsync(e->d_flags[cur], 0, e->flag_set_bytes, e->s_clear));
-  CU(cudaEventRecord(e->ev_clr[cur], e->s_clear));
   e->chunk_seq++;
+  e->prev_n = n;
   e->ord_pending = e->kind != DINT_LOG;
   e->ord_resp = resp;
   e->ord_req = req;
@@ -304,6 +298,8 @@ static int flush_ordered(dint_engine* e, cudaStream_t s) {
   c.req = nullptr;
   c.resp = nullptr;
   fill_chunk_ctx(e, c);
+  c.prev_n = 0;                  // replay only: that chunk's flags are retired by the NEXT chunk's K1 as usual (next to its tile
+                                 // loads), not by this launch, which a caller is waiting for
   int rc = launch_chunk(e, c, s);
   if (rc) return rc;
   e->ord_pending = false;
@@ -521,8 +517,6 @@ void dint_destroy(dint_engine* e) {
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
   }
-  if (e->s_clear) cudaStreamDestroy(e->s_clear);
-  for (int i = 0; i < 2; i++) { if (e->ev_k2[i]) cudaEventDestroy(e->ev_k2[i]); if (e->ev_clr[i]) cudaEventDestroy(e->ev_clr[i]); }
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -581,12 +575,6 @@ static int create_impl(dint_engine* e) {
     while (fl > 10 && (1ULL << (fl - 1)) >= groups * 2 + 2048) fl--;   // tiny group spaces need less
     c.flags_mask = (1u << fl) - 1;
     const size_t set_bytes = (size_t)4 << (fl - 3);
-    e->flag_set_bytes = set_bytes;
-    CU(cudaStreamCreateWithFlags(&e->s_clear, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-      CU(cudaEventCreateWithFlags(&e->ev_k2[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&e->ev_clr[i], cudaEventDisableTiming));
-    }
     const size_t lock_bytes = (e->kind == DINT_FASST) ? (((groups + 31) / 32) * 4 + 255) / 256 * 256 : 0;
     e->hot_bytes = 2 * set_bytes + lock_bytes;
     if ((rc = dalloc(e, &e->hot_arena, e->hot_bytes))) return rc;
@@ -1502,6 +1490,7 @@ int dint_shard_recover(dint_shard_ctx* c, uint32_t k_last, uint32_t* first_unser
   CU(cudaMemset(c->flags, 0, 4 * sizeof(uint32_t)));
   // the skipped launches changed nothing on the device, but the host-side chunk bookkeeping advanced: start clean
   e->ord_pending = false;
+  e->prev_n = 0;
   CU(cudaMemset(e->d_nc, 0, 8 * sizeof(uint32_t)));
   CU(cudaMemset(e->d_flags[0], 0, (size_t)((char*)e->d_flags[1] - (char*)e->d_flags[0]) * 2));
   CU(cudaDeviceSynchronize());

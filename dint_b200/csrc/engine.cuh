@@ -12,7 +12,7 @@
 //                 nibble holds R (an RA exists), WA, WL and W2 (two or more writers of one class).
 //                 The flag array is hash-folded to 2^25 nibbles (16 MB), so it stays in the 126 MB
 //                 L2; folding can only add conflicts, never hide one.  Two flag sets alternate
-//                 between chunks; a set is zeroed whole, by a memset on a side stream, once its chunk's K2 has run.
+//                 between chunks: K1 of chunk k also zeroes the words chunk k-1 touched.
 //   K2 apply    : a request is SOLO when nothing else in the chunk can interact with it
 //                 (RA: WA clear; WA: R and W2 clear; WL: W2 clear).  Solo requests are applied
 //                 directly, one thread each, against the HBM-resident state and their tile is
@@ -94,8 +94,10 @@ struct Ctx {
   uint32_t n_tiles;
   // conflict detection
   uint32_t* grp;           // [chunk] group id per request of THIS chunk (0xffffffff: none)
-  uint32_t* flags;         // this chunk's flag set: 2^flags_log2 nibbles (two sets alternate; a set is zeroed by a memset on a
-                           // side stream after its last reader, K2 -- two chunks before it is used again)
+  const uint32_t* grp_prev;  // [prev_n] group ids of the previous chunk (its flags are cleared by this K1)
+  uint32_t prev_n;
+  uint32_t* flags;         // this chunk's flag set: 2^flags_log2 nibbles
+  uint32_t* flags_prev;    // the previous chunk's flag set
   uint32_t flags_mask;     // 2^flags_log2 - 1
   uint32_t* clist;         // [n_tiles][kTile] indices of listed requests, tile-segmented
   uint32_t* ccnt;          // [n_tiles] listed requests per tile

@@ -243,7 +243,7 @@ template <int KIND> struct OrdSlice {
 template <int KIND> DINT_D void ordered_buckets(const Ctx& c, uint8_t* scratch);
 
 // ---------------------------------------------------------------------------------------------------
-// K1 classify (+ replays the previous chunk's listed requests)
+// K1 classify (+ clears the flag words of the previous chunk)
 // ---------------------------------------------------------------------------------------------------
 template <int KIND, bool HAS_LOG>
 __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
@@ -272,6 +272,21 @@ __global__ void __launch_bounds__(kTile) k_classify(const Ctx c) {
   const TileIter it = tile_iter(c.n_tiles);
   if (threadIdx.x == 0)
     for (uint32_t i = 0; i < NS && i < it.n_my; i++) issue_tile_load<W::MSG>(c, smem, full, it, i);
+
+  // retire the previous chunk's flags: every word it touched is zeroed (all of that set's nibbles
+  // were written by that chunk, so whole-word stores are exact).  Loads are batched four deep so that
+  // the kernel start pays one memory latency, not one per element.
+  for (uint32_t i = blockIdx.x * kTile + threadIdx.x; i < c.prev_n; i += 4 * gridDim.x * kTile) {
+    uint32_t g[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t j = i + u * gridDim.x * kTile;
+      g[u] = j < c.prev_n ? __ldcg(&c.grp_prev[j]) : kNoGroup;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (g[u] != kNoGroup) c.flags_prev[flag_word(c, g[u])] = 0;
+  }
 
   // A writer needs the OLD nibble to learn whether it is the second writer of its class (-> W2).  Waiting
   // for the atomic's return value would expose one L2 round trip per tile; the check is deferred by one

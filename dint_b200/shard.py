@@ -139,9 +139,14 @@ class ShardedEngine:
         a_req = (C.c_void_p * k)(*[r.data_ptr() for r in reqs])
         a_out = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
         a_dst = None if dsts is None or dsts[0] is None else (C.c_void_p * k)(*[d.data_ptr() for d in dsts])
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if caps is None and all(n == ns[0] for n in ns):      # equally sized batches at the full slab capacity
+            rc = lib().dint_shard_submit_many(self.p2p_ctx, k, a_req, a_dst, ns[0], a_out, C.c_void_p(s) if s else None)
+            if rc != 0:
+                raise DintError(rc, "dint_shard_submit_many")
+            return outs
         a_n = (C.c_uint64 * k)(*ns)
         a_cap = None if caps is None else (C.c_uint32 * k)(*caps)
-        s = torch.cuda.current_stream(self.device).cuda_stream
         rc = lib().dint_shard_submit_many_v(self.p2p_ctx, k, a_req, a_dst, a_n, a_cap, a_out, C.c_void_p(s) if s else None)
         if rc != 0:
             raise DintError(rc, "dint_shard_submit_many_v")
