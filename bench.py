@@ -22,8 +22,6 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # one hardware queue per stream: the multi-GPU step polls flags in
-                                                               # kernels, and streams that SHARE a queue would wait behind them
 import subprocess
 import sys
 import threading

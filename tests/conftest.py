@@ -1,7 +1,6 @@
 import os
 import sys
 
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # (see bench.py: flag-polling kernels and shared hardware queues)
 
 import pytest
 
