@@ -1078,10 +1078,12 @@ def main_reference(args, rank, world):
     rows = {}
     if kind == "reference":                          # scaling rows: 1 thread, 8 threads (the reference's own setting), all cores
         for th in sorted({1, min(8, cores), cores}):
-            rep = max(1, int(3.0 * 40e6 * min(th, 16) / n))
+            rep = max(1, min(400, int(2.0 * one(th, 2) / n)))          # about two seconds per repeat
             rates = [one(th, rep) for _ in range(3)]
             rows[str(th)] = {"req_per_s_median": sorted(rates)[1], "req_per_s_min": min(rates), "req_per_s_max": max(rates), "repeat": rep}
-    rep_all = max(1, int(2.0 * 40e6 * min(cores, 16) / n))
+    # a step = `rep_all` passes over the sample, sized from a short calibration run to take about three seconds whatever the box
+    cal = one(cores if kind == "reference" else 1, 4)
+    rep_all = max(1, min(400, int(3.0 * cal / n)))
     times, rates = [], []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()

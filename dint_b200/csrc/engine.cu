@@ -428,7 +428,7 @@ struct HostSlices {
 template <int KIND>
 static int route_dispatch_t(dint_engine* e, const RouteArgs& a, cudaStream_t s) {
   using RT = RTile<Wire<KIND>::MSG>;
-  // scratch: [0] finished-CTA counter, [1] tile tickets, [4..12] totals + valid word, then the look-back descriptors
+  // scratch: [0] finished-CTA counter, [1] the dispatch tile ticket, [4..12] totals + valid word, then the look-back descriptors
   if (!e->d_route2 || a.n_tiles > e->route_desc_tiles) {
     if (e->d_route2) { CU(cudaStreamSynchronize(s)); CU(cudaFree(e->d_route2)); e->d_route2 = nullptr; }
     e->route_desc_tiles = a.n_tiles + a.n_tiles / 2 + 64;

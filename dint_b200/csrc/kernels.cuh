@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(kThreads) k_exact_scatter(const uint8_t* req, 
   }
 }
 // ---- exchange over NVLink peer memory: epoch flags ---------------------------------------------------------
-// Every rank owns a symmetric buffer {inbox[world][cap], outbox[world][cap], signals} that its peers map
-// (torch symmetric memory / CUDA IPC).  The dispatch kernel (route.cuh) stores each record straight into the
-// OWNER's inbox slab for this source, the combine kernel loads each reply straight from the owner's outbox.
+// Every rank owns a buffer {inbox[world][cap], return buffer[world][cap], signals} that its peers map (torch symmetric
+// memory / CUDA IPC / peer access).  The dispatch kernel (route.cuh) stores each record straight into the OWNER's inbox
+// slab for this source, the owner's k_apply stores each reply tile straight into the SOURCE's return buffer.
 // Ordering across GPUs: epoch counters written with system-scope release stores after the data and polled
 // with acquire loads.
 struct PeerPtrs { uint64_t p[kMaxShards]; };

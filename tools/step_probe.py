@@ -22,7 +22,7 @@ dist.init_process_group("nccl")
 W, n, msg = 2, 1 << 20, 9
 cap = (int(n / W * 1.02) + 8 * int((n / W) ** 0.5) + 64 + 15) // 16 * 16
 region = (W * cap * msg + 255) // 256 * 256
-sym = symm_mem.empty(2 * region, dtype=torch.uint8, device=dev)          # [inbox | outbox]
+sym = symm_mem.empty(2 * region, dtype=torch.uint8, device=dev)          # [inbox | reply buffer]
 hdl = symm_mem.rendezvous(sym, group=dist.group.WORLD.group_name)
 sym.zero_(); torch.cuda.synchronize(); hdl.barrier()
 ptrs = [int(p) for p in hdl.buffer_ptrs]
