@@ -77,7 +77,7 @@ struct Worker {
   std::vector<iovec> iov;
   std::vector<sockaddr_in> peer;
   std::vector<int> from;                // fd index of every datagram
-  int n = 0;
+  int n = 0, dirty = 0;                 // dirty: headers the kernel wrote into during the last receive
   enum State { FILLING, READY, IN_FLIGHT, DONE } state = FILLING;   // guarded by the shared mutex
   uint64_t datagrams = 0, dropped = 0, controls = 0;
   std::thread th;
@@ -188,6 +188,11 @@ int main(int argc, char** argv) {
     x->iov.resize(batch_max);
     x->peer.resize(batch_max);
     x->from.resize(batch_max);
+    for (unsigned q = 0; q < batch_max; q++) {         // datagram q always lands in slot q of the batch buffer
+      x->iov[q] = {x->buf.data() + (size_t)q * msg, msg};
+      x->hdr[q].msg_hdr = {&x->peer[q], sizeof(sockaddr_in), &x->iov[q], 1, nullptr, 0, 0};
+      x->hdr[q].msg_len = 0;
+    }
     return x;
   };
 
@@ -224,6 +229,8 @@ int main(int argc, char** argv) {
     std::vector<pollfd> pfd(x.fds.size());
     while (!g_stop.load()) {
       // ---- receive (replaces net_recv): wait for the first datagram, then drain what has queued up ----
+      for (int i = 0; i < x.dirty; i++) { x.hdr[i].msg_hdr.msg_namelen = sizeof(sockaddr_in); x.hdr[i].msg_len = 0; }   // what the last batch touched
+      x.dirty = 0;
       for (size_t i = 0; i < x.fds.size(); i++) pfd[i] = {x.fds[i], POLLIN, 0};
       if (poll(pfd.data(), (nfds_t)pfd.size(), 200) <= 0) continue;     // timeout: look at the stop flag again
       int n = 0;
@@ -231,17 +238,13 @@ int main(int argc, char** argv) {
       for (;;) {
         bool any = false;
         for (size_t i = 0; i < x.fds.size() && (unsigned)n < batch_max; i++) {
-          for (unsigned q = (unsigned)n; q < batch_max; q++) {
-            x.iov[q] = {x.buf.data() + (size_t)q * msg, msg};
-            x.hdr[q].msg_hdr = {&x.peer[q], sizeof(sockaddr_in), &x.iov[q], 1, nullptr, 0, 0};
-            x.hdr[q].msg_len = 0;
-          }
           const int m = recvmmsg(x.fds[i], x.hdr.data() + n, batch_max - (unsigned)n, MSG_DONTWAIT, nullptr);
           if (m > 0) { for (int q = 0; q < m; q++) x.from[n + q] = (int)i; n += m; any = true; }
         }
         if ((unsigned)n >= batch_max) break;
         if (!any && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(linger_us)) break;   // a short linger so that load builds batches
       }
+      x.dirty = n;
       int keep = 0;                                   // a datagram of the wrong size cannot be a request of this server
       for (int i = 0; i < n; i++) {
         if (x.hdr[i].msg_len != msg) {
@@ -272,10 +275,7 @@ int main(int argc, char** argv) {
         x.state = Worker::FILLING;
       }
       // ---- send (replaces net_send): every reply goes back to the address, and from the socket, its request came to ----
-      for (int i = 0; i < keep; i++) {
-        x.iov[i] = {x.buf.data() + (size_t)i * msg, msg};
-        x.hdr[i].msg_hdr = {&x.peer[i], sizeof(sockaddr_in), &x.iov[i], 1, nullptr, 0, 0};
-      }
+      // (the headers still describe slot i <-> peer[i]; the kernel only touched msg_namelen / msg_len of the first n)
       for (int sent = 0; sent < keep;) {
         int run = 1;
         while (sent + run < keep && x.from[sent + run] == x.from[sent]) run++;
